@@ -1,0 +1,104 @@
+"""ctypes binding of libsfvos.so (include/sfvos.h).  No torch types cross this boundary: only raw device
+pointers, sizes and the CUDA stream handle.  There is no CPU fallback: if the library is missing or the device
+is not sm_100 every op raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsfvos.so")
+
+F32, BF16 = 0, 1
+i64, i32, f32, f64, vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+
+
+class ConvParams(ctypes.Structure):
+    _fields_ = [("x", vp), ("B", i64), ("T", i64), ("H", i64), ("W", i64), ("C", i64), ("x_cstride", i64),
+                ("x_hstride", i64), ("x_tstride", i64), ("x_bstride", i64),
+                ("w", vp), ("Cp", i64), ("N", i64), ("kt", i64), ("kh", i64), ("kw", i64),
+                ("pad_t", i64), ("pad_h", i64), ("pad_w", i64), ("To", i64),
+                ("y", vp), ("y_dtype", i32), ("relu", i32), ("y_cstride", i64),
+                ("scale", vp), ("shift", vp), ("sum", vp), ("sumsq", vp),
+                ("accumulate", i32), ("reserved", i32),
+                ("OH", i64), ("OW", i64), ("oy_mul", i64), ("oy_off", i64), ("ox_mul", i64), ("ox_off", i64)]
+
+
+class WgradParams(ctypes.Structure):
+    _fields_ = [("x", vp), ("B", i64), ("T", i64), ("H", i64), ("W", i64), ("C", i64), ("x_cstride", i64),
+                ("x_hstride", i64), ("x_tstride", i64), ("x_bstride", i64),
+                ("dy", vp), ("To", i64), ("N", i64), ("dy_cstride", i64),
+                ("dy_hstride", i64), ("dy_tstride", i64), ("dy_bstride", i64),
+                ("kt", i64), ("kh", i64), ("kw", i64), ("pad_t", i64), ("pad_h", i64), ("pad_w", i64),
+                ("dw", vp)]
+
+
+class RoiParams(ctypes.Structure):
+    _fields_ = [("feat", vp * 4), ("dfeat", vp * 4), ("H", i64 * 4), ("W", i64 * 4), ("scale", f32 * 4),
+                ("n_levels", i32), ("feat_dtype", i32), ("N", i64), ("C", i64), ("cstride", i64),
+                ("rois", vp), ("levels", vp), ("K", i64), ("P", i32), ("sampling_ratio", i32),
+                ("out", vp), ("out_dtype", i32), ("out_nchw", i32)]
+
+
+_SIGS = {
+    "sfvos_version": [],
+    "sfvos_device_check": [],
+    "sfvos_conv_umma": [ctypes.POINTER(ConvParams), vp],
+    "sfvos_conv_simt": [ctypes.POINTER(ConvParams), vp],
+    "sfvos_wgrad_umma": [ctypes.POINTER(WgradParams), vp],
+    "sfvos_wgrad_simt": [ctypes.POINTER(WgradParams), vp],
+    "sfvos_pack_weights": [vp, vp, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, vp],
+    "sfvos_unpack_wgrad": [vp, vp, i32, i64, i64, i64, i64, i64, i64, i64, vp],
+    "sfvos_channel_stats": [vp, i64, i64, i64, vp, vp, vp],
+    "sfvos_bn_finalize": [vp, vp, f64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp, vp, i64, vp],
+    "sfvos_bn_fold_eval": [vp, vp, vp, vp, vp, f64, vp, vp, i64, vp],
+    "sfvos_affine_act": [vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, i64, vp],
+    "sfvos_bn_bwd_reduce": [vp, i32, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, vp, vp],
+    "sfvos_bn_bwd_apply": [vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, i32, i64, vp, vp, vp],
+    "sfvos_relu_bwd": [vp, i32, i64, vp, i32, i64, vp, i32, i64, vp, i64, i64, vp],
+    "sfvos_nchw_to_nhwc": [vp, i64, vp, i32, i64, i64, i64, i64, vp],
+    "sfvos_nhwc_to_nchw": [vp, i32, i64, vp, i64, i64, i64, vp],
+    "sfvos_roi_levels": [vp, i64, i32, i32, vp, vp],
+    "sfvos_roi_align_fwd": [ctypes.POINTER(RoiParams), vp],
+    "sfvos_roi_align_bwd": [ctypes.POINTER(RoiParams), vp],
+    "sfvos_mask_targets": [vp, i64, i64, i64, vp, i64, i32, vp, vp],
+    "sfvos_mask_logits_fwd": [vp, i32, vp, vp, vp, i64, i64, i64, i32, vp],
+    "sfvos_mask_bce_fwd": [vp, vp, vp, vp, i64, i64, i32, vp],
+    "sfvos_mask_logits_bce_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i64, i64, i64, i32, vp],
+    "sfvos_mask_probs": [vp, vp, vp, i64, i64, i32, vp],
+    "sfvos_axpby": [vp, vp, f32, f32, i64, vp],
+}
+
+EXPORTED = sorted(list(_SIGS) + ["sfvos_last_error"])
+_lib = None
+
+
+def load():
+    """Load libsfvos.so (built in-tree by build.py).  Raises if it is missing -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python {os.path.join(HERE, 'build.py')}` "
+                           "(the CUDA extension is mandatory; there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    lib.sfvos_last_error.argtypes = []
+    lib.sfvos_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"libsfvos error {rc}: {load().sfvos_last_error().decode()}")
+
+
+LAUNCHES = 0   # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+
+
+def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,329 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a): fprop and dgrad of every Conv3d of SlowFastLayers
+// (code/helpers/model.py:72-76,83-90) and of the mask-head Conv2d / ConvTranspose2d
+// (TV/models/detection/mask_rcnn.py:284-296,342-344).
+//
+// GEMM view: D[M,N] = A[M,K] * B[K,N] with M = output pixels, N = output channels, K = taps * channels.
+//   * one M tile = TW x TH output pixels of one (clip, frame) (<=128 rows; the rest of the 128 UMMA rows are
+//     never stored); N is a single tile (<=256) so an activation tile is fetched once for all output channels
+//   * A is never materialised: for every tap (a,i,j) and 64-channel chunk the producer issues ONE 5-D TMA box
+//     {64ch, TW, TH, 1, 1} at the shifted coordinate; out-of-range rows/columns/frames are zero-filled by TMA,
+//     which is the convolution padding.  The box lands as 128-byte rows with the 128B swizzle = the canonical
+//     K-major UMMA operand layout.
+//   * B = pre-packed bf16 weights [N][taps*Cp], loaded as a 2-D TMA box {64, N} per K step
+//   * fp32 accumulators live in TMEM, double buffered (2*N columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1; persistent CTAs, one per SM
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator,
+//     warps 4..7 = epilogue (TMEM -> registers -> per-channel affine/ReLU -> global), which also reduces the
+//     per-channel sum / sum-of-squares of the raw fp32 accumulators for train-mode BatchNorm.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB per stage
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 128;
+
+struct ConvArgs {
+    int B, To, H, W;
+    int TW, TH, tiles_w, tiles_h, ntiles;
+    int N, kt, kh, kw, pad_t, pad_h, pad_w, cchunks, stages;
+    uint32_t idesc, tmem_cols, a_tx_bytes;
+    void* y;
+    int y_bf16, relu, accumulate;
+    long long y_cstride;
+    const float* scale;
+    const float* shift;
+    float* sum;
+    float* sumsq;
+    int OH, OW, oy_mul, oy_off, ox_mul, ox_off;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = a.N * BK * 2;
+    const int stage_bytes = A_BYTES + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + a.stages;
+    uint64_t* tmem_full = empty_bar + a.stages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
+    float* s_shift = s_scale + 256;
+    float* s_sum = s_shift + 256;
+    float* s_sq = s_sum + 256;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], EPI_THREADS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
+    for (int i = threadIdx.x; i < 256; i += NUM_THREADS) {
+        s_scale[i] = (a.scale && i < a.N) ? a.scale[i] : 1.0f;
+        s_shift[i] = (a.shift && i < a.N) ? a.shift[i] : 0.0f;
+        s_sum[i] = 0.0f;
+        s_sq[i] = 0.0f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ksteps = a.kt * a.kh * a.kw * a.cchunks;
+    const int tiles_per_frame = a.tiles_w * a.tiles_h;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ------------------------------ TMA producer ------------------------------
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const int frame = tile / tiles_per_frame;
+                const int rem = tile - frame * tiles_per_frame;
+                const int th_i = rem / a.tiles_w;
+                const int tw_i = rem - th_i * a.tiles_w;
+                const int b = frame / a.To;
+                const int t = frame - b * a.To;
+                const int h0 = th_i * a.TH, w0 = tw_i * a.TW;
+                int kcol = 0;
+                for (int ta = 0; ta < a.kt; ++ta)
+                    for (int ti = 0; ti < a.kh; ++ti)
+                        for (int tj = 0; tj < a.kw; ++tj)
+                            for (int cc = 0; cc < a.cchunks; ++cc) {
+                                mbar_wait(&empty_bar[stage], phase ^ 1);
+                                uint8_t* sa = smem + stage * stage_bytes;
+                                mbar_arrive_expect_tx(&full_bar[stage], a.a_tx_bytes + b_bytes);
+                                tma_load_5d(sa, &tmap_x, &full_bar[stage], cc * BK, w0 + tj - a.pad_w,
+                                            h0 + ti - a.pad_h, t + ta - a.pad_t, b);
+                                tma_load_2d(sa + A_BYTES, &tmap_w, &full_bar[stage], kcol, 0);
+                                kcol += BK;
+                                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                            }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ------------------------------ MMA issuer ------------------------------
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * a.N;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
+                        const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
+                        umma_bf16(d_tmem, adesc, bdesc, a.idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);      // smem slot is free once these MMAs have read it
+                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ------------------------------ epilogue ------------------------------
+        const int q = warp - EPI_WARP0;                  // TMEM lane quarter == warp id % 4
+        const int r = q * 32 + lane;                     // accumulator row = pixel within the tile
+        const int hl = r / a.TW;
+        const int wl = r - hl * a.TW;
+        const bool do_stats = (a.sum != nullptr);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const int frame = tile / tiles_per_frame;
+            const int rem = tile - frame * tiles_per_frame;
+            const int th_i = rem / a.tiles_w;
+            const int tw_i = rem - th_i * a.tiles_w;
+            const int h = th_i * a.TH + hl, w = tw_i * a.TW + wl;
+            const bool valid = (hl < a.TH) && (h < a.H) && (w < a.W);
+            const long long pix = ((long long)frame * a.OH + (h * a.oy_mul + a.oy_off)) * a.OW + (w * a.ox_mul + a.ox_off);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * a.N;
+            for (int c0 = 0; c0 < a.N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_addr + c0, v);
+                tmem_ld_wait();
+                if (do_stats) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.0f;
+                    float s = warp_transpose_reduce32(f, lane);
+                    atomicAdd(&s_sum[c0 + lane], s);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { float x = valid ? __uint_as_float(v[j]) : 0.0f; f[j] = x * x; }
+                    s = warp_transpose_reduce32(f, lane);
+                    atomicAdd(&s_sq[c0 + lane], s);
+                }
+                if (valid) {
+                    float o[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
+                        o[j] = a.relu ? fmaxf(x, 0.0f) : x;
+                    }
+                    if (a.y_bf16) {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            u.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
+                            u.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+                            u.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+                            u.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+                            dst[j] = u;
+                        }
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + pix * a.y_cstride + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 u = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                            if (a.accumulate) {
+                                float4 old = dst[j];
+                                u.x += old.x; u.y += old.y; u.z += old.z; u.w += old.w;
+                            }
+                            dst[j] = u;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (do_stats) {
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.N; i += EPI_THREADS) {
+                atomicAdd(&a.sum[i], s_sum[i]);
+                atomicAdd(&a.sumsq[i], s_sq[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+void choose_tile(int H, int W, int* TW, int* TH) {
+    double best = -1.0;
+    int bw = 1, bh = 1;
+    for (int tw = 1; tw <= W && tw <= BM; ++tw) {
+        int th = BM / tw;
+        if (th > H) th = H;
+        if (th < 1) continue;
+        long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+        double eff = (double)H * W / (double)(tiles * BM);
+        if (eff > best + 1e-9 || (fabs(eff - best) <= 1e-9 && tw > bw)) {
+            best = eff; bw = tw; bh = th;
+        }
+    }
+    *TW = bw; *TH = bh;
+}
+
+}  // namespace
+
+extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    SF_CHECK(p != nullptr, "conv_umma: null params");
+    SF_CHECK(p->N >= 32 && p->N <= 256 && p->N % 32 == 0, "conv_umma: N=%lld must be a multiple of 32 in [32,256]", (long long)p->N);
+    SF_CHECK(p->Cp % BK == 0 && p->Cp >= p->C, "conv_umma: Cp=%lld must be a multiple of 64 and >= C=%lld", (long long)p->Cp, (long long)p->C);
+    SF_CHECK(p->C % 8 == 0 && p->x_cstride % 8 == 0, "conv_umma: C and x_cstride must be multiples of 8");
+    SF_CHECK(p->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0, "conv_umma: y must be 16-byte aligned with cstride %% 8 == 0");
+    SF_CHECK(!(p->accumulate && p->y_dtype != SFVOS_F32), "conv_umma: accumulate needs an f32 output");
+    SF_CHECK((p->sum == nullptr) == (p->sumsq == nullptr), "conv_umma: sum and sumsq must be given together");
+    SF_CHECK(p->B > 0 && p->To > 0 && p->H > 0 && p->W > 0 && p->T > 0, "conv_umma: empty tensor");
+    SF_CHECK(p->B * p->To * p->H * p->W < (1LL << 31), "conv_umma: too many output pixels");
+    int rc = sfvos_device_check();
+    if (rc) return rc;
+
+    ConvArgs a;
+    a.B = (int)p->B; a.To = (int)p->To; a.H = (int)p->H; a.W = (int)p->W;
+    choose_tile(a.H, a.W, &a.TW, &a.TH);
+    a.tiles_w = (a.W + a.TW - 1) / a.TW;
+    a.tiles_h = (a.H + a.TH - 1) / a.TH;
+    a.ntiles = a.B * a.To * a.tiles_w * a.tiles_h;
+    a.N = (int)p->N;
+    a.kt = (int)p->kt; a.kh = (int)p->kh; a.kw = (int)p->kw;
+    a.pad_t = (int)p->pad_t; a.pad_h = (int)p->pad_h; a.pad_w = (int)p->pad_w;
+    a.cchunks = (int)(p->Cp / BK);
+    const int stage_bytes = A_BYTES + a.N * BK * 2;
+    const int smem_budget = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, scale/shift, stats*/;
+    a.stages = smem_budget / stage_bytes;
+    if (a.stages > 8) a.stages = 8;
+    SF_CHECK(a.stages >= 2, "conv_umma: not enough shared memory for 2 stages");
+    a.idesc = umma_idesc_bf16(BM, a.N, 0, 0);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * a.N)) cols <<= 1;
+    a.tmem_cols = cols;
+    a.a_tx_bytes = (uint32_t)(a.TW * a.TH * BK * 2);
+    a.y = p->y; a.y_bf16 = (p->y_dtype == SFVOS_BF16); a.relu = p->relu; a.accumulate = p->accumulate;
+    a.y_cstride = p->y_cstride;
+    a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
+    a.OH = (int)(p->OH ? p->OH : p->H); a.OW = (int)(p->OW ? p->OW : p->W);
+    a.oy_mul = (int)(p->oy_mul ? p->oy_mul : 1); a.ox_mul = (int)(p->ox_mul ? p->ox_mul : 1);
+    a.oy_off = (int)p->oy_off; a.ox_off = (int)p->ox_off;
+
+    CUtensorMap tx, tw;
+    {
+        uint64_t dims[5] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->T, (uint64_t)p->B};
+        const uint64_t cs = (uint64_t)p->x_cstride;
+        const uint64_t hs = p->x_hstride ? (uint64_t)p->x_hstride : cs * p->W;
+        const uint64_t ts = p->x_tstride ? (uint64_t)p->x_tstride : hs * p->H;
+        const uint64_t bs = p->x_bstride ? (uint64_t)p->x_bstride : ts * p->T;
+        uint64_t str[4] = {cs * 2, hs * 2, ts * 2, bs * 2};
+        uint32_t box[5] = {BK, (uint32_t)a.TW, (uint32_t)a.TH, 1, 1};
+        rc = sfvos_make_tmap(&tx, p->x, 5, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t ktot = (uint64_t)(p->kt * p->kh * p->kw * p->Cp);
+        uint64_t dims[2] = {ktot, (uint64_t)p->N};
+        uint64_t str[1] = {ktot * 2};
+        uint32_t box[2] = {BK, (uint32_t)p->N};
+        rc = sfvos_make_tmap(&tw, p->w, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    const int smem_bytes = a.stages * stage_bytes + 1024 + 8192;
+    SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int grid = sfvos_num_sms();
+    if (grid > a.ntiles) grid = a.ntiles;
+    conv_umma_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}

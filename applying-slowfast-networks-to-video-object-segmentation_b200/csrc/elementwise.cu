@@ -1,0 +1,513 @@
+// HBM-bound kernels around the GEMMs: weight packing, BatchNorm statistics / finalize / apply / backward,
+// ReLU backward, NCHW <-> channels-last layout conversion.  All are coalesced along the contiguous channel axis
+// with 16/32-byte vector accesses; per-channel reductions use registers -> shared memory -> one atomic per
+// channel per CTA.
+#include "common.cuh"
+
+namespace {
+
+// ---- 8-channel vector access helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ---- weight packing ---------------------------------------------------------------------------------------------
+struct PackArgs {
+    const float* w; void* out;
+    int out_bf16, mode, Cout, Cin, kt, kh, kw, Cp, tap_i, tap_j, N, Kc, taps;
+};
+__global__ void pack_weights_kernel(const PackArgs a) {
+    const long long total = (long long)a.N * a.taps * a.Cp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % a.Cp);
+        const int tap = (int)((idx / a.Cp) % a.taps);
+        const int n = (int)(idx / ((long long)a.Cp * a.taps));
+        float v = 0.f;
+        if (c < a.Kc) {
+            if (a.mode == 0 || a.mode == 1) {
+                int tj = tap % a.kw, ti = (tap / a.kw) % a.kh, ta = tap / (a.kw * a.kh);
+                int co, ci;
+                if (a.mode == 0) { co = n; ci = c; }
+                else { co = c; ci = n; ta = a.kt - 1 - ta; ti = a.kh - 1 - ti; tj = a.kw - 1 - tj; }
+                v = a.w[((((long long)co * a.Cin + ci) * a.kt + ta) * a.kh + ti) * a.kw + tj];
+            } else {
+                const int ci = a.mode == 2 ? c : n;
+                const int co = a.mode == 2 ? n : c;
+                v = a.w[(((long long)ci * a.Cout + co) * a.kh + a.tap_i) * a.kw + a.tap_j];
+            }
+        }
+        const long long k = (long long)tap * a.Cp + c;
+        if (a.out_bf16) reinterpret_cast<__nv_bfloat16*>(a.out)[(long long)n * a.taps * a.Cp + k] = __float2bfloat16(v);
+        else reinterpret_cast<float*>(a.out)[k * a.N + n] = v;
+    }
+}
+
+struct UnpackArgs { const float* dw; float* grad; int mode, Cout, Cin, kt, kh, kw, tap_i, tap_j; };
+__global__ void unpack_wgrad_kernel(const UnpackArgs a) {
+    if (a.mode == 0) {
+        const long long total = (long long)a.Cout * a.Cin * a.kt * a.kh * a.kw;
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+             idx += (long long)gridDim.x * blockDim.x) {
+            long long r = idx;
+            const int tj = (int)(r % a.kw); r /= a.kw;
+            const int ti = (int)(r % a.kh); r /= a.kh;
+            const int ta = (int)(r % a.kt); r /= a.kt;
+            const int ci = (int)(r % a.Cin); const int co = (int)(r / a.Cin);
+            const int tap = (ta * a.kh + ti) * a.kw + tj;
+            a.grad[idx] += a.dw[((long long)tap * a.Cin + ci) * a.Cout + co];
+        }
+    } else {
+        const long long total = (long long)a.Cin * a.Cout;
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+             idx += (long long)gridDim.x * blockDim.x) {
+            const int co = (int)(idx % a.Cout), ci = (int)(idx / a.Cout);
+            a.grad[(((long long)ci * a.Cout + co) * a.kh + a.tap_i) * a.kw + a.tap_j] += a.dw[idx];
+        }
+    }
+}
+
+// ---- per-channel reductions -------------------------------------------------------------------------------------
+// Block of 256 threads: thread -> (pixel lane, 8-channel group).  G = C/8 groups, L = 256/G pixel lanes.
+constexpr int RED_THREADS = 256;
+constexpr int RED_PIX_PER_CTA = 2048;
+
+template <int NQ>
+__device__ __forceinline__ void block_reduce_to_global(float (&acc)[NQ][8], int g, int lane_pix, int G, int L,
+                                                       float* const (&dst)[NQ], float* smem) {
+    // smem: [NQ][L][G*8]
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (g < G && lane_pix < L) smem[(q * L + lane_pix) * G * 8 + g * 8 + j] = acc[q][j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NQ * G * 8; i += blockDim.x) {
+        const int q = i / (G * 8), c = i - q * G * 8;
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s += smem[(q * L + l) * G * 8 + c];
+        atomicAdd(dst[q] + c, s);
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long long cstride, float* sum, float* sumsq) {
+    extern __shared__ float red_smem[];
+    const int G = C / 8, L = RED_THREADS / G;
+    const int g = threadIdx.x % G, lp = threadIdx.x / G;
+    float acc[2][8] = {};
+    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
+    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    if (lp < L)
+        for (long long p = p0 + lp; p < p1; p += L) {
+            float v[8];
+            load8(x + p * cstride + g * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
+        }
+    float* const dst[2] = {sum, sumsq};
+    block_reduce_to_global<2>(acc, g, lp, G, L, dst, red_smem);
+}
+
+template <typename DyT>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, int relu, long long npix, int C, float* sums) {
+    extern __shared__ float red_smem[];
+    const int G = C / 8, L = RED_THREADS / G;
+    const int g = threadIdx.x % G, lp = threadIdx.x / G;
+    float acc[2][8] = {};
+    float sc[8], sh[8], mu[8], rs[8];
+    if (lp < L) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j]; mu[j] = mean[g * 8 + j]; rs[j] = rstd[g * 8 + j]; }
+    }
+    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
+    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    if (lp < L)
+        for (long long p = p0 + lp; p < p1; p += L) {
+            float d[8], v[8];
+            load8(dy + p * dy_cstride + g * 8, d);
+            load8(x + p * x_cstride + g * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dm = (relu && fmaf(v[j], sc[j], sh[j]) <= 0.f) ? 0.f : d[j];
+                acc[0][j] += dm;
+                acc[1][j] = fmaf(dm, (v[j] - mu[j]) * rs[j], acc[1][j]);
+            }
+        }
+    float* const dst[2] = {sums, sums + C};
+    block_reduce_to_global<2>(acc, g, lp, G, L, dst, red_smem);
+}
+
+template <typename DyT, typename DxT>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
+                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, int relu, long long npix, int C,
+                    const float* __restrict__ sums, DxT* dx, long long dx_cstride, float* dgamma, float* dbeta) {
+    const int G = C / 8;
+    const float inv_n = 1.0f / (float)npix;
+    if (blockIdx.x == 0 && dgamma != nullptr)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] += sums[c]; dgamma[c] += sums[C + c]; }
+    const long long total = npix * G;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % G);
+        const long long p = idx / G;
+        float d[8], v[8], o[8];
+        load8(dy + p * dy_cstride + g * 8, d);
+        load8(x + p * x_cstride + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            const float dm = (relu && fmaf(v[j], scale[c], shift[c]) <= 0.f) ? 0.f : d[j];
+            const float xh = (v[j] - mean[c]) * rstd[c];
+            o[j] = gamma[c] * rstd[c] * (dm - sums[c] * inv_n - xh * sums[C + c] * inv_n);
+        }
+        store8(dx + p * dx_cstride + g * 8, o);
+    }
+}
+
+template <typename DyT, typename YT, typename DxT>
+__global__ void __launch_bounds__(RED_THREADS)
+relu_bwd_kernel(const DyT* __restrict__ dy, long long dy_cstride, const YT* __restrict__ y, long long y_cstride, DxT* dx,
+                long long dx_cstride, float* dbias, long long npix, int C) {
+    extern __shared__ float red_smem[];
+    const int G = C / 8, L = RED_THREADS / G;
+    const int g = threadIdx.x % G, lp = threadIdx.x / G;
+    float acc[1][8] = {};
+    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
+    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    if (lp < L)
+        for (long long p = p0 + lp; p < p1; p += L) {
+            float d[8], v[8];
+            load8(dy + p * dy_cstride + g * 8, d);
+            load8(y + p * y_cstride + g * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { d[j] = v[j] > 0.f ? d[j] : 0.f; acc[0][j] += d[j]; }
+            store8(dx + p * dx_cstride + g * 8, d);
+        }
+    if (dbias != nullptr) {
+        float* const dst[1] = {dbias};
+        block_reduce_to_global<1>(acc, g, lp, G, L, dst, red_smem);
+    }
+}
+
+template <typename XT, typename YT>
+__global__ void __launch_bounds__(256)
+affine_act_kernel(const XT* __restrict__ x, long long x_cstride, YT* y, long long y_cstride, const float* __restrict__ scale,
+                  const float* __restrict__ shift, int relu, long long npix, int C) {
+    const int G = C / 8;
+    const long long total = npix * G;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % G);
+        const long long p = idx / G;
+        float v[8];
+        load8(x + p * x_cstride + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float r = fmaf(v[j], scale[g * 8 + j], shift[g * 8 + j]);
+            v[j] = relu ? fmaxf(r, 0.f) : r;
+        }
+        store8(y + p * y_cstride + g * 8, v);
+    }
+}
+
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, double count, const float* conv_bias,
+                                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                   long long* nbt, double momentum, double eps, float* scale, float* shift, float* mean,
+                                   float* rstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt != nullptr) *nbt += 1;
+    if (c >= C) return;
+    const double m = (double)sum[c] / count;
+    double var = (double)sumsq[c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const double rs = 1.0 / sqrt(var + eps);
+    const double g = gamma[c];
+    scale[c] = (float)(g * rs);
+    shift[c] = (float)((double)beta[c] - m * g * rs);
+    mean[c] = (float)m;
+    rstd[c] = (float)rs;
+    if (running_mean != nullptr) {
+        const double mb = m + (conv_bias ? (double)conv_bias[c] : 0.0);
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mb);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    }
+}
+
+__global__ void bn_fold_eval_kernel(const float* conv_bias, const float* gamma, const float* beta, const float* rm,
+                                    const float* rv, double eps, float* scale, float* shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double s = (double)gamma[c] / sqrt((double)rv[c] + eps);
+    scale[c] = (float)s;
+    shift[c] = (float)((double)beta[c] + ((conv_bias ? (double)conv_bias[c] : 0.0) - (double)rm[c]) * s);
+}
+
+// ---- layout -----------------------------------------------------------------------------------------------------
+// [F][C][HW] f32 -> [F][HW][cstride]; tile = 64 channels x 32 pixels, block (32, 8)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, long long src_fstride, OutT* dst, long long dst_cstride, int C, long long HW) {
+    __shared__ float tile[64][33];
+    const int f = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 64;
+    const float* s = src + (long long)f * src_fstride;
+    for (int cy = threadIdx.y; cy < 64; cy += 8) {
+        const long long p = p0 + threadIdx.x;
+        const int c = c0 + cy;
+        tile[cy][threadIdx.x] = (c < C && p < HW) ? s[(long long)c * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int py = threadIdx.y; py < 32; py += 8) {
+        const long long p = p0 + py;
+        const int c = c0 + 2 * threadIdx.x;
+        if (p < HW && c < C) {
+            const float v0 = tile[2 * threadIdx.x][py], v1 = tile[2 * threadIdx.x + 1][py];
+            OutT* d = dst + ((long long)f * HW + p) * dst_cstride + c;
+            if constexpr (sizeof(OutT) == 2) *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(v0, v1);
+            else *reinterpret_cast<float2*>(d) = make_float2(v0, v1);
+        }
+    }
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const InT* __restrict__ src, long long src_cstride, float* dst, int C, long long HW) {
+    __shared__ float tile[64][33];
+    const int f = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 64;
+    for (int py = threadIdx.y; py < 32; py += 8) {
+        const long long p = p0 + py;
+        const int c = c0 + 2 * threadIdx.x;
+        float v0 = 0.f, v1 = 0.f;
+        if (p < HW && c < C) {
+            const InT* s = src + ((long long)f * HW + p) * src_cstride + c;
+            if constexpr (sizeof(InT) == 2) {
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(s);
+                v0 = __uint_as_float(u << 16); v1 = __uint_as_float(u & 0xffff0000u);
+            } else {
+                const float2 t = *reinterpret_cast<const float2*>(s);
+                v0 = t.x; v1 = t.y;
+            }
+        }
+        tile[2 * threadIdx.x][py] = v0;
+        tile[2 * threadIdx.x + 1][py] = v1;
+    }
+    __syncthreads();
+    for (int cy = threadIdx.y; cy < 64; cy += 8) {
+        const long long p = p0 + threadIdx.x;
+        const int c = c0 + cy;
+        if (c < C && p < HW) dst[((long long)f * C + c) * HW + p] = tile[cy][threadIdx.x];
+    }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, float* y, float a, float b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
+}
+
+inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+    long long g = (work_items + threads - 1) / threads;
+    long long cap = (long long)sfvos_num_sms() * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+#define CS(s) reinterpret_cast<cudaStream_t>(s)
+#define CHECK_C8(C) SF_CHECK((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, "channel count %lld must be a multiple of 8 in [8,2048]", (long long)(C))
+
+extern "C" int sfvos_pack_weights(const float* w, void* out, int32_t out_dtype, int32_t mode, int64_t Cout, int64_t Cin,
+                                  int64_t kt, int64_t kh, int64_t kw, int64_t Cp, int64_t tap_i, int64_t tap_j,
+                                  sfvos_stream stream) {
+    SF_CHECK(mode >= 0 && mode <= 3, "pack_weights: bad mode %d", mode);
+    PackArgs a;
+    a.w = w; a.out = out; a.out_bf16 = (out_dtype == SFVOS_BF16); a.mode = mode;
+    a.Cout = (int)Cout; a.Cin = (int)Cin; a.kt = (int)kt; a.kh = (int)kh; a.kw = (int)kw; a.Cp = (int)Cp;
+    a.tap_i = (int)tap_i; a.tap_j = (int)tap_j;
+    a.N = (mode == 0 || mode == 2) ? (int)Cout : (int)Cin;
+    a.Kc = (mode == 0 || mode == 2) ? (int)Cin : (int)Cout;
+    a.taps = (mode <= 1) ? (int)(kt * kh * kw) : 1;
+    SF_CHECK(Cp >= a.Kc, "pack_weights: Cp=%lld smaller than the channel count %d", (long long)Cp, a.Kc);
+    const long long total = (long long)a.N * a.taps * a.Cp;
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, CS(stream)>>>(a);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_unpack_wgrad(const float* dw, float* grad, int32_t mode, int64_t Cout, int64_t Cin, int64_t kt,
+                                  int64_t kh, int64_t kw, int64_t tap_i, int64_t tap_j, sfvos_stream stream) {
+    SF_CHECK(mode == 0 || mode == 2, "unpack_wgrad: bad mode %d", mode);
+    UnpackArgs a{dw, grad, mode, (int)Cout, (int)Cin, (int)kt, (int)kh, (int)kw, (int)tap_i, (int)tap_j};
+    const long long total = mode == 0 ? Cout * Cin * kt * kh * kw : Cout * Cin;
+    unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, CS(stream)>>>(a);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+static inline size_t red_smem_bytes(int nq, int C) { return (size_t)nq * (RED_THREADS / (C / 8)) * C * sizeof(float); }
+
+extern "C" int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride, float* sum, float* sumsq,
+                                   sfvos_stream stream) {
+    CHECK_C8(C);
+    SF_CHECK(cstride % 4 == 0, "channel_stats: cstride must be a multiple of 4");
+    if (npix == 0) return SFVOS_OK;
+    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    channel_stats_kernel<<<grid, RED_THREADS, red_smem_bytes(2, (int)C), CS(stream)>>>(x, npix, (int)C, cstride, sum, sumsq);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_bn_finalize(const float* sum, const float* sumsq, double count, const float* conv_bias,
+                                 const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                 int64_t* num_batches_tracked, double momentum, double eps, float* scale, float* shift,
+                                 float* mean, float* rstd, int64_t C, sfvos_stream stream) {
+    SF_CHECK(count > 0, "bn_finalize: empty batch");
+    bn_finalize_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(sum, sumsq, count, conv_bias, gamma, beta,
+        running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, mean, rstd, (int)C);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_bn_fold_eval(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, double eps, float* scale, float* shift, int64_t C,
+                                  sfvos_stream stream) {
+    bn_fold_eval_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(conv_bias, gamma, beta, running_mean, running_var, eps, scale, shift, (int)C);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstride, void* y, int32_t y_dtype,
+                                int64_t y_cstride, const float* scale, const float* shift, int32_t relu, int64_t npix,
+                                int64_t C, sfvos_stream stream) {
+    CHECK_C8(C);
+    SF_CHECK(x_cstride % 8 == 0 && y_cstride % 8 == 0, "affine_act: strides must be multiples of 8");
+    if (npix == 0) return SFVOS_OK;
+    const int grid = grid_for(npix * (C / 8), 256);
+    using bf = __nv_bfloat16;
+#define LAUNCH(XT, YT) affine_act_kernel<XT, YT><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const XT*>(x), x_cstride, reinterpret_cast<YT*>(y), y_cstride, scale, shift, relu, npix, (int)C)
+    if (x_dtype == SFVOS_F32 && y_dtype == SFVOS_F32) LAUNCH(float, float);
+    else if (x_dtype == SFVOS_F32) LAUNCH(float, bf);
+    else if (y_dtype == SFVOS_F32) LAUNCH(bf, float);
+    else LAUNCH(bf, bf);
+#undef LAUNCH
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
+                                   const float* scale, const float* shift, const float* mean, const float* rstd,
+                                   int32_t relu, int64_t npix, int64_t C, float* sums, sfvos_stream stream) {
+    CHECK_C8(C);
+    SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0, "bn_bwd_reduce: strides must be multiples of 8");
+    if (npix == 0) return SFVOS_OK;
+    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    const size_t sm = red_smem_bytes(2, (int)C);
+    if (dy_dtype == SFVOS_F32)
+        bn_bwd_reduce_kernel<float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums);
+    else
+        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
+                                  const float* scale, const float* shift, const float* mean, const float* rstd,
+                                  const float* gamma, int32_t relu, int64_t npix, int64_t C, const float* sums, void* dx,
+                                  int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, sfvos_stream stream) {
+    CHECK_C8(C);
+    SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0 && dx_cstride % 8 == 0, "bn_bwd_apply: strides must be multiples of 8");
+    SF_CHECK((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply: dgamma and dbeta go together");
+    if (npix == 0) return SFVOS_OK;
+    const int grid = grid_for(npix * (C / 8), 256);
+    using bf = __nv_bfloat16;
+#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta)
+    if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float);
+    else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf);
+    else if (dx_dtype == SFVOS_F32) LAUNCH(bf, float);
+    else LAUNCH(bf, bf);
+#undef LAUNCH
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const void* y, int32_t y_dtype,
+                              int64_t y_cstride, void* dx, int32_t dx_dtype, int64_t dx_cstride, float* dbias, int64_t npix,
+                              int64_t C, sfvos_stream stream) {
+    CHECK_C8(C);
+    SF_CHECK(dy_cstride % 8 == 0 && y_cstride % 8 == 0 && dx_cstride % 8 == 0, "relu_bwd: strides must be multiples of 8");
+    if (npix == 0) return SFVOS_OK;
+    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    const size_t sm = red_smem_bytes(1, (int)C);
+    using bf = __nv_bfloat16;
+#define LAUNCH(DT, YT, XT) relu_bwd_kernel<DT, YT, XT><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, reinterpret_cast<const YT*>(y), y_cstride, reinterpret_cast<XT*>(dx), dx_cstride, dbias, npix, (int)C)
+    if (dy_dtype == SFVOS_F32 && y_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float, float);
+    else if (dy_dtype == SFVOS_F32 && y_dtype == SFVOS_BF16 && dx_dtype == SFVOS_BF16) LAUNCH(float, bf, bf);
+    else if (dy_dtype == SFVOS_BF16 && y_dtype == SFVOS_BF16 && dx_dtype == SFVOS_BF16) LAUNCH(bf, bf, bf);
+    else { sfvos_set_error("relu_bwd: unsupported dtype combination (%d,%d,%d)", dy_dtype, y_dtype, dx_dtype); return SFVOS_ERR_INVALID; }
+#undef LAUNCH
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_nchw_to_nhwc(const float* src, int64_t src_fstride, void* dst, int32_t dst_dtype, int64_t dst_cstride,
+                                  int64_t F, int64_t C, int64_t HW, sfvos_stream stream) {
+    SF_CHECK(C % 2 == 0 && dst_cstride % 2 == 0, "nchw_to_nhwc: C and cstride must be even");
+    SF_CHECK(F <= 65535, "nchw_to_nhwc: too many frames in one call");
+    if (F == 0 || HW == 0) return SFVOS_OK;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)F), block(32, 8);
+    if (dst_dtype == SFVOS_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, CS(stream)>>>(src, src_fstride, reinterpret_cast<__nv_bfloat16*>(dst), dst_cstride, (int)C, HW);
+    else nchw_to_nhwc_kernel<float><<<grid, block, 0, CS(stream)>>>(src, src_fstride, reinterpret_cast<float*>(dst), dst_cstride, (int)C, HW);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_nhwc_to_nchw(const void* src, int32_t src_dtype, int64_t src_cstride, float* dst, int64_t F, int64_t C,
+                                  int64_t HW, sfvos_stream stream) {
+    SF_CHECK(C % 2 == 0 && src_cstride % 2 == 0, "nhwc_to_nchw: C and cstride must be even");
+    SF_CHECK(F <= 65535, "nhwc_to_nchw: too many frames in one call");
+    if (F == 0 || HW == 0) return SFVOS_OK;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)F), block(32, 8);
+    if (src_dtype == SFVOS_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_cstride, dst, (int)C, HW);
+    else nhwc_to_nchw_kernel<float><<<grid, block, 0, CS(stream)>>>(reinterpret_cast<const float*>(src), src_cstride, dst, (int)C, HW);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_axpby(const float* x, float* y, float a, float b, int64_t n, sfvos_stream stream) {
+    if (n == 0) return SFVOS_OK;
+    axpby_kernel<<<grid_for(n, 256), 256, 0, CS(stream)>>>(x, y, a, b, n);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}

@@ -1,0 +1,187 @@
+// Tail of the mask branch: mask_fcn_logits (1x1 conv C->n_cls, TV/models/detection/mask_rcnn.py:344), the
+// class-channel BCE-with-logits loss of maskrcnn_loss (TV/models/detection/roi_heads.py:100-129), their fused
+// backward, and the sigmoid/select of maskrcnn_inference (roi_heads.py:56-82).
+// N = n_cls (2) is far too narrow for a tensor-core tile, so these are warp-per-pixel dot products over the
+// contiguous channel axis (16-byte vector loads, shuffle reductions): HBM-bound on reading x once.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+constexpr int MAX_CLS = 8;
+
+template <typename XT>
+__global__ void __launch_bounds__(256)
+mask_logits_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* logits,
+                       long long K, int S, int C, int n_cls) {
+    const int lane = threadIdx.x & 31;
+    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long ss = (long long)S * S;
+    if (pix >= K * ss) return;
+    float acc[MAX_CLS] = {};
+    for (int c8 = lane; c8 < C / 8; c8 += 32) {
+        float v[8];
+        ld8(x + pix * C + c8 * 8, v);
+        for (int cls = 0; cls < n_cls; ++cls) {
+            float wv[8];
+            ld8(w + (long long)cls * C + c8 * 8, wv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[cls] = fmaf(v[j], wv[j], acc[cls]);
+        }
+    }
+    const long long k = pix / ss, p = pix - k * ss;
+    for (int cls = 0; cls < n_cls; ++cls) {
+        const float s = warp_sum(acc[cls]);
+        if (lane == 0) logits[(k * n_cls + cls) * ss + p] = s + b[cls];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mask_bce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ targets,
+                    float* loss, long long K, int S, int n_cls) {
+    __shared__ float part[8];
+    const long long ss = (long long)S * S, total = K * ss;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long k = i / ss, p = i - k * ss;
+        const float z = logits[(k * n_cls + labels[k]) * ss + p];
+        const float t = targets[i];
+        acc += fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) s += part[i];
+        atomicAdd(loss, s / (float)total);
+    }
+}
+
+// one CTA per ROI (8 warps stride over its S*S pixels): dx = dz * w[label], dw[label] += dz * x, db[label] += dz
+template <typename XT, typename DxT>
+__global__ void __launch_bounds__(256)
+mask_logits_bce_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ logits,
+                           const long long* __restrict__ labels, const float* __restrict__ targets,
+                           const float* __restrict__ gloss, DxT* dx, float* dw, float* db, long long K, int S, int C, int n_cls) {
+    extern __shared__ float s_dw[];          // [8 warps][C]
+    __shared__ float s_db[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long k = blockIdx.x;
+    const int label = (int)labels[k];
+    const int ss = S * S;
+    const float g = gloss[0] / (float)(K * ss);
+    float dbacc = 0.f;
+    for (int c8 = lane; c8 < C / 8; c8 += 32) {      // C <= 256 -> at most one iteration per lane
+        float wv[8], dwacc[8] = {};
+        ld8(w + (long long)label * C + c8 * 8, wv);
+        for (int p = warp; p < ss; p += 8) {
+            const float z = logits[(k * n_cls + label) * ss + p];
+            const float t = targets[k * ss + p];
+            const float dz = g * (1.f / (1.f + expf(-z)) - t);
+            float v[8], o[8];
+            ld8(x + (k * ss + p) * C + c8 * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j] = dz * wv[j]; dwacc[j] = fmaf(dz, v[j], dwacc[j]); }
+            st8(dx + (k * ss + p) * C + c8 * 8, o);
+            if (c8 == 0) dbacc += dz;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_dw[warp * C + c8 * 8 + j] = dwacc[j];
+    }
+    if (lane == 0) s_db[warp] = dbacc;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += s_dw[i * C + c];
+        atomicAdd(dw + (long long)label * C + c, s);
+    }
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += s_db[i];
+        atomicAdd(db + label, s);
+    }
+}
+
+__global__ void mask_probs_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, float* prob,
+                                  long long K, int S, int n_cls) {
+    const long long ss = (long long)S * S, total = K * ss;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long k = i / ss, p = i - k * ss;
+    prob[i] = 1.f / (1.f + expf(-logits[(k * n_cls + labels[k]) * ss + p]));
+}
+
+}  // namespace
+
+#define CS(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int sfvos_mask_logits_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, float* logits,
+                                     int64_t K, int64_t S, int64_t C, int32_t n_cls, sfvos_stream stream) {
+    SF_CHECK(C % 8 == 0 && n_cls >= 1 && n_cls <= MAX_CLS, "mask_logits: C %% 8 == 0 and n_cls <= 8 required");
+    if (K == 0) return SFVOS_OK;
+    const long long npix = K * S * S;
+    const int grid = (int)((npix + 7) / 8);
+    if (x_dtype == SFVOS_BF16) mask_logits_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, logits, K, (int)S, (int)C, n_cls);
+    else mask_logits_fwd_kernel<float><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const float*>(x), w, b, logits, K, (int)S, (int)C, n_cls);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, const float* targets, float* loss, int64_t K,
+                                  int64_t S, int32_t n_cls, sfvos_stream stream) {
+    SF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), CS(stream)));
+    if (K == 0) return SFVOS_OK;
+    const long long total = K * S * S;
+    long long grid = (total + 255) / 256;
+    if (grid > 2 * sfvos_num_sms()) grid = 2 * sfvos_num_sms();
+    mask_bce_fwd_kernel<<<(int)grid, 256, 0, CS(stream)>>>(logits, reinterpret_cast<const long long*>(labels), targets, loss, K, (int)S, n_cls);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_mask_logits_bce_bwd(const void* x, int32_t x_dtype, const float* w, const float* logits,
+                                         const int64_t* labels, const float* targets, const float* gloss, void* dx,
+                                         int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C,
+                                         int32_t n_cls, sfvos_stream stream) {
+    SF_CHECK(C % 8 == 0 && C <= 256 * 8, "mask_logits_bce_bwd: unsupported C");
+    SF_CHECK(x_dtype == dx_dtype, "mask_logits_bce_bwd: x and dx must share a dtype");
+    if (K == 0) return SFVOS_OK;
+    const size_t sm = (size_t)8 * C * sizeof(float);
+    const long long* lab = reinterpret_cast<const long long*>(labels);
+    if (x_dtype == SFVOS_BF16)
+        mask_logits_bce_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, logits, lab, targets, gloss, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, K, (int)S, (int)C, n_cls);
+    else
+        mask_logits_bce_bwd_kernel<float, float><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, logits, lab, targets, gloss, reinterpret_cast<float*>(dx), dw, db, K, (int)S, (int)C, n_cls);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_mask_probs(const float* logits, const int64_t* labels, float* prob, int64_t K, int64_t S, int32_t n_cls,
+                                sfvos_stream stream) {
+    if (K == 0) return SFVOS_OK;
+    const long long total = K * S * S;
+    mask_probs_kernel<<<(int)((total + 255) / 256), 256, 0, CS(stream)>>>(logits, reinterpret_cast<const long long*>(labels), prob, K, (int)S, n_cls);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}

@@ -1,0 +1,99 @@
+// Host-side runtime shared by all entry points: error string, device check, SM count, TMA descriptor encode.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void sfvos_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* sfvos_last_error(void) { return g_err; }
+extern "C" int sfvos_version(void) { return 100; }
+
+extern "C" int sfvos_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        sfvos_set_error("no CUDA device: %s (libsfvos has no CPU fallback)", cudaGetErrorString(e));
+        return SFVOS_ERR_UNSUPPORTED;
+    }
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major != 10) {
+        sfvos_set_error("device %d is sm_%d%d; libsfvos is built for sm_100a only", dev, major, minor);
+        return SFVOS_ERR_UNSUPPORTED;
+    }
+    return SFVOS_OK;
+}
+
+int sfvos_num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
+// cuTensorMapEncodeTiled is a driver-API symbol; fetch it through the runtime so the library links without -lcuda
+// (the build container has no libcuda.so.1).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+int sfvos_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode_fn();
+    SF_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    SF_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        SF_CHECK(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %u out of range", i, box[i]);
+    }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gstr[i] = strides_bytes[i];
+        SF_CHECK((strides_bytes[i] & 15) == 0, "TMA stride %d = %llu not a multiple of 16 bytes", i,
+                 (unsigned long long)strides_bytes[i]);
+    }
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                    bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        sfvos_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,.. box %u,%u,..)",
+                        (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        return SFVOS_ERR_CUDA;
+    }
+    return SFVOS_OK;
+}

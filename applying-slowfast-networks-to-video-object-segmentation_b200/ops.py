@@ -1,0 +1,254 @@
+"""Torch-facing wrappers over the C ABI (include/sfvos.h).  torch is used only for device memory and streams;
+every arithmetic kernel is in libsfvos.so.  All wrappers require CUDA tensors and raise otherwise (no fallback)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, ConvParams, RoiParams, WgradParams, call
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def torch_dtype(code):
+    return torch.float32 if code == F32 else torch.bfloat16
+
+
+def _p(t, byte_off=0):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libsfvos ops need CUDA tensors (there is no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr() + byte_off)
+
+
+class Act:
+    """A channels-last activation [B,T,H,W,C] living in (a channel slice of) a dense [B*T*H*W, cstride] buffer."""
+
+    __slots__ = ("buf", "B", "T", "H", "W", "C", "cstride", "ch_off", "bstride")
+
+    def __init__(self, buf, B, T, H, W, C, cstride=None, ch_off=0, bstride=0):
+        self.buf, self.B, self.T, self.H, self.W, self.C = buf, B, T, H, W, C
+        self.cstride = cstride if cstride is not None else C
+        self.ch_off = ch_off          # element offset of the first channel / first frame inside buf
+        self.bstride = bstride        # elements between clips; 0 = dense (T*H*W*cstride)
+
+    @staticmethod
+    def empty(B, T, H, W, C, dtype, device, cstride=None):
+        cs = cstride if cstride is not None else C
+        return Act(torch.empty(B * T * H * W * cs, dtype=dtype, device=device), B, T, H, W, C, cs, 0)
+
+    @property
+    def npix(self):
+        return self.B * self.T * self.H * self.W
+
+    @property
+    def dtype(self):
+        return self.buf.dtype
+
+    def ptr(self):
+        return _p(self.buf, self.ch_off * self.buf.element_size())
+
+    def slice(self, ch_off, C):
+        return Act(self.buf, self.B, self.T, self.H, self.W, C, self.cstride, self.ch_off + ch_off, self.bstride)
+
+    def frames(self, t0, t1):
+        """Temporal sub-range [t0,t1) of every clip (same storage; clips keep the parent's batch stride)."""
+        per = self.H * self.W * self.cstride
+        bs = self.bstride if self.bstride else self.T * per
+        return Act(self.buf, self.B, t1 - t0, self.H, self.W, self.C, self.cstride, self.ch_off + t0 * per, bs)
+
+    def as_nchw(self):
+        """[B*T, C, H, W]-shaped strided view (channels_last memory) of a dense activation -- no copy."""
+        assert self.bstride == 0 and self.ch_off < self.cstride
+        v = self.buf.view(self.B * self.T, self.H, self.W, self.cstride)[..., self.ch_off:self.ch_off + self.C]
+        return v.permute(0, 3, 1, 2)
+
+
+def device_check():
+    call("sfvos_device_check")
+
+
+def pack_weights(w, mode, out_dtype, Cp, tap=(0, 0)):
+    """mode 0/1: w [Cout,Cin,kt,kh,kw]; mode 2/3: ConvTranspose2d w [Cin,Cout,kh,kw], single tap."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    if mode <= 1:
+        if w.dim() == 4:
+            w = w.unsqueeze(2)
+        Cout, Cin, kt, kh, kw = w.shape
+        taps = kt * kh * kw
+    else:
+        Cin, Cout, kh, kw = w.shape
+        kt, taps = 1, 1
+    N = Cout if mode in (0, 2) else Cin
+    if out_dtype == BF16:
+        out = torch.empty(N, taps * Cp, dtype=torch.bfloat16, device=w.device)
+    else:
+        out = torch.empty(taps * Cp, N, dtype=torch.float32, device=w.device)
+    call("sfvos_pack_weights", _p(w), _p(out), out_dtype, mode, Cout, Cin, kt, kh, kw, Cp, tap[0], tap[1], stream())
+    return out
+
+
+def unpack_wgrad(dw, grad, mode, tap=(0, 0)):
+    if mode == 0:
+        g5 = grad if grad.dim() == 5 else grad.unsqueeze(2)
+        Cout, Cin, kt, kh, kw = g5.shape
+    else:
+        Cin, Cout, kh, kw = grad.shape
+        kt = 1
+    assert grad.is_contiguous() and grad.dtype == torch.float32
+    call("sfvos_unpack_wgrad", _p(dw), _p(grad), mode, Cout, Cin, kt, kh, kw, tap[0], tap[1], stream())
+
+
+def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shift=None, stats=None, accumulate=False,
+         x_strides=None, scatter=None):
+    """x: Act (input), y: Act (output, B*To*OH*OW pixels).  k=(kt,kh,kw), pad=(pt,ph,pw).
+    stats: optional f32 [2,N] tensor receiving (sum, sumsq) of the raw accumulators (umma only)."""
+    p = ConvParams()
+    p.x = x.ptr(); p.B, p.T, p.H, p.W, p.C, p.x_cstride = x.B, x.T, x.H, x.W, x.C, x.cstride
+    p.x_bstride = x.bstride
+    if x_strides is not None:
+        p.x_hstride, p.x_tstride, p.x_bstride = x_strides
+    p.w = _p(w_packed); p.Cp = Cp; p.N = N
+    p.kt, p.kh, p.kw = k
+    p.pad_t, p.pad_h, p.pad_w = pad
+    p.To = To
+    p.y = y.ptr(); p.y_dtype = dt(y.buf); p.relu = int(relu); p.y_cstride = y.cstride
+    p.scale = _p(scale); p.shift = _p(shift)
+    if stats is not None:
+        p.sum = _p(stats); p.sumsq = _p(stats, N * 4)
+    p.accumulate = int(accumulate)
+    if scatter is not None:
+        p.OH, p.OW, p.oy_mul, p.oy_off, p.ox_mul, p.ox_off = scatter
+    call("sfvos_conv_umma" if umma else "sfvos_conv_simt", ctypes.byref(p), stream())
+
+
+def wgrad(x, dy, k, pad, dw, *, umma, dy_strides=None):
+    """dw f32 [taps, x.C, dy.C] += x^T dy over all pixels (x shifted per tap)."""
+    p = WgradParams()
+    p.x = x.ptr(); p.B, p.T, p.H, p.W, p.C, p.x_cstride = x.B, x.T, x.H, x.W, x.C, x.cstride
+    p.x_bstride = x.bstride
+    p.dy = dy.ptr(); p.To = dy.T; p.N = dy.C; p.dy_cstride = dy.cstride
+    if dy_strides is not None:
+        p.dy_hstride, p.dy_tstride, p.dy_bstride = dy_strides
+    p.kt, p.kh, p.kw = k
+    p.pad_t, p.pad_h, p.pad_w = pad
+    p.dw = _p(dw)
+    call("sfvos_wgrad_umma" if umma else "sfvos_wgrad_simt", ctypes.byref(p), stream())
+
+
+def channel_stats(x, stats):
+    assert x.dtype == torch.float32
+    call("sfvos_channel_stats", x.ptr(), x.npix, x.C, x.cstride, _p(stats), _p(stats, x.C * 4), stream())
+
+
+def bn_finalize(stats, count, conv_bias, gamma, beta, running_mean, running_var, nbt, momentum, eps, out4):
+    """out4: f32 [4,C] = (scale, shift, mean, rstd)."""
+    C = gamma.numel()
+    call("sfvos_bn_finalize", _p(stats), _p(stats, C * 4), float(count), _p(conv_bias), _p(gamma), _p(beta),
+         _p(running_mean), _p(running_var), _p(nbt), float(momentum), float(eps),
+         _p(out4), _p(out4, C * 4), _p(out4, 2 * C * 4), _p(out4, 3 * C * 4), C, stream())
+
+
+def bn_fold_eval(conv_bias, gamma, beta, running_mean, running_var, eps, out2):
+    C = gamma.numel()
+    call("sfvos_bn_fold_eval", _p(conv_bias), _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps),
+         _p(out2), _p(out2, C * 4), C, stream())
+
+
+def affine_act(x, y, scale, shift, relu):
+    call("sfvos_affine_act", x.ptr(), dt(x.buf), x.cstride, y.ptr(), dt(y.buf), y.cstride, _p(scale), _p(shift),
+         int(relu), x.npix, x.C, stream())
+
+
+def bn_bwd(dy, raw, bn4, gamma, relu, dx, dgamma, dbeta):
+    """dy, raw (f32), dx: Acts over the same pixels; bn4 = (scale, shift, mean, rstd) [4,C]."""
+    C = raw.C
+    sums = torch.zeros(2 * C, dtype=torch.float32, device=raw.buf.device)
+    sc, sh, mu, rs = _p(bn4), _p(bn4, C * 4), _p(bn4, 2 * C * 4), _p(bn4, 3 * C * 4)
+    call("sfvos_bn_bwd_reduce", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), raw.cstride, sc, sh, mu, rs, int(relu),
+         raw.npix, C, _p(sums), stream())
+    call("sfvos_bn_bwd_apply", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), raw.cstride, sc, sh, mu, rs, _p(gamma),
+         int(relu), raw.npix, C, _p(sums), dx.ptr(), dt(dx.buf), dx.cstride, _p(dgamma), _p(dbeta), stream())
+
+
+def relu_bwd(dy, y, dx, dbias):
+    call("sfvos_relu_bwd", dy.ptr(), dt(dy.buf), dy.cstride, y.ptr(), dt(y.buf), y.cstride, dx.ptr(), dt(dx.buf),
+         dx.cstride, _p(dbias), y.npix, y.C, stream())
+
+
+def nchw_to_nhwc(src, dst_act, frame_off=0):
+    """src f32 [F,C,H,W] contiguous -> frames [frame_off, frame_off+F) of dst_act."""
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    F, C, H, W = src.shape
+    esz = dst_act.buf.element_size()
+    off = (frame_off * H * W * dst_act.cstride + dst_act.ch_off) * esz
+    call("sfvos_nchw_to_nhwc", _p(src), C * H * W, _p(dst_act.buf, off), dt(dst_act.buf), dst_act.cstride, F, C, H * W,
+         stream())
+
+
+def nhwc_to_nchw(src_act, dst):
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    call("sfvos_nhwc_to_nchw", src_act.ptr(), dt(src_act.buf), src_act.cstride, _p(dst), src_act.B * src_act.T,
+         src_act.C, src_act.H * src_act.W, stream())
+
+
+def roi_levels(rois, k_min, k_max):
+    K = rois.shape[0]
+    levels = torch.empty(K, dtype=torch.int32, device=rois.device)
+    call("sfvos_roi_levels", _p(rois), K, k_min, k_max, _p(levels), stream())
+    return levels
+
+
+def _roi_params(feats, dfeats, shapes, scales, N, C, cstride, feat_dtype, rois, levels, P, sr, out, out_nchw):
+    p = RoiParams()
+    for i in range(len(shapes)):
+        if feats is not None:
+            p.feat[i] = feats[i].data_ptr()
+        if dfeats is not None:
+            p.dfeat[i] = dfeats[i].data_ptr()
+        p.H[i], p.W[i] = shapes[i]
+        p.scale[i] = scales[i]
+    p.n_levels = len(shapes); p.feat_dtype = feat_dtype
+    p.N, p.C, p.cstride = N, C, cstride
+    p.rois = _p(rois); p.levels = _p(levels); p.K = rois.shape[0]; p.P = P; p.sampling_ratio = sr
+    p.out = _p(out); p.out_dtype = dt(out); p.out_nchw = int(out_nchw)
+    return p
+
+
+def roi_align_fwd(feats, shapes, scales, N, C, rois, levels, P, sr, out, out_nchw):
+    p = _roi_params(feats, None, shapes, scales, N, C, C, dt(feats[0]), rois, levels, P, sr, out, out_nchw)
+    call("sfvos_roi_align_fwd", ctypes.byref(p), stream())
+
+
+def roi_align_bwd(dfeats, shapes, scales, N, C, rois, levels, P, sr, gout, out_nchw):
+    p = _roi_params(None, dfeats, shapes, scales, N, C, C, F32, rois, levels, P, sr, gout, out_nchw)
+    call("sfvos_roi_align_bwd", ctypes.byref(p), stream())
+
+
+def mask_targets(masks_u8, rois, M):
+    n_obj, H, W = masks_u8.shape
+    K = rois.shape[0]
+    out = torch.empty(K, M, M, dtype=torch.float32, device=rois.device)
+    call("sfvos_mask_targets", _p(masks_u8), n_obj, H, W, _p(rois), K, M, _p(out), stream())
+    return out
+
+
+def axpby(x, y, a, b):
+    call("sfvos_axpby", _p(x), _p(y), float(a), float(b), x.numel(), stream())
+
+
+def launches():
+    return _lib.LAUNCHES

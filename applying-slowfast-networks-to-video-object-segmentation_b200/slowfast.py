@@ -1,0 +1,385 @@
+"""SlowFastLayers -- drop-in for the reference module (code/helpers/model.py:30-165) running on libsfvos.so.
+
+Same constructor arguments, attribute names, parameter registration order and state_dict keys (the nn.Conv3d /
+nn.BatchNorm3d submodules are kept as *parameter containers* only -- their forward is never called; all
+arithmetic goes through the C ABI in include/sfvos.h).  Differences that are deliberate:
+  * activations are channels-last (NDHWC) bf16 internally (fp32 in validation mode, ``precision="fp32"`` or
+    SFVOS_PRECISION=fp32); conv outputs are written straight into channel slices of the concat buffers, so the
+    torch.cat / stack / transpose copies of model.py:115,157-158,162 do not exist
+  * returned feature maps have the reference's shapes and dtype (fp32 [B,256,H,W]) but channels_last strides
+  * there is no CPU path: inputs are moved to ``self.device`` (model.py:157-158 does the same) and the call fails
+    loudly if that is not an sm_100 GPU.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import BF16, F32
+from .ops import Act
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class _Spec:
+    __slots__ = ("conv", "bn", "cin", "cout", "kt", "khw", "pad", "relu")
+
+    def __init__(self, conv, bn, cin, cout, kt, khw, relu):
+        self.conv, self.bn, self.cin, self.cout, self.kt, self.khw, self.relu = conv, bn, cin, cout, kt, khw, relu
+        self.pad = 1 if khw == 3 else 0
+
+    @property
+    def k(self):
+        return (self.kt, self.khw, self.khw)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class SlowFastLayers(nn.Module):
+    def __init__(self, input_size, device, slow_pathway_size, fast_pathway_size):
+        super().__init__()
+        self.device = device
+        self.slow_pathway_size = slow_pathway_size
+        self.fast_pathway_size = fast_pathway_size
+
+        ks1, ks2, ks3 = self._calc_kernel_sizes(slow_pathway_size)
+        kf1, kf2, kf3 = self._calc_kernel_sizes(fast_pathway_size)
+        kl1, slow_out1, fast_out1 = self._calc_fuse_kernel_size(slow_pathway_size, ks1, fast_pathway_size, kf1)
+        kl2, _, _ = self._calc_fuse_kernel_size(slow_out1, ks2, fast_out1, kf2)
+
+        # registration order == reference (model.py:47-67): it fixes state_dict order and SGD state indices
+        self.fast_conv1, self.bn_f1 = self._init_conv_and_bn(kf1, input_size, 32)
+        self.slow_conv1, self.bn_s1 = self._init_conv_and_bn(ks1, input_size, 192)
+        self.fast_conv2, self.bn_f2 = self._init_conv_and_bn(kf2, 32, 32)
+        self.slow_conv2, self.bn_s2 = self._init_conv_and_bn(ks2, 256, 192)
+        self.fast_conv3, self.bn_f3 = self._init_conv_and_bn(kf3, 32, 32)
+        self.slow_conv3, self.bn_s3 = self._init_conv_and_bn(ks3, 256, 224)
+        self.conv_f2s1, self.bn_f2s1 = self._init_fuse_and_bn(kl1)
+        self.conv_f2s2, self.bn_f2s2 = self._init_fuse_and_bn(kl2)
+        self.relu = nn.ReLU(inplace=True)
+
+        self.input_size = input_size
+        self.precision = os.environ.get("SFVOS_PRECISION", "bf16")
+        self._specs = OrderedDict((s.conv, s) for s in [
+            _Spec("fast_conv1", "bn_f1", input_size, 32, kf1, 3, True),
+            _Spec("slow_conv1", "bn_s1", input_size, 192, ks1, 3, True),
+            _Spec("fast_conv2", "bn_f2", 32, 32, kf2, 3, True),
+            _Spec("slow_conv2", "bn_s2", 256, 192, ks2, 3, True),
+            _Spec("fast_conv3", "bn_f3", 32, 32, kf3, 3, False),
+            _Spec("slow_conv3", "bn_s3", 256, 224, ks3, 3, False),
+            _Spec("conv_f2s1", "bn_f2s1", 32, 64, kl1, 1, True),
+            _Spec("conv_f2s2", "bn_f2s2", 32, 64, kl2, 1, True),
+        ])
+        self._pack_cache = {}
+
+    # ---- construction helpers (same names as the reference) ------------------------------------------------------
+    def _init_conv_and_bn(self, temporal_kernelsize, in_channels, out_channels):
+        conv = nn.Conv3d(in_channels, out_channels, kernel_size=(temporal_kernelsize, 3, 3), padding=(0, 1, 1))
+        return conv, nn.BatchNorm3d(out_channels)
+
+    def _init_fuse_and_bn(self, temporal_kernelsize):
+        conv = nn.Conv3d(32, 64, kernel_size=[temporal_kernelsize, 1, 1], stride=[1, 1, 1], padding=[0, 0, 0], bias=False)
+        return conv, nn.BatchNorm3d(64)
+
+    def _calc_kernel_sizes(self, pathway_size):
+        div, rem = divmod(pathway_size, 3)
+        if rem == 0:
+            return (div, div + 1, div + 1)
+        if rem == 1:
+            return (div + 1, div + 1, div + 1)
+        return (div + 1, div + 1, div + 2)
+
+    def _calc_fuse_kernel_size(self, slow_in, slow_kernel, fast_in, fast_kernel):
+        out_slow = slow_in - slow_kernel + 1
+        out_fast = fast_in - fast_kernel + 1
+        return out_fast - out_slow + 1, out_slow, out_fast
+
+    # ---- helpers ----------------------------------------------------------------------------------------------------
+    @property
+    def _umma(self):
+        return self.precision != "fp32"
+
+    @property
+    def _act_dtype(self):
+        return torch.bfloat16 if self._umma else torch.float32
+
+    def _packed(self, name, mode):
+        """Packed GEMM operand of a conv weight, cached until the parameter changes."""
+        w = getattr(self, name).weight
+        spec = self._specs[name]
+        kc = spec.cin if mode == 0 else spec.cout
+        cp = _round_up(kc, 64) if self._umma else kc
+        key = (name, mode, self._umma)
+        tag = (w.data_ptr(), w._version, str(w.device))
+        hit = self._pack_cache.get(key)
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.pack_weights(w, mode, BF16 if self._umma else F32, cp), cp)
+            self._pack_cache[key] = hit
+        return hit[1], hit[2]
+
+    def _param_list(self):
+        ps = []
+        for s in self._specs.values():
+            conv, bn = getattr(self, s.conv), getattr(self, s.bn)
+            ps.append(conv.weight)
+            if conv.bias is not None:
+                ps.append(conv.bias)
+            ps.extend([bn.weight, bn.bias])
+        return ps
+
+    # ---- reference API ------------------------------------------------------------------------------------------------
+    def fuse(self, slow, fast, conv, bn):
+        """Kept for API parity (model.py:111-116).  The fused pipeline never calls it; provided for callers that do:
+        runs the lateral conv+BN+ReLU and concatenates on the channel axis."""
+        name = next(n for n, s in self._specs.items() if getattr(self, n) is conv)
+        spec = self._specs[name]
+        f = _to_act(fast, self._act_dtype)
+        out = Act.empty(f.B, f.T - spec.kt + 1, f.H, f.W, 64, torch.float32, fast.device)
+        _conv_bn_forward(self, spec, f, out, self.training, None)
+        lateral = out.as_nchw().reshape(f.B, out.T, 64, f.H, f.W).permute(0, 2, 1, 3, 4)
+        return torch.cat([slow, lateral.to(slow.dtype)], 1), fast
+
+    def forward(self, slow, fast):
+        """slow [B,256,sp,H,W], fast [B,256,fp,H,W] (any strides) -> (slow [B,224,1,H,W], fast [B,32,1,H,W])."""
+        dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
+        slow, fast = slow.to(dev), fast.to(dev)
+        merged = _SlowFastLevelFn.apply(self, None, None, slow, fast, *self._param_list())
+        b, _, h, w = merged.shape
+        return merged[:, :224].unsqueeze(2), merged[:, 224:].unsqueeze(2)
+
+    def temporally_enhance_features(self, slow_features, fast_features):
+        """list (len B) of {level: [T,256,H,W]} -> OrderedDict{level: [B,256,H,W]} (model.py:151-165)."""
+        dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
+        merged = OrderedDict()
+        params = self._param_list()
+        for key in slow_features[0].keys():
+            slow_list = [d[key].to(dev) for d in slow_features]
+            fast_list = [d[key].to(dev) for d in fast_features]
+            needs_grad = any(t.requires_grad for t in slow_list + fast_list) and torch.is_grad_enabled()
+            if needs_grad:
+                s = torch.stack(slow_list).transpose(1, 2)
+                f = torch.stack(fast_list).transpose(1, 2)
+                merged[key] = _SlowFastLevelFn.apply(self, None, None, s, f, *params)
+            else:
+                merged[key] = _SlowFastLevelFn.apply(self, slow_list, fast_list, None, None, *params)
+        return merged
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# engine
+# ----------------------------------------------------------------------------------------------------------------------
+def _to_act(x5, dtype):
+    """[B,C,T,H,W] tensor (any strides) -> dense channels-last Act."""
+    b, c, t, h, w = x5.shape
+    frames = x5.permute(0, 2, 1, 3, 4)
+    if frames.dtype != torch.float32:
+        frames = frames.float()
+    frames = frames.contiguous().view(b * t, c, h, w)
+    act = Act.empty(b, t, h, w, c, dtype, x5.device)
+    ops.nchw_to_nhwc(frames, act)
+    return act
+
+
+def _clips_to_act(clips, dtype):
+    """list of per-clip [T,C,H,W] fp32 tensors -> one channels-last Act [B,T,H,W,C] (no torch.stack copy)."""
+    t, c, h, w = clips[0].shape
+    act = Act.empty(len(clips), t, h, w, c, dtype, clips[0].device)
+    for b, clip in enumerate(clips):
+        if clip.dtype != torch.float32 or not clip.is_contiguous():
+            clip = clip.float().contiguous()
+        ops.nchw_to_nhwc(clip, act, frame_off=b * t)
+    return act
+
+
+def _alias_offset(slow_list, fast_list):
+    """If every slow clip is a contiguous frame range of its fast clip (the reference's _slice_features,
+    model.py:242-248, yields exactly such views) return the common first-frame offset, else None."""
+    off = None
+    for s, f in zip(slow_list, fast_list):
+        if not (s.is_contiguous() and f.is_contiguous() and s.dtype == f.dtype == torch.float32):
+            return None
+        if s.untyped_storage().data_ptr() != f.untyped_storage().data_ptr() or s.shape[1:] != f.shape[1:]:
+            return None
+        frame_bytes = f[0].numel() * 4
+        delta = s.data_ptr() - f.data_ptr()
+        if delta < 0 or delta % frame_bytes:
+            return None
+        o = delta // frame_bytes
+        if o + s.shape[0] > f.shape[0] or (off is not None and o != off):
+            return None
+        off = o
+    return off
+
+
+def _conv_bn_forward(mod, spec, x, out, training, saved):
+    """conv -> BN (-> ReLU) of one layer, writing into ``out`` (an Act, possibly a channel slice)."""
+    conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
+    umma = mod._umma
+    wp, cp = mod._packed(spec.conv, 0)
+    to = x.T - spec.kt + 1
+    dev = x.buf.device
+    pad = (0, spec.pad, spec.pad)
+    if training:
+        raw = Act.empty(x.B, to, x.H, x.W, spec.cout, torch.float32, dev)
+        stats = torch.zeros(2 * spec.cout, dtype=torch.float32, device=dev)
+        if umma:
+            ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=True, stats=stats)
+        else:
+            ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=False)
+            ops.channel_stats(raw, stats)
+        bn4 = torch.empty(4 * spec.cout, dtype=torch.float32, device=dev)
+        track = bn.track_running_stats and bn.running_mean is not None
+        ops.bn_finalize(stats, raw.npix, conv.bias, bn.weight, bn.bias, bn.running_mean if track else None,
+                        bn.running_var if track else None, bn.num_batches_tracked if track else None,
+                        BN_MOMENTUM if bn.momentum is None else bn.momentum, bn.eps, bn4)
+        ops.affine_act(raw, out, bn4[:spec.cout], bn4[spec.cout:2 * spec.cout], spec.relu)
+        if saved is not None:
+            saved[spec.conv] = (raw, bn4)
+    else:
+        fold = torch.empty(2 * spec.cout, dtype=torch.float32, device=dev)
+        ops.bn_fold_eval(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, fold)
+        ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, out, umma=umma, relu=spec.relu, scale=fold[:spec.cout],
+                 shift=fold[spec.cout:])
+
+
+def _level_forward(mod, slow_in, fast_in, training, saved):
+    """One pyramid level (model.py:118-149 + the concat of :162).  Returns the merged f32 Act [B,1,H,W,256]."""
+    sp = mod._specs
+    dt_act = mod._act_dtype
+    dev = fast_in.buf.device
+    B, H, W = fast_in.B, fast_in.H, fast_in.W
+    t1s, t1f = slow_in.T - sp["slow_conv1"].kt + 1, fast_in.T - sp["fast_conv1"].kt + 1
+    t2s, t2f = t1s - sp["slow_conv2"].kt + 1, t1f - sp["fast_conv2"].kt + 1
+    # layer 1 (+ lateral 1 straight into channels 192..255 of the slow buffer)
+    f1 = Act.empty(B, t1f, H, W, 32, dt_act, dev)
+    s1 = Act.empty(B, t1s, H, W, 256, dt_act, dev)
+    _conv_bn_forward(mod, sp["slow_conv1"], slow_in, s1.slice(0, 192), training, saved)
+    _conv_bn_forward(mod, sp["fast_conv1"], fast_in, f1, training, saved)
+    _conv_bn_forward(mod, sp["conv_f2s1"], f1, s1.slice(192, 64), training, saved)
+    # layer 2
+    f2 = Act.empty(B, t2f, H, W, 32, dt_act, dev)
+    s2 = Act.empty(B, t2s, H, W, 256, dt_act, dev)
+    _conv_bn_forward(mod, sp["slow_conv2"], s1, s2.slice(0, 192), training, saved)
+    _conv_bn_forward(mod, sp["fast_conv2"], f1, f2, training, saved)
+    _conv_bn_forward(mod, sp["conv_f2s2"], f2, s2.slice(192, 64), training, saved)
+    # layer 3: both pathways land in one f32 [B,H,W,256] buffer = cat([slow, fast], 1).squeeze(2)
+    out = Act.empty(B, 1, H, W, 256, torch.float32, dev)
+    _conv_bn_forward(mod, sp["slow_conv3"], s2, out.slice(0, 224), training, saved)
+    _conv_bn_forward(mod, sp["fast_conv3"], f2, out.slice(224, 32), training, saved)
+    if saved is not None:
+        saved["_acts"] = dict(slow_in=slow_in, fast_in=fast_in, f1=f1, s1=s1, f2=f2, s2=s2)
+    return out
+
+
+def _layer_backward(mod, spec, dy, x_in, saved, grads, dx=None, dx_accumulate=False, need_dx=True):
+    """BN(+ReLU) backward -> weight gradient -> (optionally) data gradient of one layer.
+    dy: Act gradient wrt the layer's post-activation output; returns dx Act (f32) or None."""
+    conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
+    umma = mod._umma
+    raw, bn4 = saved[spec.conv]
+    dev = raw.buf.device
+    dconv = Act.empty(raw.B, raw.T, raw.H, raw.W, spec.cout, mod._act_dtype, dev)
+    dgamma = torch.zeros_like(bn.weight)
+    dbeta = torch.zeros_like(bn.bias)
+    ops.bn_bwd(dy, raw, bn4, bn.weight, spec.relu, dconv, dgamma, dbeta)
+    grads[spec.bn + ".weight"], grads[spec.bn + ".bias"] = dgamma, dbeta
+    pad = (0, spec.pad, spec.pad)
+    if conv.weight.requires_grad:
+        taps = spec.kt * spec.khw * spec.khw
+        dwp = torch.zeros(taps * spec.cin * spec.cout, dtype=torch.float32, device=dev)
+        ops.wgrad(x_in, dconv, spec.k, pad, dwp, umma=umma)
+        gw = torch.zeros_like(conv.weight)
+        ops.unpack_wgrad(dwp, gw, 0)
+        grads[spec.conv + ".weight"] = gw
+    if conv.bias is not None:
+        # a per-channel constant added before train-mode BN has exactly zero gradient
+        grads[spec.conv + ".bias"] = torch.zeros_like(conv.bias)
+    if not need_dx:
+        return None
+    wd, cpd = mod._packed(spec.conv, 1)
+    if dx is None:
+        dx = Act.empty(x_in.B, x_in.T, x_in.H, x_in.W, spec.cin, torch.float32, dev)
+    dpad = (spec.kt - 1, spec.khw - 1 - spec.pad, spec.khw - 1 - spec.pad)
+    ops.conv(dconv, wd, cpd, spec.cin, spec.k, dpad, x_in.T, dx, umma=umma, accumulate=dx_accumulate)
+    return dx
+
+
+def _level_backward(mod, saved, g_out, need_input_grad):
+    """g_out: f32 Act [B,1,H,W,256] = gradient of the merged output.  Returns ({param name: grad}, d_slow, d_fast)."""
+    sp = mod._specs
+    a = saved["_acts"]
+    grads = {}
+    d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, grads)
+    d_f2 = _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, grads)
+    _layer_backward(mod, sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], saved, grads, dx=d_f2, dx_accumulate=True)
+    d_s1 = _layer_backward(mod, sp["slow_conv2"], d_s2.slice(0, 192), a["s1"], saved, grads)
+    d_f1 = _layer_backward(mod, sp["fast_conv2"], d_f2, a["f1"], saved, grads)
+    _layer_backward(mod, sp["conv_f2s1"], d_s1.slice(192, 64), a["f1"], saved, grads, dx=d_f1, dx_accumulate=True)
+    d_slow = _layer_backward(mod, sp["slow_conv1"], d_s1.slice(0, 192), a["slow_in"], saved, grads, need_dx=need_input_grad)
+    d_fast = _layer_backward(mod, sp["fast_conv1"], d_f1, a["fast_in"], saved, grads, need_dx=need_input_grad)
+    return grads, d_slow, d_fast
+
+
+def _act_to_ncdhw(act):
+    out = torch.empty(act.B * act.T, act.C, act.H, act.W, dtype=torch.float32, device=act.buf.device)
+    ops.nhwc_to_nchw(act, out)
+    return out.view(act.B, act.T, act.C, act.H, act.W).permute(0, 2, 1, 3, 4)
+
+
+class _SlowFastLevelFn(torch.autograd.Function):
+    """forward(slow, fast) of one pyramid level with a hand-written backward over the saved raw conv outputs."""
+
+    @staticmethod
+    def forward(ctx, mod, slow_list, fast_list, slow5, fast5, *params):
+        ops.device_check()
+        dt_act = mod._act_dtype
+        if fast5 is not None:
+            fast_in = _to_act(fast5, dt_act)
+            slow_in = _to_act(slow5, dt_act)
+        else:
+            fast_in = _clips_to_act(fast_list, dt_act)
+            off = _alias_offset(slow_list, fast_list)
+            if off is not None:
+                slow_in = fast_in.frames(off, off + slow_list[0].shape[0])
+            else:
+                slow_in = _clips_to_act(slow_list, dt_act)
+        training = mod.training
+        want_grad = training and torch.is_grad_enabled() and (
+            any(p.requires_grad for p in params) or (fast5 is not None and (fast5.requires_grad or slow5.requires_grad)))
+        saved = {} if want_grad else None
+        out = _level_forward(mod, slow_in, fast_in, training, saved)
+        ctx.mod, ctx.saved_acts = mod, saved
+        ctx.need_input_grad = fast5 is not None and (fast5.requires_grad or slow5.requires_grad)
+        ctx.names = []
+        for s in mod._specs.values():
+            ctx.names.append(s.conv + ".weight")
+            if getattr(mod, s.conv).bias is not None:
+                ctx.names.append(s.conv + ".bias")
+            ctx.names.extend([s.bn + ".weight", s.bn + ".bias"])
+        merged = out.as_nchw()                      # [B,256,H,W] f32 view, channels_last strides
+        if saved is None:
+            ctx.mark_non_differentiable(merged)
+        return merged
+
+    @staticmethod
+    def backward(ctx, g):
+        mod, saved = ctx.mod, ctx.saved_acts
+        if saved is None:
+            raise RuntimeError("SlowFastLayers: backward needs a train-mode forward with grad enabled")
+        b, c, h, w = g.shape
+        gl = g.permute(0, 2, 3, 1)
+        if gl.is_contiguous() and g.dtype == torch.float32:
+            g_act = Act(gl.reshape(-1), b, 1, h, w, c, c, 0)
+        else:
+            g_act = Act.empty(b, 1, h, w, c, torch.float32, g.device)
+            ops.nchw_to_nhwc(g.float().contiguous(), g_act)
+        grads, d_slow, d_fast = _level_backward(mod, saved, g_act, ctx.need_input_grad)
+        ctx.saved_acts = None
+        g_slow = _act_to_ncdhw(d_slow) if d_slow is not None else None
+        g_fast = _act_to_ncdhw(d_fast) if d_fast is not None else None
+        return (None, None, None, g_slow, g_fast) + tuple(grads.get(n) for n in ctx.names)

@@ -1,0 +1,225 @@
+/* sfvos.h -- C ABI of libsfvos.so: the B200 (sm_100a) kernels behind the SlowFast-VOS hot path.
+ *
+ * The reference (ChantalMP/Applying-SlowFast-networks-to-video-object-segmentation) has no native code and no
+ * FFI: every entry point below replaces a *dependency kernel* the reference reaches through torch.nn /
+ * torchvision.ops.  The reference call site each one stands in for is cited per function
+ * (code/... = /root/reference/code/...; TV/... = torchvision 0.26).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host
+ *   - the caller owns every buffer; no entry point allocates device memory, frees, or synchronises
+ *   - every launch goes to the cudaStream_t passed as the last argument (0 = legacy default stream)
+ *   - return 0 on success; otherwise an SFVOS_ERR_* code, message via sfvos_last_error() (thread-local)
+ *   - there is NO CPU fallback: without an sm_100 device sfvos_device_check() fails and launches error out
+ *   - activations are channels-last: N(D)HWC, i.e. [B, T, H, W, C] with C contiguous; `cstride` arguments give
+ *     the element distance between consecutive pixels so a kernel can read/write a channel slice of a wider
+ *     (concatenated) buffer -- that is how torch.cat at code/helpers/model.py:115,162 disappears.
+ */
+#ifndef SFVOS_H
+#define SFVOS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFVOS_OK 0
+#define SFVOS_ERR_INVALID 1      /* bad argument / unsupported shape */
+#define SFVOS_ERR_CUDA 2         /* CUDA runtime / driver error */
+#define SFVOS_ERR_UNSUPPORTED 3  /* no sm_100 device */
+
+#define SFVOS_F32 0
+#define SFVOS_BF16 1
+
+typedef void* sfvos_stream;      /* cudaStream_t */
+
+int sfvos_version(void);
+const char* sfvos_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200).  No fallback exists. */
+int sfvos_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution (fprop and dgrad share one kernel).
+ * Replaces aten::conv3d / cudnn_convolution reached from nn.Conv3d at code/helpers/model.py:72-76,83-90
+ * (invoked :112,120,124,132,136,144,147) and aten::conv2d / conv_transpose2d of MaskRCNNHeads /
+ * MaskRCNNPredictor (TV/models/detection/mask_rcnn.py:284-296,342-344); the dgrad use replaces their
+ * autograd backward-data kernels.
+ *
+ *   y[b,t,h,w,n] = act( scale[n] * sum_{a,i,j,c} x[b, t+a-pad_t, h+i-pad_h, w+j-pad_w, c] * Wp[n, (a,i,j), c]
+ *                       + shift[n] )
+ * Out-of-range input coordinates read as zero (TMA out-of-bounds fill = the conv padding).  Spatial size is
+ * preserved (stride 1); To is the output temporal extent.
+ * Packed weights Wp (see sfvos_pack_weights): umma = bf16 [N][taps*Cp] (K-major), simt = f32 [taps*Cp][N].
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct sfvos_conv_params {
+    const void* x;            /* input activations, bf16 (umma) or f32 (simt), [B,T,H,W,*] */
+    int64_t B, T, H, W;
+    int64_t C;                /* input channels read per tap */
+    int64_t x_cstride;        /* elements between consecutive pixels (w -> w+1) of x (>= C) */
+    int64_t x_hstride, x_tstride, x_bstride;   /* element strides of the h / t / b axes; 0 = dense
+                                                  (W*cstride, H*W*cstride, T*H*W*cstride).  Non-dense strides let
+                                                  the ConvTranspose2d backward read every 2nd row/column of dy */
+    const void* w;            /* packed weights */
+    int64_t Cp;               /* per-tap K extent of the packed weights (C rounded up to 64 for umma) */
+    int64_t N;                /* output channels (multiple of 32, <= 256) */
+    int64_t kt, kh, kw;
+    int64_t pad_t, pad_h, pad_w;
+    int64_t To;
+    void* y;                  /* output, already offset to its first channel */
+    int32_t y_dtype;          /* SFVOS_F32 | SFVOS_BF16 */
+    int32_t relu;
+    int64_t y_cstride;
+    const float* scale;       /* optional [N] (NULL = 1) */
+    const float* shift;       /* optional [N] (NULL = 0) */
+    float* sum;               /* optional [N]: += column sums of the raw fp32 accumulators (train-mode BN stats) */
+    float* sumsq;             /* optional [N]: += column sums of squares */
+    int32_t accumulate;       /* y += result (f32 y only): merges the two gradient paths into the fast pathway */
+    int32_t reserved;
+    /* output pixel scatter (identity: OH=H, OW=W, mul=1, off=0); ConvTranspose2d k2 s2 uses mul=2, off=i|j */
+    int64_t OH, OW, oy_mul, oy_off, ox_mul, ox_off;
+} sfvos_conv_params;
+
+/* tcgen05/TMEM/TMA bf16 kernel (the product path). */
+int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream);
+/* fp32 CUDA-core kernel: the "fp32 validation mode" of the north star (<=1e-4), same semantics. */
+int sfvos_conv_simt(const sfvos_conv_params* p, sfvos_stream stream);
+
+/* Weight-gradient GEMM: dw[(a,i,j)][c][n] += sum_{b,t,h,w} x[b,t+a-pad_t,h+i-pad_h,w+j-pad_w,c] * dy[b,t,h,w,n].
+ * Replaces cudnn_convolution_backward_weight for the same modules.  dw is f32 [taps][C][N], accumulated. */
+typedef struct sfvos_wgrad_params {
+    const void* x;  int64_t B, T, H, W, C, x_cstride;
+    int64_t x_hstride, x_tstride, x_bstride;      /* 0 = dense */
+    const void* dy; int64_t To, N, dy_cstride;
+    int64_t dy_hstride, dy_tstride, dy_bstride;   /* 0 = dense, as for sfvos_conv_params.x_*stride */
+    int64_t kt, kh, kw, pad_t, pad_h, pad_w;
+    float* dw;
+} sfvos_wgrad_params;
+int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream);   /* x, dy bf16 */
+int sfvos_wgrad_simt(const sfvos_wgrad_params* p, sfvos_stream stream);   /* x, dy f32 */
+
+/* fp32 master weight [Cout,Cin,kt,kh,kw] (the state_dict tensor) -> packed operands.
+ *   mode 0 fprop : N=Cout, taps in (a,i,j) order, K=(tap,cin)
+ *   mode 1 dgrad : N=Cin, taps flipped, K=(tap',cout)            (input coord = out + tap' - (k-1-pad))
+ *   mode 2 convT : weight is [Cin,Cout,kh,kw] (ConvTranspose2d); packs the single tap (i,j)=(tap_i,tap_j):
+ *                  N=Cout, K=cin  (TV/models/detection/mask_rcnn.py:342)
+ *   mode 3 convT dgrad : N=Cin, K=cout for tap (tap_i,tap_j)
+ * out_dtype SFVOS_BF16 -> [N][taps*Cp]; SFVOS_F32 -> [taps*Cp][N].  Padding entries are written as zero. */
+int sfvos_pack_weights(const float* w, void* out, int32_t out_dtype, int32_t mode, int64_t Cout, int64_t Cin,
+                       int64_t kt, int64_t kh, int64_t kw, int64_t Cp, int64_t tap_i, int64_t tap_j,
+                       sfvos_stream stream);
+/* dw [taps][C][N] f32 -> grad += in the state_dict layout.  mode as above (0: [Cout=N,Cin=C,kt,kh,kw];
+ * 2: ConvTranspose2d [Cin=C,Cout=N,kh,kw] single tap (tap_i,tap_j) from a [1][C][N] dw). */
+int sfvos_unpack_wgrad(const float* dw, float* grad, int32_t mode, int64_t Cout, int64_t Cin, int64_t kt,
+                       int64_t kh, int64_t kw, int64_t tap_i, int64_t tap_j, sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BatchNorm3d pieces.  Replace aten::native_batch_norm (+backward) and aten::relu_ reached from
+ * nn.BatchNorm3d / nn.ReLU at code/helpers/model.py:69,78,92 (invoked :113-114,121-122,...,148).
+ * ------------------------------------------------------------------------------------------------------- */
+/* per-channel sum / sumsq over npix pixels of an f32 channels-last tensor (simt path; umma fuses this). */
+int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride, float* sum, float* sumsq,
+                        sfvos_stream stream);
+/* train: mean/var from (sum,sumsq,count) of the bias-free conv output; writes scale=gamma*rstd,
+ * shift=beta-mean*scale, mean, rstd; updates running stats with PyTorch's rules (momentum, unbiased var,
+ * conv bias added back to the mean) and num_batches_tracked += 1 (int64, may be NULL). */
+int sfvos_bn_finalize(const float* sum, const float* sumsq, double count, const float* conv_bias,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, double momentum, double eps, float* scale, float* shift,
+                      float* mean, float* rstd, int64_t C, sfvos_stream stream);
+/* eval: scale=gamma/sqrt(rv+eps), shift=beta+(conv_bias-rm)*scale. */
+int sfvos_bn_fold_eval(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, double eps, float* scale, float* shift, int64_t C,
+                       sfvos_stream stream);
+/* y = act(x*scale+shift) over a channels-last slice; x f32|bf16, y f32|bf16. */
+int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstride, void* y, int32_t y_dtype,
+                     int64_t y_cstride, const float* scale, const float* shift, int32_t relu, int64_t npix,
+                     int64_t C, sfvos_stream stream);
+/* BN(+ReLU) backward, pass 1: sums[0][c] += sum dy_m, sums[1][c] += sum dy_m*xhat, with
+ * dy_m = dy * (relu ? (x*scale+shift > 0) : 1), xhat = (x-mean)*rstd.  x is the saved raw conv output (f32). */
+int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
+                        const float* scale, const float* shift, const float* mean, const float* rstd,
+                        int32_t relu, int64_t npix, int64_t C, float* sums, sfvos_stream stream);
+/* pass 2: dx = gamma*rstd*(dy_m - sums0/n - xhat*sums1/n) written as bf16|f32; block 0 also does
+ * dgamma += sums1, dbeta += sums0 (may be NULL). */
+int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
+                       const float* scale, const float* shift, const float* mean, const float* rstd,
+                       const float* gamma, int32_t relu, int64_t npix, int64_t C, const float* sums, void* dx,
+                       int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, sfvos_stream stream);
+/* bias+ReLU layers (mask head): dx = dy * (y > 0) as bf16|f32 and dbias[c] += sum dx. */
+int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const void* y, int32_t y_dtype,
+                   int64_t y_cstride, void* dx, int32_t dx_dtype, int64_t dx_cstride, float* dbias, int64_t npix,
+                   int64_t C, sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Layout.  Replaces torch.stack(...).transpose(1,2) at code/helpers/model.py:157-158 and
+ * torch.cat(...).squeeze at :162 (the latter by writing both pathways into one channels-last buffer).
+ * ------------------------------------------------------------------------------------------------------- */
+/* src f32 [F, C, HW] (frame stride src_fstride elements) -> dst (f32|bf16) [F, HW, cstride]. */
+int sfvos_nchw_to_nhwc(const float* src, int64_t src_fstride, void* dst, int32_t dst_dtype, int64_t dst_cstride,
+                       int64_t F, int64_t C, int64_t HW, sfvos_stream stream);
+/* src (f32|bf16) [F, HW, cstride] -> dst f32 [F, C, HW]. */
+int sfvos_nhwc_to_nchw(const void* src, int32_t src_dtype, int64_t src_cstride, float* dst, int64_t F, int64_t C,
+                       int64_t HW, sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * ROIAlign (legacy aligned=False), multi-level, one launch for all levels.
+ * Replaces torch.ops.torchvision.roi_align / _roi_align_backward (TV/ops/roi_align.py:258) and the
+ * LevelMapper + per-level gather/scatter glue of MultiScaleRoIAlign (TV/ops/poolers.py:73-95,147-227), reached
+ * from code/helpers/model.py:346 via TV/models/detection/roi_heads.py:772,815.
+ * ------------------------------------------------------------------------------------------------------- */
+/* levels[k] = clamp(floor(4 + log2(sqrt(area)/224) + 1e-6), k_min, k_max) - k_min, fp32 like the reference. */
+int sfvos_roi_levels(const float* rois /*[K,5]*/, int64_t K, int32_t k_min, int32_t k_max, int32_t* levels,
+                     sfvos_stream stream);
+typedef struct sfvos_roi_params {
+    const void* feat[4];      /* per level, channels-last [N, H_l, W_l, C] (f32|bf16) */
+    void* dfeat[4];           /* backward only: f32 gradient buffers, same shape, pre-zeroed by the caller */
+    int64_t H[4], W[4];
+    float scale[4];
+    int32_t n_levels, feat_dtype;
+    int64_t N, C, cstride;    /* C multiple of 8 */
+    const float* rois;        /* [K,5] = (batch idx, x1, y1, x2, y2) in image pixels */
+    const int32_t* levels;    /* [K] from sfvos_roi_levels */
+    int64_t K;
+    int32_t P, sampling_ratio;   /* output P x P; sampling_ratio > 0 */
+    void* out;                /* fwd: output; bwd: grad of the output */
+    int32_t out_dtype;        /* SFVOS_F32 | SFVOS_BF16 */
+    int32_t out_nchw;         /* 0: [K,P,P,C] (feeds the mask head); 1: [K,C,P,P] (torch box head order) */
+} sfvos_roi_params;
+int sfvos_roi_align_fwd(const sfvos_roi_params* p, sfvos_stream stream);
+int sfvos_roi_align_bwd(const sfvos_roi_params* p, sfvos_stream stream);
+/* project_masks_on_boxes (TV/models/detection/roi_heads.py:85-97): masks u8 [n_obj,H,W], rois [K,5] with the
+ * matched object index in column 0, output f32 [K,M,M]; spatial_scale 1, adaptive sampling (sampling_ratio=-1). */
+int sfvos_mask_targets(const uint8_t* masks, int64_t n_obj, int64_t H, int64_t W, const float* rois, int64_t K,
+                       int32_t M, float* out, sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Mask predictor tail + loss.  Replaces mask_fcn_logits (1x1 conv 256->n_cls, TV/.../mask_rcnn.py:344),
+ * the class-channel gather and F.binary_cross_entropy_with_logits of maskrcnn_loss (TV/.../roi_heads.py:100-129)
+ * and the sigmoid/select of maskrcnn_inference (:56-82).
+ * ------------------------------------------------------------------------------------------------------- */
+/* x (bf16|f32) [K,S,S,C] -> logits f32 [K,n_cls,S,S] (NCHW like the reference). */
+int sfvos_mask_logits_fwd(const void* x, int32_t x_dtype, const float* w /*[n_cls,C]*/, const float* b,
+                          float* logits, int64_t K, int64_t S, int64_t C, int32_t n_cls, sfvos_stream stream);
+/* loss[0] = mean over K*S*S of BCE-with-logits(logits[k,labels[k]], targets[k]). */
+int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, const float* targets, float* loss, int64_t K,
+                       int64_t S, int32_t n_cls, sfvos_stream stream);
+/* backward of both: dlogit = gloss*(sigmoid(z)-t)/(K*S*S) on the label channel; dx (bf16|f32) [K,S,S,C];
+ * dw [n_cls,C] += , db [n_cls] += . */
+int sfvos_mask_logits_bce_bwd(const void* x, int32_t x_dtype, const float* w, const float* logits,
+                              const int64_t* labels, const float* targets, const float* gloss, void* dx,
+                              int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C,
+                              int32_t n_cls, sfvos_stream stream);
+/* maskrcnn_inference: prob[k,0,s,s] = sigmoid(logits[k,labels[k]]). */
+int sfvos_mask_probs(const float* logits, const int64_t* labels, float* prob, int64_t K, int64_t S, int32_t n_cls,
+                     sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimiser-side helpers for the data-parallel step (the one collective is NCCL all-reduce, called from Python).
+ * ------------------------------------------------------------------------------------------------------- */
+/* y[i] = a*x[i] + b*y[i]  (flat f32), used to fold 1/world_size into the reduced gradient bucket. */
+int sfvos_axpby(const float* x, float* y, float a, float b, int64_t n, sfvos_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFVOS_H */

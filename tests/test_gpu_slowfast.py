@@ -1,0 +1,135 @@
+"""GPU parity of the SlowFastLayers drop-in (through the C ABI) against the CPU oracle and the committed golden
+fixtures produced by the unmodified reference.  Metric: max|d| / max|ref| per tensor;
+<= 1e-4 in the fp32 validation mode, <= 1e-2 in bf16."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import slowfast_oracle as so
+
+pytestmark = pytest.mark.gpu
+LEVELS = OrderedDict([("0", (8, 12)), ("pool", (4, 6))])
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+def _nerr(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item() / (b.detach().abs().max().item() + 1e-12)
+
+
+def _inputs(sp, fp, levels=LEVELS, n_clips=2):
+    fast, slow = [], []
+    for clip in range(n_clips):
+        f = so.synthetic_clip(levels, fp, seed=1234 + 100 * clip, zero_left=(fp // 2 if clip == 1 else 0))
+        fast.append(f)
+        slow.append(so.slice_window(f, fp // 2, sp))
+    return slow, fast
+
+
+def _to_cuda(list_of_dicts):
+    return [OrderedDict((k, v.cuda()) for k, v in d.items()) for d in list_of_dicts]
+
+
+def _module(sp, fp, precision):
+    from sfvos_b200 import SlowFastLayers
+    torch.manual_seed(63)
+    m = SlowFastLayers(256, torch.device("cuda"), sp, fp).cuda()
+    m.precision = precision
+    return m
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("sp,fp", [(1, 8), (3, 7), (2, 16), (4, 32), (1, 1)])
+def test_train_forward_backward_matches_reference_golden(sp, fp, precision):
+    gold = np.load(os.path.join(GOLDEN, f"slowfast_sp{sp}_fp{fp}.npz"))
+    m = _module(sp, fp, precision).train()
+    assert sum(p.numel() for p in m.parameters()) == int(gold["n_params"])
+    slow, fast = _inputs(sp, fp)
+    # views into the fast clip, exactly like the reference's _slice_features (exercises the aliasing path)
+    fast_c = _to_cuda(fast)
+    slow_c = [so.slice_window(f, fp // 2, sp) for f in fast_c]
+    out = m.temporally_enhance_features(slow_c, fast_c)
+    tol = TOL[precision]
+    assert list(out.keys()) == list(LEVELS.keys())
+    for k, v in out.items():
+        ref = torch.from_numpy(gold["train_out_" + k])
+        assert v.shape == ref.shape and v.dtype == torch.float32
+        assert _nerr(v, ref) <= tol, (k, _nerr(v, ref))
+    loss = so.module_loss(out)
+    assert abs(loss.item() - float(gold["loss"])) <= tol * abs(float(gold["loss"]))
+    loss.backward()
+    # oracle gradients (full tensors) on CPU
+    sd = so.init_state_dict(sp, fp, seed=63)
+    _, _, grads, buffers = so.grads_of(sd, slow, fast)
+    gtol = 2e-3 if precision == "fp32" else 3e-2
+    for name, p in m.named_parameters():
+        ref = grads[name]
+        if name.endswith("conv1.bias") or name.endswith("conv2.bias") or name.endswith("conv3.bias"):
+            assert p.grad.abs().max().item() <= 1e-6 + 1e-3 * ref.abs().max().item()   # exactly zero through train BN
+            continue
+        assert _nerr(p.grad, ref) <= gtol, (name, _nerr(p.grad, ref))
+    btol = 1e-4 if precision == "fp32" else 5e-3
+    for name, b in m.named_buffers():
+        ref = torch.from_numpy(gold["buf_" + name])
+        if name.endswith("num_batches_tracked"):
+            assert int(b) == int(ref)
+        else:
+            assert _nerr(b, ref.float()) <= btol, (name, _nerr(b, ref.float()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("sp,fp", [(1, 8), (4, 32)])
+def test_eval_forward_matches_reference_golden(sp, fp, precision):
+    gold = np.load(os.path.join(GOLDEN, f"slowfast_sp{sp}_fp{fp}.npz"))
+    m = _module(sp, fp, precision)
+    sd = m.state_dict()
+    for k in sd:
+        if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+            sd[k] = torch.from_numpy(gold["buf_" + k]).to(sd[k].dtype)
+    m.load_state_dict(sd)
+    m.eval()
+    slow, fast = _inputs(sp, fp)
+    with torch.no_grad():
+        out = m.temporally_enhance_features(_to_cuda(slow), _to_cuda(fast))
+    for k, v in out.items():
+        assert _nerr(v, torch.from_numpy(gold["eval_out_" + k])) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_api_and_input_grads(precision):
+    """forward(slow, fast) on [B,C,T,H,W] tensors requiring grad (the OSVOS caller trains the backbone)."""
+    sp, fp = 3, 7
+    m = _module(sp, fp, precision).train()
+    g = torch.Generator().manual_seed(9)
+    fast = torch.randn(2, fp, 256, 6, 10, generator=g)
+    slow = fast[:, 2:5].clone()
+    sd = so.init_state_dict(sp, fp, seed=63)
+    fr, sr = fast.transpose(1, 2).clone().requires_grad_(True), slow.transpose(1, 2).clone().requires_grad_(True)
+    s_ref, f_ref = so.forward({k: v.clone() for k, v in sd.items()}, sr, fr, True)
+    (s_ref.square().mean() + f_ref.square().mean()).backward()
+    fc, sc = fast.cuda().transpose(1, 2).requires_grad_(True), slow.cuda().transpose(1, 2).requires_grad_(True)
+    s_out, f_out = m(sc, fc)
+    assert s_out.shape == s_ref.shape and f_out.shape == f_ref.shape
+    tol = TOL[precision]
+    assert _nerr(s_out, s_ref) <= tol and _nerr(f_out, f_ref) <= tol
+    (s_out.square().mean() + f_out.square().mean()).backward()
+    gtol = 2e-3 if precision == "fp32" else 3e-2
+    assert _nerr(fc.grad, fr.grad) <= gtol and _nerr(sc.grad, sr.grad) <= gtol
+
+
+def test_state_dict_roundtrip_and_no_cpu_fallback():
+    from sfvos_b200 import SlowFastLayers
+    m = _module(1, 8, "bf16")
+    ref_keys = list(so.init_state_dict(1, 8).keys())
+    assert list(m.state_dict().keys()) == ref_keys
+    m2 = SlowFastLayers(256, torch.device("cuda"), 1, 8).cuda()
+    m2.load_state_dict(m.state_dict())
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    cpu = SlowFastLayers(256, torch.device("cpu"), 1, 8)
+    x = torch.randn(1, 256, 8, 4, 6)
+    with pytest.raises(RuntimeError):
+        cpu(x[:, :, 4:5], x)
