@@ -148,7 +148,7 @@ class SlowFastLayers(nn.Module):
         """slow [B,256,sp,H,W], fast [B,256,fp,H,W] (any strides) -> (slow [B,224,1,H,W], fast [B,32,1,H,W])."""
         dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
         slow, fast = slow.to(dev), fast.to(dev)
-        merged = _SlowFastLevelFn.apply(self, None, None, slow, fast, *self._param_list())
+        merged = _SlowFastLevelFn.apply(self, torch.is_grad_enabled(), None, None, slow, fast, *self._param_list())
         b, _, h, w = merged.shape
         return merged[:, :224].unsqueeze(2), merged[:, 224:].unsqueeze(2)
 
@@ -164,9 +164,9 @@ class SlowFastLayers(nn.Module):
             if needs_grad:
                 s = torch.stack(slow_list).transpose(1, 2)
                 f = torch.stack(fast_list).transpose(1, 2)
-                merged[key] = _SlowFastLevelFn.apply(self, None, None, s, f, *params)
+                merged[key] = _SlowFastLevelFn.apply(self, True, None, None, s, f, *params)
             else:
-                merged[key] = _SlowFastLevelFn.apply(self, slow_list, fast_list, None, None, *params)
+                merged[key] = _SlowFastLevelFn.apply(self, torch.is_grad_enabled(), slow_list, fast_list, None, None, *params)
         return merged
 
 
@@ -335,7 +335,7 @@ class _SlowFastLevelFn(torch.autograd.Function):
     """forward(slow, fast) of one pyramid level with a hand-written backward over the saved raw conv outputs."""
 
     @staticmethod
-    def forward(ctx, mod, slow_list, fast_list, slow5, fast5, *params):
+    def forward(ctx, mod, grad_enabled, slow_list, fast_list, slow5, fast5, *params):
         ops.device_check()
         dt_act = mod._act_dtype
         if fast5 is not None:
@@ -349,7 +349,7 @@ class _SlowFastLevelFn(torch.autograd.Function):
             else:
                 slow_in = _clips_to_act(slow_list, dt_act)
         training = mod.training
-        want_grad = training and torch.is_grad_enabled() and (
+        want_grad = training and grad_enabled and (
             any(p.requires_grad for p in params) or (fast5 is not None and (fast5.requires_grad or slow5.requires_grad)))
         saved = {} if want_grad else None
         out = _level_forward(mod, slow_in, fast_in, training, saved)
@@ -382,4 +382,4 @@ class _SlowFastLevelFn(torch.autograd.Function):
         ctx.saved_acts = None
         g_slow = _act_to_ncdhw(d_slow) if d_slow is not None else None
         g_fast = _act_to_ncdhw(d_fast) if d_fast is not None else None
-        return (None, None, None, g_slow, g_fast) + tuple(grads.get(n) for n in ctx.names)
+        return (None, None, None, None, g_slow, g_fast) + tuple(grads.get(n) for n in ctx.names)

@@ -157,7 +157,7 @@ def test_wgrad(cin, cout, kt, khw, T, H, W, umma):
     taps = kt * khw * khw
     dwp = torch.zeros(taps * cin * cout, device=DEV)
     ops.wgrad(xa, dya, (kt, khw, khw), (0, pad, pad), dwp, umma=umma)
-    gw = torch.zeros_like(dw_ref)
+    gw = torch.zeros(dw_ref.shape, device=DEV)
     ops.unpack_wgrad(dwp, gw, 0)
     assert _err(gw, dw_ref) < 5e-5
 
