@@ -165,8 +165,15 @@ def synthetic_clip(level_shapes, fp, seed=1234, zero_left=0, scale=1.0):
 
 
 def module_loss(merged):
-    """Module-only scalar used to seed gradients in benches/tests: sum_l mean(out_l^2)."""
-    return sum((v * v).mean() for v in merged.values())
+    """Module-only scalar used to seed gradients in tests/benches: sum_l mean(out_l * r_l) with a fixed seeded
+    random projection r_l.  (A plain sum_l mean(out_l^2), as SURVEY 8(d) suggests for benches, is invariant under
+    the final BatchNorm -- its true gradient is zero -- so it cannot pin a backward pass.)"""
+    total = 0
+    for i, v in enumerate(merged.values()):
+        g = torch.Generator().manual_seed(777 + i)
+        r = torch.randn(v.shape, generator=g).to(v.device)
+        total = total + (v * r).mean()
+    return total
 
 
 def grads_of(sd, slow_features, fast_features, loss_fn=module_loss):

@@ -59,7 +59,7 @@ def test_train_forward_backward_matches_reference_golden(sp, fp, precision):
         assert v.shape == ref.shape and v.dtype == torch.float32
         assert _nerr(v, ref) <= tol, (k, _nerr(v, ref))
     loss = so.module_loss(out)
-    assert abs(loss.item() - float(gold["loss"])) <= tol * abs(float(gold["loss"]))
+    assert abs(loss.item() - float(gold["loss"])) <= tol
     loss.backward()
     # oracle gradients (full tensors) on CPU
     sd = so.init_state_dict(sp, fp, seed=63)
@@ -109,13 +109,14 @@ def test_forward_api_and_input_grads(precision):
     sd = so.init_state_dict(sp, fp, seed=63)
     fr, sr = fast.transpose(1, 2).clone().requires_grad_(True), slow.transpose(1, 2).clone().requires_grad_(True)
     s_ref, f_ref = so.forward({k: v.clone() for k, v in sd.items()}, sr, fr, True)
-    (s_ref.square().mean() + f_ref.square().mean()).backward()
+    rs, rf = torch.randn(s_ref.shape, generator=g), torch.randn(f_ref.shape, generator=g)
+    ((s_ref * rs).mean() + (f_ref * rf).mean()).backward()
     fc, sc = fast.cuda().transpose(1, 2).requires_grad_(True), slow.cuda().transpose(1, 2).requires_grad_(True)
     s_out, f_out = m(sc, fc)
     assert s_out.shape == s_ref.shape and f_out.shape == f_ref.shape
     tol = TOL[precision]
     assert _nerr(s_out, s_ref) <= tol and _nerr(f_out, f_ref) <= tol
-    (s_out.square().mean() + f_out.square().mean()).backward()
+    ((s_out * rs.cuda()).mean() + (f_out * rf.cuda()).mean()).backward()
     gtol = 2e-3 if precision == "fp32" else 3e-2
     assert _nerr(fc.grad, fr.grad) <= gtol and _nerr(sc.grad, sr.grad) <= gtol
 
