@@ -1,5 +1,8 @@
 """Public API of the product package (re-exported by the ``sfvos_b200`` alias)."""
+from . import _lib, ops  # noqa: F401
 from .slowfast import SlowFastLayers  # noqa: F401
-from . import ops, _lib  # noqa: F401
+from .roi_heads import (MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, RoIHeads, install,  # noqa: F401
+                        maskrcnn_inference, maskrcnn_loss, project_masks_on_boxes)
 
-__all__ = ["SlowFastLayers", "ops", "_lib"]
+__all__ = ["SlowFastLayers", "MultiScaleRoIAlign", "MaskRCNNHeads", "MaskRCNNPredictor", "RoIHeads", "install",
+           "maskrcnn_loss", "maskrcnn_inference", "project_masks_on_boxes", "ops", "_lib"]

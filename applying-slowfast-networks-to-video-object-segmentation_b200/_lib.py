@@ -62,7 +62,8 @@ _SIGS = {
     "sfvos_mask_targets": [vp, i64, i64, i64, vp, i64, i32, vp, vp],
     "sfvos_mask_logits_fwd": [vp, i32, vp, vp, vp, i64, i64, i64, i32, vp],
     "sfvos_mask_bce_fwd": [vp, vp, vp, vp, i64, i64, i32, vp],
-    "sfvos_mask_logits_bce_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i64, i64, i64, i32, vp],
+    "sfvos_mask_logits_bwd": [vp, i32, vp, vp, vp, i32, vp, vp, i64, i64, i64, i32, vp],
+    "sfvos_mask_bce_bwd": [vp, vp, vp, vp, vp, i64, i64, i32, vp],
     "sfvos_mask_probs": [vp, vp, vp, i64, i64, i32, vp],
     "sfvos_axpby": [vp, vp, f32, f32, i64, vp],
 }

@@ -78,49 +78,70 @@ mask_bce_fwd_kernel(const float* __restrict__ logits, const long long* __restric
     }
 }
 
-// one CTA per ROI (8 warps stride over its S*S pixels): dx = dz * w[label], dw[label] += dz * x, db[label] += dz
+// one CTA per ROI (8 warps stride over its S*S pixels): dx = sum_cls g_cls * w[cls], dw[cls] += g_cls * x, db[cls] += g_cls
 template <typename XT, typename DxT>
 __global__ void __launch_bounds__(256)
-mask_logits_bce_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ logits,
-                           const long long* __restrict__ labels, const float* __restrict__ targets,
-                           const float* __restrict__ gloss, DxT* dx, float* dw, float* db, long long K, int S, int C, int n_cls) {
-    extern __shared__ float s_dw[];          // [8 warps][C]
-    __shared__ float s_db[8];
+mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ glogits, DxT* dx,
+                       float* dw, float* db, long long K, int S, int C, int n_cls) {
+    extern __shared__ float s_dw[];          // [8 warps][n_cls][C]
+    __shared__ float s_db[8][MAX_CLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long k = blockIdx.x;
-    const int label = (int)labels[k];
     const int ss = S * S;
-    const float g = gloss[0] / (float)(K * ss);
-    float dbacc = 0.f;
-    for (int c8 = lane; c8 < C / 8; c8 += 32) {      // C <= 256 -> at most one iteration per lane
-        float wv[8], dwacc[8] = {};
-        ld8(w + (long long)label * C + c8 * 8, wv);
-        for (int p = warp; p < ss; p += 8) {
-            const float z = logits[(k * n_cls + label) * ss + p];
-            const float t = targets[k * ss + p];
-            const float dz = g * (1.f / (1.f + expf(-z)) - t);
-            float v[8], o[8];
-            ld8(x + (k * ss + p) * C + c8 * 8, v);
+    float dbacc[MAX_CLS] = {};
+    for (int c8 = lane; c8 < C / 8; c8 += 32) {
+        for (int cls0 = 0; cls0 < n_cls; cls0 += 2) {            // two classes per pass keeps registers bounded
+            const int ncl = min(2, n_cls - cls0);
+            float wv[2][8], dwacc[2][8] = {};
+            for (int q = 0; q < ncl; ++q) ld8(w + (long long)(cls0 + q) * C + c8 * 8, wv[q]);
+            for (int p = warp; p < ss; p += 8) {
+                float v[8], o[8];
+                ld8(x + (k * ss + p) * C + c8 * 8, v);
+                if (cls0 == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { o[j] = dz * wv[j]; dwacc[j] = fmaf(dz, v[j], dwacc[j]); }
-            st8(dx + (k * ss + p) * C + c8 * 8, o);
-            if (c8 == 0) dbacc += dz;
+                    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+                } else {
+                    ld8(dx + (k * ss + p) * C + c8 * 8, o);
+                }
+                for (int q = 0; q < ncl; ++q) {
+                    const float g = glogits[(k * n_cls + cls0 + q) * ss + p];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { o[j] = fmaf(g, wv[q][j], o[j]); dwacc[q][j] = fmaf(g, v[j], dwacc[q][j]); }
+                    if (c8 == 0) dbacc[cls0 + q] += g;
+                }
+                st8(dx + (k * ss + p) * C + c8 * 8, o);
+            }
+            for (int q = 0; q < ncl; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s_dw[(warp * n_cls + cls0 + q) * C + c8 * 8 + j] = dwacc[q][j];
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s_dw[warp * C + c8 * 8 + j] = dwacc[j];
     }
-    if (lane == 0) s_db[warp] = dbacc;
+    if (lane == 0)
+        for (int q = 0; q < n_cls; ++q) s_db[warp][q] = dbacc[q];
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int i = threadIdx.x; i < n_cls * C; i += blockDim.x) {
         float s = 0.f;
-        for (int i = 0; i < 8; ++i) s += s_dw[i * C + c];
-        atomicAdd(dw + (long long)label * C + c, s);
+        for (int wi = 0; wi < 8; ++wi) s += s_dw[wi * n_cls * C + i];
+        atomicAdd(dw + i, s);
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < n_cls) {
         float s = 0.f;
-        for (int i = 0; i < 8; ++i) s += s_db[i];
-        atomicAdd(db + label, s);
+        for (int wi = 0; wi < 8; ++wi) s += s_db[wi][threadIdx.x];
+        atomicAdd(db + threadIdx.x, s);
     }
+}
+
+// glogits[k, cls, p] = (cls == labels[k]) ? gloss * (sigmoid(z) - t) / (K*S*S) : 0
+__global__ void mask_bce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                    const float* __restrict__ targets, const float* __restrict__ gloss, float* glogits,
+                                    long long K, int S, int n_cls) {
+    const long long ss = (long long)S * S, total = K * n_cls * ss;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long p = i % ss, cls = (i / ss) % n_cls, k = i / (ss * n_cls);
+    float g = 0.f;
+    if (cls == labels[k]) g = gloss[0] / (float)(K * ss) * (1.f / (1.f + expf(-logits[i])) - targets[k * ss + p]);
+    glogits[i] = g;
 }
 
 __global__ void mask_probs_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, float* prob,
@@ -160,19 +181,27 @@ extern "C" int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, co
     return SFVOS_OK;
 }
 
-extern "C" int sfvos_mask_logits_bce_bwd(const void* x, int32_t x_dtype, const float* w, const float* logits,
-                                         const int64_t* labels, const float* targets, const float* gloss, void* dx,
-                                         int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C,
-                                         int32_t n_cls, sfvos_stream stream) {
-    SF_CHECK(C % 8 == 0 && C <= 256 * 8, "mask_logits_bce_bwd: unsupported C");
-    SF_CHECK(x_dtype == dx_dtype, "mask_logits_bce_bwd: x and dx must share a dtype");
+extern "C" int sfvos_mask_logits_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
+                                     int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C,
+                                     int32_t n_cls, sfvos_stream stream) {
+    SF_CHECK(C % 8 == 0 && n_cls >= 1 && n_cls <= MAX_CLS, "mask_logits_bwd: C %% 8 == 0 and n_cls <= 8 required");
+    SF_CHECK(x_dtype == dx_dtype, "mask_logits_bwd: x and dx must share a dtype");
     if (K == 0) return SFVOS_OK;
-    const size_t sm = (size_t)8 * C * sizeof(float);
-    const long long* lab = reinterpret_cast<const long long*>(labels);
+    const size_t sm = (size_t)8 * n_cls * C * sizeof(float);
+    SF_CHECK(sm <= 48 * 1024, "mask_logits_bwd: n_cls*C too large");
     if (x_dtype == SFVOS_BF16)
-        mask_logits_bce_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, logits, lab, targets, gloss, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, K, (int)S, (int)C, n_cls);
     else
-        mask_logits_bce_bwd_kernel<float, float><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, logits, lab, targets, gloss, reinterpret_cast<float*>(dx), dw, db, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<float, float><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, K, (int)S, (int)C, n_cls);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_mask_bce_bwd(const float* logits, const int64_t* labels, const float* targets, const float* gloss,
+                                  float* glogits, int64_t K, int64_t S, int32_t n_cls, sfvos_stream stream) {
+    if (K == 0) return SFVOS_OK;
+    const long long total = K * n_cls * S * S;
+    mask_bce_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, CS(stream)>>>(logits, reinterpret_cast<const long long*>(labels), targets, gloss, glogits, K, (int)S, n_cls);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

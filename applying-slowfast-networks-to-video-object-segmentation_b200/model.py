@@ -1,0 +1,170 @@
+"""SegmentationModel -- the caller of the hot path, mirroring code/helpers/model.py:168-389 (same constructor,
+attributes, helper-method names, forward contract) with SlowFastLayers and the ROIAlign / mask branch running on
+libsfvos.so.  The frozen backbone, RPN, transform and box head are torchvision modules used as-is.
+
+``from helpers.model import SegmentationModel`` keeps working for the reference's train.py / prediction.py through
+the shim package in ``compat/helpers``."""
+import os
+import warnings
+from collections import OrderedDict
+from math import ceil, floor
+
+import torch
+import torchvision
+from torch import nn
+from torchvision.models.detection.faster_rcnn import FastRCNNPredictor
+from torchvision.models.detection.image_list import ImageList
+
+from . import roi_heads as sf_roi_heads
+from .roi_heads import MaskRCNNPredictor
+from .slowfast import SlowFastLayers
+
+
+def get_model_instance_segmentation(num_classes, pretrained=True):
+    """code/helpers/model.py:12-27.  ``pretrained`` weights need the torchvision hub cache; offline we fall back to
+    random init with FrozenBatchNorm2d so the parameter count matches the reference's report."""
+    kwargs = {}
+    if pretrained:
+        try:
+            model = torchvision.models.detection.maskrcnn_resnet50_fpn(weights="DEFAULT")
+        except Exception as exc:  # no network / no cache
+            warnings.warn(f"pretrained Mask R-CNN weights unavailable ({exc.__class__.__name__}); using random init")
+            pretrained = False
+    if not pretrained:
+        kwargs = dict(weights=None, weights_backbone=None, norm_layer=torchvision.ops.misc.FrozenBatchNorm2d)
+        try:
+            model = torchvision.models.detection.maskrcnn_resnet50_fpn(**kwargs)
+        except TypeError:
+            kwargs.pop("norm_layer")
+            model = torchvision.models.detection.maskrcnn_resnet50_fpn(**kwargs)
+    in_features = model.roi_heads.box_predictor.cls_score.in_features
+    model.roi_heads.box_predictor = FastRCNNPredictor(in_features, num_classes)
+    in_features_mask = model.roi_heads.mask_predictor.conv5_mask.in_channels
+    model.roi_heads.mask_predictor = MaskRCNNPredictor(in_features_mask, 256, num_classes)
+    return model
+
+
+class SegmentationModel(nn.Module):
+    def __init__(self, device, slow_pathway_size, fast_pathway_size, maskrcnn_weights='maskrcnn/maskrcnn_model.pth',
+                 pretrained=True):
+        super().__init__()
+        self.device = device
+        self.maskrcnn_model = get_model_instance_segmentation(num_classes=2, pretrained=pretrained)
+        if maskrcnn_weights and os.path.exists(maskrcnn_weights):
+            self.maskrcnn_model.load_state_dict(torch.load(maskrcnn_weights, map_location="cpu"))
+        elif maskrcnn_weights:
+            warnings.warn(f"{maskrcnn_weights} not found; Mask R-CNN keeps its initial weights")
+        for param in self.maskrcnn_model.backbone.parameters():
+            param.requires_grad = False
+        for param in self.maskrcnn_model.rpn.parameters():
+            param.requires_grad = False
+        self.slow_pathway_size = slow_pathway_size
+        self.fast_pathway_size = fast_pathway_size
+        self.slow_fast = SlowFastLayers(256, device=device, slow_pathway_size=slow_pathway_size,
+                                        fast_pathway_size=fast_pathway_size)
+        self.maskrcnn_model.roi_heads.detections_per_img = 10
+        sf_roi_heads.install(self.maskrcnn_model.roi_heads)      # same parameters, libsfvos kernels
+        self.features_cache = {}
+        self.use_caching = True
+
+    # ---- feature cache / windowing (model.py:191-273) ----------------------------------------------------------------
+    def compute_maskrcnn_features(self, images_tensors, indices):
+        n = len(images_tensors)
+        for key in [k for k in self.features_cache if k < indices[0]]:
+            self.features_cache.pop(key)
+        per_frame = []
+        for idx in indices:
+            if not 0 <= idx < n:
+                continue
+            if self.use_caching and idx in self.features_cache:
+                feats = self._detach_features(self.features_cache[idx])
+            else:
+                feats = self.maskrcnn_model.backbone(images_tensors[idx:idx + 1].to(self.device))
+                if self.use_caching:
+                    self.features_cache[idx] = feats
+            per_frame.append(feats)
+        left = sum(1 for i in indices if i < 0)
+        right = sum(1 for i in indices if i >= n)
+        out = OrderedDict()
+        for key in per_frame[0].keys():
+            stacked = torch.cat([f[key] for f in per_frame])
+            if left or right:        # out-of-sequence frames are all-zero feature maps (model.py:215-225)
+                pad_l = stacked.new_zeros((left,) + stacked.shape[1:])
+                pad_r = stacked.new_zeros((right,) + stacked.shape[1:])
+                stacked = torch.cat([pad_l, stacked, pad_r])
+            out[key] = stacked
+        return out
+
+    def batch_slice_features(self, features, begin, end):
+        return OrderedDict((k, v[begin:end].to(self.device)) for k, v in features.items())
+
+    def compute_rpn_proposals(self, image_tensors, image_sizes, features, target):
+        batch_imgs = ImageList(image_tensors.to(self.device), image_sizes)
+        return self.maskrcnn_model.rpn(batch_imgs, features, target)
+
+    def _slice_features(self, features, image_feature_idx, pathway_size):
+        lo = image_feature_idx - floor(pathway_size / 2)
+        hi = image_feature_idx + ceil(pathway_size / 2)
+        return OrderedDict((k, v[lo:hi]) for k, v in features.items())
+
+    def _targets_to_device(self, targets, device):
+        return [OrderedDict((k, v.to(device)) for k, v in t.items()) for t in targets]
+
+    def _index_features(self, features, i_begin, i_end):
+        return OrderedDict((k, v[i_begin:i_end]) for k, v in features.items())
+
+    def _detach_features(self, features):
+        return OrderedDict((k, v.detach()) for k, v in features.items())
+
+    # ---- forward (model.py:275-389) --------------------------------------------------------------------------------------
+    def forward(self, images, targets=None, optimizer=None):
+        self.features_cache = {}
+        original_image_sizes = [tuple(img.shape[-2:]) for img in images]
+        transformed_images, _ = self.maskrcnn_model.transform(images)
+
+        valid = [int('boxes' in targets[i] and len(targets[i]['boxes']) > 0) for i in range(len(transformed_images.tensors))]
+        valid_imgs = [images[i] for i, v in enumerate(valid) if v]
+        valid_targets = [targets[i] for i, v in enumerate(valid) if v]
+        _, t_targets = self.maskrcnn_model.transform(valid_imgs, valid_targets)
+        it = iter(t_targets)
+        targets = [next(it) if v else {} for v in valid]
+        images = transformed_images
+
+        total_loss = 0.
+        all_detections = []
+        count = 0
+        half_lo, half_hi = floor(self.fast_pathway_size / 2), ceil(self.fast_pathway_size / 2)
+        centre = self.fast_pathway_size // 2
+        for idx, ok in enumerate(valid):
+            if not ok:
+                continue
+            indices = range(idx - half_lo, idx + half_hi)
+            with torch.no_grad():
+                window = self.compute_maskrcnn_features(transformed_images.tensors, indices)
+            centre_feats = self._index_features(window, centre, centre + 1)
+            target = self._targets_to_device(targets[idx:idx + 1], self.device)
+            with torch.no_grad():
+                rpn_proposals, proposal_losses = self.compute_rpn_proposals(
+                    transformed_images.tensors[idx:idx + 1], transformed_images.image_sizes[idx:idx + 1], centre_feats, target)
+            target[0]['proposals'] = rpn_proposals[0]
+            slow_valid = [self._slice_features(window, centre, self.slow_pathway_size)]
+            fast_valid = [window]
+            slow_fast_features = self.slow_fast.temporally_enhance_features(slow_valid, fast_valid)
+            batch_original_sizes = original_image_sizes[idx:idx + 1]
+            batch_image_sizes = images.image_sizes[0:1] * len(batch_original_sizes)
+            proposals = [t['proposals'] for t in target]
+            detections, detector_losses = self.maskrcnn_model.roi_heads(slow_fast_features, proposals, batch_image_sizes, target)
+            detections = self.maskrcnn_model.transform.postprocess(detections, batch_image_sizes, batch_original_sizes)
+            all_detections.extend(self._targets_to_device(detections, torch.device('cpu')))
+            if self.training:
+                losses = sum(list(detector_losses.values()) + list(proposal_losses.values()))
+                total_loss += losses.item()
+                losses.backward()
+                count += 1
+                if count % 2 == 0:
+                    optimizer.step()
+                    optimizer.zero_grad()
+        if not self.training:
+            it = iter(all_detections)
+            all_detections = [next(it) if v else {} for v in valid]
+        return (total_loss, all_detections)

@@ -1,0 +1,425 @@
+"""ROIAlign + mask branch on libsfvos.so, behind torchvision's own module interfaces.
+
+The reference reaches this arithmetic at code/helpers/model.py:346 (``self.maskrcnn_model.roi_heads(...)``); the
+modules below keep torchvision's constructor arguments, call signatures and state_dict keys so they can be swapped
+into ``maskrcnn_model.roi_heads`` (see ``install`` and INTEGRATION.md):
+
+  MultiScaleRoIAlign   <- torchvision.ops.MultiScaleRoIAlign            (TV/ops/poolers.py:230-321)
+  MaskRCNNHeads        <- torchvision...mask_rcnn.MaskRCNNHeads          (TV/models/detection/mask_rcnn.py:271-303)
+  MaskRCNNPredictor    <- torchvision...mask_rcnn.MaskRCNNPredictor      (TV/models/detection/mask_rcnn.py:337-353)
+  maskrcnn_loss / maskrcnn_inference <- TV/models/detection/roi_heads.py:56-129
+  RoIHeads             <- torchvision...roi_heads.RoIHeads.forward       (TV/models/detection/roi_heads.py:739-887)
+
+Tensors exchanged between these modules keep torchvision's logical shapes ([K,C,P,P]) but are channels_last in
+memory and bf16 on the product path (fp32 when ``precision == "fp32"``), which is what the tensor-core kernels
+consume directly.  Box sampling, box head, box losses and NMS stay torchvision/torch (SURVEY 8(f) "next").
+"""
+import math
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn, Tensor
+from torchvision.models.detection import mask_rcnn as tv_mask_rcnn
+from torchvision.models.detection import roi_heads as tv_roi_heads
+from torchvision.ops import boxes as box_ops
+
+from . import ops
+from ._lib import BF16, F32, call
+from .ops import Act, _p, stream
+
+
+def _default_precision():
+    return os.environ.get("SFVOS_PRECISION", "bf16")
+
+
+def _act_dtype(precision):
+    return torch.float32 if precision == "fp32" else torch.bfloat16
+
+
+def _is_channels_last(x):
+    return x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous()
+
+
+def _nchw_view(buf, K, H, W, C):
+    """[K,C,H,W]-shaped view (channels_last strides) of a flat channels-last buffer."""
+    return buf.view(K, H, W, C).permute(0, 3, 1, 2)
+
+
+def _to_cl_act(x, dtype):
+    """[K,C,H,W] tensor of any layout/dtype -> dense channels-last Act [K,1,H,W,C] in ``dtype`` (zero-copy if possible)."""
+    K, C, H, W = x.shape
+    if _is_channels_last(x) and x.dtype == dtype:
+        return Act(x.permute(0, 2, 3, 1).reshape(-1), K, 1, H, W, C)
+    act = Act.empty(K, 1, H, W, C, dtype, x.device)
+    if K:
+        ops.nchw_to_nhwc(x.float().contiguous(), act)
+    return act
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# MultiScaleRoIAlign
+# ----------------------------------------------------------------------------------------------------------------------
+class _RoiAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rois, levels, scales, P, sr, out_nchw, out_dtype, *feats):
+        ops.device_check()
+        N, C = feats[0].shape[:2]
+        shapes = [tuple(f.shape[-2:]) for f in feats]
+        cl = []
+        for f in feats:                                    # channels-last f32 (the SlowFast output already is)
+            if _is_channels_last(f) and f.dtype == torch.float32:
+                cl.append(f.permute(0, 2, 3, 1))
+            else:
+                a = Act.empty(N, 1, f.shape[2], f.shape[3], C, torch.float32, f.device)
+                ops.nchw_to_nhwc(f.float().contiguous(), a)
+                cl.append(a.buf)
+        K = rois.shape[0]
+        if out_nchw:
+            out = torch.empty(K, C, P, P, dtype=out_dtype, device=rois.device)
+        else:
+            out = torch.empty(K, P, P, C, dtype=out_dtype, device=rois.device)
+        if K:
+            ops.roi_align_fwd(cl, shapes, scales, N, C, rois, levels, P, sr, out, out_nchw)
+        ctx.save_for_backward(rois, levels)
+        ctx.meta = (shapes, scales, N, C, P, sr, out_nchw, [f.dtype for f in feats])
+        return out if out_nchw else out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        rois, levels = ctx.saved_tensors
+        shapes, scales, N, C, P, sr, out_nchw, dtypes = ctx.meta
+        dfeats = [torch.zeros(N, h, w, C, dtype=torch.float32, device=g.device) for (h, w) in shapes]
+        if rois.shape[0]:
+            if out_nchw:
+                gg = g if g.dtype in (torch.float32, torch.bfloat16) else g.float()
+                gg = gg.contiguous()
+            else:
+                gl = g.permute(0, 2, 3, 1)
+                gg = gl if gl.is_contiguous() else gl.contiguous()
+            ops.roi_align_bwd(dfeats, shapes, scales, N, C, rois, levels, P, sr, gg, out_nchw)
+        grads = tuple(d.permute(0, 3, 1, 2).to(dt) for d, dt in zip(dfeats, dtypes))
+        return (None,) * 7 + grads
+
+
+class MultiScaleRoIAlign(nn.Module):
+    """Same arguments and call signature as torchvision.ops.MultiScaleRoIAlign (aligned=False legacy ROIAlign).
+    ``out_layout="nchw"`` returns a contiguous f32 [K,C,P,P] (what the torch box head flattens);
+    ``out_layout="nhwc"`` returns the same logical shape with channels_last strides in the activation dtype."""
+
+    def __init__(self, featmap_names: List[str], output_size, sampling_ratio: int, *, canonical_scale: int = 224,
+                 canonical_level: int = 4, out_layout: str = "nchw", precision: Optional[str] = None):
+        super().__init__()
+        if isinstance(output_size, int):
+            output_size = (output_size, output_size)
+        assert output_size[0] == output_size[1], "square pooling only"
+        self.featmap_names = featmap_names
+        self.sampling_ratio = sampling_ratio
+        self.output_size = tuple(output_size)
+        self.scales = None
+        self.map_levels = None
+        self.canonical_scale = canonical_scale
+        self.canonical_level = canonical_level
+        self.out_layout = out_layout
+        self.precision = precision or _default_precision()
+
+    def _setup_scales(self, feats, image_shapes):
+        max_h = max(s[0] for s in image_shapes)
+        self.scales = [2.0 ** float(round(math.log2(float(f.shape[-2]) / float(max_h)))) for f in feats]
+        self.k_min = int(-math.log2(self.scales[0]))
+        self.k_max = int(-math.log2(self.scales[-1]))
+
+    def forward(self, x: Dict[str, Tensor], boxes: List[Tensor], image_shapes: List[Tuple[int, int]]) -> Tensor:
+        feats = [v for k, v in x.items() if k in self.featmap_names]
+        if self.scales is None:
+            self._setup_scales(feats, image_shapes)
+        dev = feats[0].device
+        ids = torch.cat([torch.full((b.shape[0], 1), float(i), dtype=torch.float32, device=dev) for i, b in enumerate(boxes)])
+        rois = torch.cat([ids, torch.cat(boxes).to(device=dev, dtype=torch.float32)], dim=1).contiguous()
+        levels = ops.roi_levels(rois, self.k_min, self.k_max) if len(feats) > 1 else None
+        nchw = self.out_layout == "nchw"
+        out_dtype = torch.float32 if nchw else _act_dtype(self.precision)
+        return _RoiAlignFn.apply(rois, levels, self.scales, self.output_size[0], self.sampling_ratio, nchw, out_dtype, *feats)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# mask head: 4 x (conv3x3 + bias + ReLU) on [K,256,14,14]
+# ----------------------------------------------------------------------------------------------------------------------
+def _pack(w, mode, umma, kc, tap=(0, 0)):
+    cp = (kc + 63) // 64 * 64 if umma else kc
+    return ops.pack_weights(w, mode, BF16 if umma else F32, cp, tap), cp
+
+
+class _MaskHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, precision, *wb):
+        ops.device_check()
+        umma = precision != "fp32"
+        dt_act = _act_dtype(precision)
+        K, C, H, W = x.shape
+        cur = _to_cl_act(x, dt_act)
+        acts = [cur]
+        for i in range(len(wb) // 2):
+            w, b = wb[2 * i], wb[2 * i + 1]
+            wp, cp = _pack(w, 0, umma, w.shape[1])
+            y = Act.empty(K, 1, H, W, w.shape[0], dt_act, x.device)
+            if K:
+                ops.conv(cur, wp, cp, w.shape[0], (1, 3, 3), (0, 1, 1), 1, y, umma=umma, relu=True, shift=b.detach().float())
+            acts.append(y)
+            cur = y
+        ctx.acts, ctx.umma, ctx.dt_act, ctx.x_dtype = acts, umma, dt_act, x.dtype
+        ctx.save_for_backward(*wb)
+        return _nchw_view(cur.buf, K, H, W, cur.C)
+
+    @staticmethod
+    def backward(ctx, g):
+        wb = ctx.saved_tensors
+        acts, umma, dt_act = ctx.acts, ctx.umma, ctx.dt_act
+        K, C, H, W = g.shape
+        dy = _to_cl_act(g, g.dtype if g.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+        if dt_act == torch.float32 and dy.dtype != torch.float32:
+            dy = _to_cl_act(g.float(), torch.float32)
+        grads = [None] * len(wb)
+        n = len(wb) // 2
+        for i in range(n - 1, -1, -1):
+            w, b = wb[2 * i], wb[2 * i + 1]
+            x_in, y = acts[i], acts[i + 1]
+            dconv = Act.empty(K, 1, H, W, y.C, dt_act, g.device)
+            db = torch.zeros_like(b, dtype=torch.float32)
+            gw = torch.zeros_like(w, dtype=torch.float32)
+            if K:
+                ops.relu_bwd(dy, y, dconv, db)
+                dwp = torch.zeros(9 * x_in.C * y.C, dtype=torch.float32, device=g.device)
+                ops.wgrad(x_in, dconv, (1, 3, 3), (0, 1, 1), dwp, umma=umma)
+                ops.unpack_wgrad(dwp, gw, 0)
+            grads[2 * i], grads[2 * i + 1] = gw.to(w.dtype), db.to(b.dtype)
+            if i > 0 or ctx.needs_input_grad[0]:
+                wd, cpd = _pack(w, 1, umma, w.shape[0])
+                last = i == 0
+                dx = Act.empty(K, 1, H, W, x_in.C, (dt_act if last else torch.float32), g.device)
+                if K:
+                    ops.conv(dconv, wd, cpd, x_in.C, (1, 3, 3), (0, 1, 1), 1, dx, umma=umma)
+                dy = dx
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = _nchw_view(dy.buf, K, H, W, dy.C).to(ctx.x_dtype)
+        ctx.acts = None
+        return (gx, None) + tuple(grads)
+
+
+class MaskRCNNHeads(tv_mask_rcnn.MaskRCNNHeads):
+    """torchvision's container (same ctor, same state_dict keys ``{i}.0.weight|bias``); forward on libsfvos."""
+
+    precision = None
+
+    def forward(self, x):
+        wb = []
+        for blk in self:
+            conv = blk[0]
+            assert conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.dilation == (1, 1), "3x3 pad-1 convs only"
+            assert len(blk) == 2 and isinstance(blk[1], nn.ReLU), "norm layers in the mask head are not supported"
+            wb.extend([conv.weight, conv.bias])
+        return _MaskHeadFn.apply(x, self.precision or _default_precision(), *wb)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# mask predictor: ConvTranspose2d(k2,s2)+ReLU -> 1x1 conv to n_cls logits
+# ----------------------------------------------------------------------------------------------------------------------
+_TAPS = [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+
+class _MaskPredictorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, precision, wt, bt, wl, bl):
+        ops.device_check()
+        umma = precision != "fp32"
+        dt_act = _act_dtype(precision)
+        K, C, H, W = x.shape
+        co = wt.shape[1]
+        n_cls = wl.shape[0]
+        xin = _to_cl_act(x, dt_act)
+        up = Act.empty(K, 1, 2 * H, 2 * W, co, dt_act, x.device)
+        logits = torch.empty(K, n_cls, 2 * H, 2 * W, dtype=torch.float32, device=x.device)
+        if K:
+            for (i, j) in _TAPS:
+                wp, cp = _pack(wt, 2, umma, C, (i, j))
+                ops.conv(xin, wp, cp, co, (1, 1, 1), (0, 0, 0), 1, up, umma=umma, relu=True, shift=bt.detach().float(),
+                         scatter=(2 * H, 2 * W, 2, i, 2, j))
+            call("sfvos_mask_logits_fwd", up.ptr(), ops.dt(up.buf), _p(wl.detach().float().contiguous()),
+                 _p(bl.detach().float().contiguous()), _p(logits), K, 2 * H, co, n_cls, stream())
+        ctx.acts = (xin, up)
+        ctx.meta = (umma, dt_act, x.dtype, K, C, H, W, co, n_cls)
+        ctx.save_for_backward(wt, bt, wl, bl)
+        return logits
+
+    @staticmethod
+    def backward(ctx, glogits):
+        wt, bt, wl, bl = ctx.saved_tensors
+        xin, up = ctx.acts
+        umma, dt_act, x_dtype, K, C, H, W, co, n_cls = ctx.meta
+        dev = glogits.device
+        gwl = torch.zeros(n_cls, co, dtype=torch.float32, device=dev)
+        gbl = torch.zeros(n_cls, dtype=torch.float32, device=dev)
+        gwt = torch.zeros_like(wt, dtype=torch.float32)
+        gbt = torch.zeros(co, dtype=torch.float32, device=dev)
+        gx = None
+        if K:
+            gl = glogits.float().contiguous()
+            dup = Act.empty(K, 1, 2 * H, 2 * W, co, dt_act, dev)
+            call("sfvos_mask_logits_bwd", up.ptr(), ops.dt(up.buf), _p(wl.detach().float().contiguous()), _p(gl),
+                 dup.ptr(), ops.dt(dup.buf), _p(gwl), _p(gbl), K, 2 * H, co, n_cls, stream())
+            dconv = Act.empty(K, 1, 2 * H, 2 * W, co, dt_act, dev)
+            ops.relu_bwd(dup, up, dconv, gbt)
+            # the (i,j) tap of dconv as a [K,1,H,W,co] activation: rows 2h+i, columns 2w+j
+            cs = 2 * co
+            hs, bs = 2 * (2 * W) * co, (2 * H) * (2 * W) * co
+            need_dx = ctx.needs_input_grad[0]
+            dx = Act.empty(K, 1, H, W, C, torch.float32, dev) if need_dx else None
+            for n, (i, j) in enumerate(_TAPS):
+                tap = Act(dconv.buf, K, 1, H, W, co, cs, (i * 2 * W + j) * co)
+                dwp = torch.zeros(C * co, dtype=torch.float32, device=dev)
+                ops.wgrad(xin, tap, (1, 1, 1), (0, 0, 0), dwp, umma=umma, dy_strides=(hs, bs, bs))
+                ops.unpack_wgrad(dwp, gwt, 2, (i, j))
+                if need_dx:
+                    wd, cpd = _pack(wt, 3, umma, co, (i, j))
+                    ops.conv(tap, wd, cpd, C, (1, 1, 1), (0, 0, 0), 1, dx, umma=umma, accumulate=(n > 0),
+                             x_strides=(hs, bs, bs))
+            if need_dx:
+                gx = _nchw_view(dx.buf, K, H, W, C).to(x_dtype)
+        elif ctx.needs_input_grad[0]:
+            gx = torch.zeros(K, C, H, W, dtype=x_dtype, device=dev)
+        ctx.acts = None
+        return gx, None, gwt.to(wt.dtype), gbt.to(bt.dtype), gwl.view_as(wl).to(wl.dtype), gbl.to(bl.dtype)
+
+
+class MaskRCNNPredictor(tv_mask_rcnn.MaskRCNNPredictor):
+    """Same ctor / state_dict keys (conv5_mask.*, mask_fcn_logits.*) as torchvision; forward on libsfvos."""
+
+    precision = None
+
+    def forward(self, x):
+        return _MaskPredictorFn.apply(x, self.precision or _default_precision(), self.conv5_mask.weight, self.conv5_mask.bias,
+                                      self.mask_fcn_logits.weight, self.mask_fcn_logits.bias)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# loss / inference
+# ----------------------------------------------------------------------------------------------------------------------
+class _MaskBceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, targets):
+        K, n_cls, S, _ = logits.shape
+        logits = logits.float().contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        call("sfvos_mask_bce_fwd", _p(logits), _p(labels), _p(targets), _p(loss), K, S, n_cls, stream())
+        ctx.save_for_backward(logits, labels, targets)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, targets = ctx.saved_tensors
+        K, n_cls, S, _ = logits.shape
+        gl = torch.empty_like(logits)
+        gg = g.reshape(1).float().contiguous()
+        call("sfvos_mask_bce_bwd", _p(logits), _p(labels), _p(targets), _p(gg), _p(gl), K, S, n_cls, stream())
+        return gl, None, None
+
+
+def project_masks_on_boxes(gt_masks, boxes, matched_idxs, M):
+    """TV roi_heads.py:85-97 on the GPU: adaptive-sampling ROIAlign of the u8 GT masks to M x M."""
+    rois = torch.cat([matched_idxs[:, None].to(boxes), boxes], dim=1).float().contiguous()
+    masks = gt_masks.to(torch.uint8).contiguous()
+    return ops.mask_targets(masks, rois, M)
+
+
+def maskrcnn_loss(mask_logits, proposals, gt_masks, gt_labels, mask_matched_idxs):
+    """Same signature and value as torchvision's maskrcnn_loss (TV roi_heads.py:100-129)."""
+    M = mask_logits.shape[-1]
+    labels = torch.cat([gl[idxs] for gl, idxs in zip(gt_labels, mask_matched_idxs)], dim=0)
+    targets = [project_masks_on_boxes(m, p, i, M) for m, p, i in zip(gt_masks, proposals, mask_matched_idxs)]
+    targets = torch.cat(targets, dim=0)
+    if targets.numel() == 0:
+        return mask_logits.sum() * 0
+    return _MaskBceFn.apply(mask_logits, labels.to(torch.int64).contiguous(), targets.contiguous())
+
+
+def maskrcnn_inference(x, labels):
+    """TV roi_heads.py:56-82: sigmoid of the predicted-class channel, split per image."""
+    per_img = [lab.shape[0] for lab in labels]
+    lab = torch.cat(labels).to(torch.int64).contiguous()
+    K, n_cls, S, _ = x.shape
+    prob = torch.empty(K, 1, S, S, dtype=torch.float32, device=x.device)
+    if K:
+        call("sfvos_mask_probs", _p(x.float().contiguous()), _p(lab), _p(prob), K, S, n_cls, stream())
+    return prob.split(per_img, dim=0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# RoIHeads
+# ----------------------------------------------------------------------------------------------------------------------
+class RoIHeads(tv_roi_heads.RoIHeads):
+    """torchvision RoIHeads with the mask branch (pool -> head -> predictor -> loss/inference) on libsfvos kernels.
+    Box sampling / box head / box losses / NMS are inherited unchanged."""
+
+    def forward(self, features, proposals, image_shapes, targets=None):
+        if self.training:
+            proposals, matched_idxs, labels, regression_targets = self.select_training_samples(proposals, targets)
+        else:
+            labels = regression_targets = matched_idxs = None
+        box_features = self.box_roi_pool(features, proposals, image_shapes)
+        box_features = self.box_head(box_features)
+        class_logits, box_regression = self.box_predictor(box_features)
+
+        result: List[Dict[str, Tensor]] = []
+        losses = {}
+        if self.training:
+            loss_classifier, loss_box_reg = tv_roi_heads.fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
+            losses = {"loss_classifier": loss_classifier, "loss_box_reg": loss_box_reg}
+        else:
+            boxes, scores, labels = self.postprocess_detections(class_logits, box_regression, proposals, image_shapes)
+            for i in range(len(boxes)):
+                result.append({"boxes": boxes[i], "labels": labels[i], "scores": scores[i]})
+
+        if self.has_mask():
+            mask_proposals = [p["boxes"] for p in result]
+            pos_matched_idxs = None
+            if self.training:
+                mask_proposals, pos_matched_idxs = [], []
+                for img_id in range(len(proposals)):
+                    pos = torch.where(labels[img_id] > 0)[0]
+                    mask_proposals.append(proposals[img_id][pos])
+                    pos_matched_idxs.append(matched_idxs[img_id][pos])
+            mask_features = self.mask_roi_pool(features, mask_proposals, image_shapes)
+            mask_features = self.mask_head(mask_features)
+            mask_logits = self.mask_predictor(mask_features)
+            if self.training:
+                gt_masks = [t["masks"] for t in targets]
+                gt_labels = [t["labels"] for t in targets]
+                losses["loss_mask"] = maskrcnn_loss(mask_logits, mask_proposals, gt_masks, gt_labels, pos_matched_idxs)
+            else:
+                labels = [r["labels"] for r in result]
+                for mask_prob, r in zip(maskrcnn_inference(mask_logits, labels), result):
+                    r["masks"] = mask_prob
+        return result, losses
+
+
+def install(roi_heads: tv_roi_heads.RoIHeads, precision: Optional[str] = None):
+    """Swap the libsfvos modules into an existing torchvision ``roi_heads`` IN PLACE, keeping every parameter
+    (same tensors, same state_dict keys, same registration order).  Returns the same object, now a ``RoIHeads``."""
+    precision = precision or _default_precision()
+    for name, layout in (("box_roi_pool", "nchw"), ("mask_roi_pool", "nhwc")):
+        old = getattr(roi_heads, name)
+        if old is None:
+            continue
+        new = MultiScaleRoIAlign(list(old.featmap_names), old.output_size, old.sampling_ratio,
+                                 canonical_scale=old.canonical_scale, canonical_level=old.canonical_level,
+                                 out_layout=layout, precision=precision)
+        setattr(roi_heads, name, new)
+    if roi_heads.mask_head is not None:
+        roi_heads.mask_head.__class__ = MaskRCNNHeads
+        roi_heads.mask_head.precision = precision
+    if roi_heads.mask_predictor is not None:
+        roi_heads.mask_predictor.__class__ = MaskRCNNPredictor
+        roi_heads.mask_predictor.precision = precision
+    roi_heads.__class__ = RoIHeads
+    return roi_heads

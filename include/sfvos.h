@@ -203,12 +203,14 @@ int sfvos_mask_logits_fwd(const void* x, int32_t x_dtype, const float* w /*[n_cl
 /* loss[0] = mean over K*S*S of BCE-with-logits(logits[k,labels[k]], targets[k]). */
 int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, const float* targets, float* loss, int64_t K,
                        int64_t S, int32_t n_cls, sfvos_stream stream);
-/* backward of both: dlogit = gloss*(sigmoid(z)-t)/(K*S*S) on the label channel; dx (bf16|f32) [K,S,S,C];
- * dw [n_cls,C] += , db [n_cls] += . */
-int sfvos_mask_logits_bce_bwd(const void* x, int32_t x_dtype, const float* w, const float* logits,
-                              const int64_t* labels, const float* targets, const float* gloss, void* dx,
-                              int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C,
-                              int32_t n_cls, sfvos_stream stream);
+/* backward of the 1x1 conv: dx[k,p,:] = sum_cls glogits[k,cls,p]*w[cls,:] (bf16|f32, same dtype as x);
+ * dw [n_cls,C] += sum glogits*x; db [n_cls] += sum glogits. */
+int sfvos_mask_logits_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
+                          int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C, int32_t n_cls,
+                          sfvos_stream stream);
+/* backward of the loss: glogits[k,cls,p] = gloss*(sigmoid(z)-t)/(K*S*S) on the label channel, 0 elsewhere. */
+int sfvos_mask_bce_bwd(const float* logits, const int64_t* labels, const float* targets, const float* gloss,
+                       float* glogits, int64_t K, int64_t S, int32_t n_cls, sfvos_stream stream);
 /* maskrcnn_inference: prob[k,0,s,s] = sigmoid(logits[k,labels[k]]). */
 int sfvos_mask_probs(const float* logits, const int64_t* labels, float* prob, int64_t K, int64_t S, int32_t n_cls,
                      sfvos_stream stream);
