@@ -31,13 +31,21 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(autouse=True)
-def _exact_fp32_references():
-    """torch fp32 references on the GPU must not silently drop to TF32."""
+def force_ieee_fp32():
+    """torch fp32 references on the GPU must not silently drop to TF32 (cuDNN convs default to TF32)."""
+    import torch
     try:
-        import torch
+        torch.backends.cudnn.conv.fp32_precision = "ieee"
+        torch.backends.cuda.matmul.fp32_precision = "ieee"
+    except Exception:
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_references():
+    try:
+        force_ieee_fp32()
     except Exception:
         pass
     yield
