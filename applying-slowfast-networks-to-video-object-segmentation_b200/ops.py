@@ -8,8 +8,22 @@ from . import _lib
 from ._lib import BF16, F32, ConvParams, RoiParams, WgradParams, call
 
 
+TIMING = None   # bench.py sets this to a list: every conv / wgrad launch then appends (kernel, flops, start, end)
+
+
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _timed_call(kernel, flops, name, params):
+    if TIMING is None:
+        call(name, ctypes.byref(params), stream())
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, ctypes.byref(params), stream())
+    e1.record()
+    TIMING.append((kernel, flops, e0, e1))
 
 
 def dt(t):
@@ -132,7 +146,8 @@ def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shi
     p.accumulate = int(accumulate)
     if scatter is not None:
         p.OH, p.OW, p.oy_mul, p.oy_off, p.ox_mul, p.ox_off = scatter
-    call("sfvos_conv_umma" if umma else "sfvos_conv_simt", ctypes.byref(p), stream())
+    flops = 2.0 * x.B * To * x.H * x.W * N * x.C * k[0] * k[1] * k[2]
+    _timed_call("conv_umma" if umma else "conv_simt", flops, "sfvos_conv_umma" if umma else "sfvos_conv_simt", p)
 
 
 def wgrad(x, dy, k, pad, dw, *, umma, dy_strides=None):
@@ -146,7 +161,8 @@ def wgrad(x, dy, k, pad, dw, *, umma, dy_strides=None):
     p.kt, p.kh, p.kw = k
     p.pad_t, p.pad_h, p.pad_w = pad
     p.dw = _p(dw)
-    call("sfvos_wgrad_umma" if umma else "sfvos_wgrad_simt", ctypes.byref(p), stream())
+    flops = 2.0 * x.B * dy.T * x.H * x.W * dy.C * x.C * k[0] * k[1] * k[2]
+    _timed_call("wgrad_umma" if umma else "wgrad_simt", flops, "sfvos_wgrad_umma" if umma else "sfvos_wgrad_simt", p)
 
 
 def channel_stats(x, stats):

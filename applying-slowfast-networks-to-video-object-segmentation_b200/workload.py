@@ -1,0 +1,146 @@
+"""Synthetic DAVIS-shaped hot-path step: SlowFast temporal module on B clips (all 5 FPN levels) ->
+multi-level ROIAlign for the box (7x7) and mask (14x14) branches -> mask head -> mask predictor -> mask loss,
+forward + backward.  Used by bench.py (the measured step) and the data-parallel trainer; everything numeric runs
+in libsfvos.so except the stand-in box loss (mean of squares of the pooled box features: the torch box head is
+outside the hot path)."""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from .roi_heads import MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, maskrcnn_loss
+from .slowfast import SlowFastLayers
+
+# 480x854 DAVIS frame -> GeneralizedRCNNTransform -> 749x1333 -> padded 768x1344 -> FPN strides 4..64
+IMAGE_HW = (749, 1333)
+LEVELS = OrderedDict([("0", (192, 336)), ("1", (96, 168)), ("2", (48, 84)), ("3", (24, 42)), ("pool", (12, 21))])
+POOL_LEVELS = ["0", "1", "2", "3"]
+
+
+def synthetic_rois(n_clips, k_per_clip, image_hw=IMAGE_HW, seed=4321, lo=16.0, hi=700.0):
+    """Log-uniform side 16..700 px, aspect U(0.5,2), uniform centre, clipped; all 4 levels are hit."""
+    g = torch.Generator().manual_seed(seed)
+    h_img, w_img = image_hw
+    out = []
+    for _ in range(n_clips):
+        s = torch.exp(torch.rand(k_per_clip, generator=g) * (math.log(hi) - math.log(lo)) + math.log(lo))
+        a = torch.rand(k_per_clip, generator=g) * 1.5 + 0.5
+        bw, bh = s * torch.sqrt(a), s / torch.sqrt(a)
+        cx = torch.rand(k_per_clip, generator=g) * w_img
+        cy = torch.rand(k_per_clip, generator=g) * h_img
+        x1 = (cx - bw / 2).clamp(0, w_img - 1)
+        y1 = (cy - bh / 2).clamp(0, h_img - 1)
+        x2 = torch.maximum((cx + bw / 2).clamp(0, w_img), x1 + 1)
+        y2 = torch.maximum((cy + bh / 2).clamp(0, h_img), y1 + 1)
+        out.append(torch.stack([x1, y1, x2, y2], dim=1))
+    return out
+
+
+def synthetic_features(n_clips, fp, levels=LEVELS, seed=1234, device="cpu", pin=False):
+    """Per clip an OrderedDict {level: f32 [fp,256,H,W]} of seeded unit-variance features."""
+    clips = []
+    for b in range(n_clips):
+        d = OrderedDict()
+        for i, (k, (h, w)) in enumerate(levels.items()):
+            if device == "cpu":
+                g = torch.Generator().manual_seed(seed + 100 * b + i)
+                t = torch.randn(fp, 256, h, w, generator=g)
+                if pin:
+                    t = t.pin_memory()
+            else:
+                g = torch.Generator(device=device).manual_seed(seed + 100 * b + i)
+                t = torch.randn(fp, 256, h, w, generator=g, device=device)
+            d[k] = t
+        clips.append(d)
+    return clips
+
+
+def conv_flops(sp, fp, levels=LEVELS, fwd_only=False):
+    """Algorithmic FLOPs per clip of the 8 Conv3d layers: fwd, and fwd + wgrad + dgrad (no dgrad for
+    the two first-layer convs, whose inputs carry no gradient)."""
+    def ks(p):
+        d, r = divmod(p, 3)
+        return (d, d + 1, d + 1) if r == 0 else (d + 1, d + 1, d + 1) if r == 1 else (d + 1, d + 1, d + 2)
+    s, f = ks(sp), ks(fp)
+    ts = [sp - s[0] + 1]; ts.append(ts[0] - s[1] + 1); ts.append(ts[1] - s[2] + 1)
+    tf = [fp - f[0] + 1]; tf.append(tf[0] - f[1] + 1); tf.append(tf[1] - f[2] + 1)
+    kl1, kl2 = tf[0] - ts[0] + 1, tf[1] - ts[1] + 1
+    hw = sum(h * w for h, w in levels.values())
+    layers = [  # (T_out, Cout, Cin, taps, first)
+        (ts[0], 192, 256, s[0] * 9, True), (tf[0], 32, 256, f[0] * 9, True), (ts[0], 64, 32, kl1, False),
+        (ts[1], 192, 256, s[1] * 9, False), (tf[1], 32, 32, f[1] * 9, False), (ts[1], 64, 32, kl2, False),
+        (ts[2], 224, 256, s[2] * 9, False), (tf[2], 32, 32, f[2] * 9, False)]
+    fwd = sum(2.0 * t * hw * co * ci * taps for t, co, ci, taps, _ in layers)
+    first = sum(2.0 * t * hw * co * ci * taps for t, co, ci, taps, fl in layers if fl)
+    return fwd if fwd_only else 3.0 * fwd - first
+
+
+MASK_HEAD_FLOPS_PER_ROI = 2.0 * 196 * 256 * 2304 * 4 + 2.0 * 196 * 256 * 1024 + 2.0 * 784 * 2 * 256   # fwd
+
+
+class HotPathStep:
+    """One forward+backward of the hot path on a batch of clips.  ``features``: list (len B) of {level: [fp,256,H,W]}
+    CUDA f32 tensors (e.g. the frozen backbone's output windows)."""
+
+    def __init__(self, sp=1, fp=8, n_clips=8, k_box=512, k_mask=128, levels=LEVELS, device="cuda", precision="bf16", seed=63):
+        self.sp, self.fp, self.B, self.levels = sp, fp, n_clips, levels
+        self.device = torch.device(device)
+        torch.manual_seed(seed)
+        self.slow_fast = SlowFastLayers(256, self.device, sp, fp).to(self.device).train()
+        self.slow_fast.precision = precision
+        self.mask_head = MaskRCNNHeads(256, (256, 256, 256, 256), 1).to(self.device)
+        self.mask_predictor = MaskRCNNPredictor(256, 256, 2).to(self.device)
+        self.mask_head.precision = self.mask_predictor.precision = precision
+        names = [k for k in levels if k in POOL_LEVELS]
+        self.box_roi_pool = MultiScaleRoIAlign(names, 7, 2, out_layout="nchw", precision=precision)
+        self.mask_roi_pool = MultiScaleRoIAlign(names, 14, 2, out_layout="nhwc", precision=precision)
+        self.image_shapes = [IMAGE_HW] * n_clips
+        box = synthetic_rois(n_clips, k_box, seed=4321)
+        self.box_props = [b.to(self.device) for b in box]
+        self.mask_props = [b[:k_mask].to(self.device) for b in box]
+        gt = torch.zeros(1, IMAGE_HW[0], IMAGE_HW[1], dtype=torch.uint8)
+        gt[0, 200:500, 400:600] = 1                                     # one 300x200 object per clip
+        self.gt_masks = [gt.to(self.device) for _ in range(n_clips)]
+        self.gt_labels = [torch.ones(1, dtype=torch.int64, device=self.device) for _ in range(n_clips)]
+        self.matched = [torch.zeros(k_mask, dtype=torch.int64, device=self.device) for _ in range(n_clips)]
+        self.k_box, self.k_mask = k_box, k_mask
+
+    def parameters(self):
+        return list(self.slow_fast.parameters()) + list(self.mask_head.parameters()) + list(self.mask_predictor.parameters())
+
+    def state_dict(self):
+        sd = OrderedDict(("slow_fast." + k, v) for k, v in self.slow_fast.state_dict().items())
+        sd.update(("mask_head." + k, v) for k, v in self.mask_head.state_dict().items())
+        sd.update(("mask_predictor." + k, v) for k, v in self.mask_predictor.state_dict().items())
+        return sd
+
+    def forward(self, features):
+        lo = self.fp // 2 - self.sp // 2
+        slow = [OrderedDict((k, v[lo:lo + self.sp]) for k, v in f.items()) for f in features]
+        merged = self.slow_fast.temporally_enhance_features(slow, features)
+        box_feats = self.box_roi_pool(merged, self.box_props, self.image_shapes)
+        loss_box = box_feats.square().mean()                          # stand-in for the torch box head + losses
+        mask_feats = self.mask_roi_pool(merged, self.mask_props, self.image_shapes)
+        logits = self.mask_predictor(self.mask_head(mask_feats))
+        loss_mask = maskrcnn_loss(logits, self.mask_props, self.gt_masks, self.gt_labels, self.matched)
+        return loss_mask + loss_box, merged
+
+    def step(self, features, zero_grad=True):
+        loss, _ = self.forward(features)
+        loss.backward()
+        if zero_grad:
+            for p in self.parameters():
+                p.grad = None
+        return loss
+
+    def flops_per_step(self):
+        conv = conv_flops(self.sp, self.fp, self.levels) * self.B
+        mask = 3.0 * MASK_HEAD_FLOPS_PER_ROI * self.k_mask * self.B
+        return conv, mask
+
+
+def flat_grads(params):
+    """One contiguous f32 bucket holding every parameter gradient (what the DP step all-reduces)."""
+    gs = [p.grad for p in params if p.grad is not None]
+    return torch.cat([g.reshape(-1) for g in gs]) if gs else None
