@@ -22,8 +22,6 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KB per stage
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
@@ -43,9 +41,15 @@ struct ConvArgs {
     int OH, OW, oy_mul, oy_off, ox_mul, ox_off;
 };
 
+// BK = channels per K step: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle; used for the
+// Cin = 32 fast-pathway layers so that no zero-filled half rows are ingested).
+template <int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvArgs a) {
+    constexpr int A_BYTES = BM * BK * 2;
+    constexpr uint32_t LAYOUT = BK == 64 ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
+    constexpr uint32_t SBO = 8 * BK * 2;                      // 8 rows of one swizzle atom
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = a.N * BK * 2;
@@ -140,8 +144,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
-                        const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
+                        const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, SBO, LAYOUT);
+                        const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, SBO, LAYOUT);
                         umma_bf16(d_tmem, adesc, bdesc, a.idesc, (ks | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);      // smem slot is free once these MMAs have read it
@@ -262,7 +266,9 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     SF_CHECK(p != nullptr, "conv_umma: null params");
     SF_CHECK(p->N >= 32 && p->N <= 256 && p->N % 32 == 0, "conv_umma: N=%lld must be a multiple of 32 in [32,256]", (long long)p->N);
-    SF_CHECK(p->Cp % BK == 0 && p->Cp >= p->C, "conv_umma: Cp=%lld must be a multiple of 64 and >= C=%lld", (long long)p->Cp, (long long)p->C);
+    SF_CHECK(p->Cp % 32 == 0 && p->Cp >= p->C, "conv_umma: Cp=%lld must be a multiple of 32 and >= C=%lld", (long long)p->Cp, (long long)p->C);
+    const int BK = (p->Cp % 64 == 0) ? 64 : 32;
+    const int A_BYTES = BM * BK * 2;
     SF_CHECK(p->C % 8 == 0 && p->x_cstride % 8 == 0, "conv_umma: C and x_cstride must be multiples of 8");
     SF_CHECK(p->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0, "conv_umma: y must be 16-byte aligned with cstride %% 8 == 0");
     SF_CHECK(!(p->accumulate && p->y_dtype != SFVOS_F32), "conv_umma: accumulate needs an f32 output");
@@ -307,23 +313,25 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         const uint64_t ts = p->x_tstride ? (uint64_t)p->x_tstride : hs * p->H;
         const uint64_t bs = p->x_bstride ? (uint64_t)p->x_bstride : ts * p->T;
         uint64_t str[4] = {cs * 2, hs * 2, ts * 2, bs * 2};
-        uint32_t box[5] = {BK, (uint32_t)a.TW, (uint32_t)a.TH, 1, 1};
-        rc = sfvos_make_tmap(&tx, p->x, 5, dims, str, box, 128);
+        uint32_t box[5] = {(uint32_t)BK, (uint32_t)a.TW, (uint32_t)a.TH, 1, 1};
+        rc = sfvos_make_tmap(&tx, p->x, 5, dims, str, box, BK * 2);
         if (rc) return rc;
     }
     {
         const uint64_t ktot = (uint64_t)(p->kt * p->kh * p->kw * p->Cp);
         uint64_t dims[2] = {ktot, (uint64_t)p->N};
         uint64_t str[1] = {ktot * 2};
-        uint32_t box[2] = {BK, (uint32_t)p->N};
-        rc = sfvos_make_tmap(&tw, p->w, 2, dims, str, box, 128);
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)p->N};
+        rc = sfvos_make_tmap(&tw, p->w, 2, dims, str, box, BK * 2);
         if (rc) return rc;
     }
     const int smem_bytes = a.stages * stage_bytes + 1024 + 8192;
-    SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (BK == 64) SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int grid = sfvos_num_sms();
     if (grid > a.ntiles) grid = a.ntiles;
-    conv_umma_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
+    if (BK == 64) conv_umma_kernel<64><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
+    else conv_umma_kernel<32><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -10,6 +10,8 @@
 // Out-of-image pixels are zero-filled by TMA in both operands, so halo / overhang terms vanish.
 // Work item = (tap, channel block, pixel split); split-K partial sums are merged with vector atomics
 // (red.global.add.v4.f32) into the f32 dw buffer.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -172,6 +174,8 @@ void choose_ktile(int H, int W, int* PW, int* PH) {
 
 }  // namespace
 
+int sfvos_wgrad_stack_launch(const sfvos_wgrad_params* p, cudaStream_t stream);   // wgrad_stack_umma.cu
+
 extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     SF_CHECK(p != nullptr, "wgrad_umma: null params");
@@ -181,6 +185,8 @@ extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream
     SF_CHECK(p->B > 0 && p->To > 0 && p->H > 0 && p->W > 0, "wgrad_umma: empty tensor");
     int rc = sfvos_device_check();
     if (rc) return rc;
+    if (p->N == 32 && getenv("SFVOS_NO_WGRAD_STACK") == nullptr)
+        return sfvos_wgrad_stack_launch(p, stream);     // narrow fast-pathway GEMMs: taps stacked along N
 
     WgArgs a;
     a.B = (int)p->B; a.To = (int)p->To; a.H = (int)p->H; a.W = (int)p->W; a.C = (int)p->C; a.N = (int)p->N;

@@ -113,7 +113,7 @@ class SlowFastLayers(nn.Module):
         w = getattr(self, name).weight
         spec = self._specs[name]
         kc = spec.cin if mode == 0 else spec.cout
-        cp = _round_up(kc, 64) if self._umma else kc
+        cp = (32 if kc <= 32 else _round_up(kc, 64)) if self._umma else kc     # 32-wide K steps for Cin = 32 layers
         key = (name, mode, self._umma)
         tag = (w.data_ptr(), w._version, str(w.device))
         hit = self._pack_cache.get(key)

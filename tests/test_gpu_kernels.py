@@ -60,7 +60,7 @@ def test_conv_fprop(case, umma):
     pad = 1 if khw == 3 else 0
     ref = F.conv3d(x.permute(0, 4, 1, 2, 3), w, padding=(0, pad, pad)).permute(0, 2, 3, 4, 1)
     xa = _mk_act(ops, x, dtype)
-    cp = (C + 63) // 64 * 64 if umma else C
+    cp = (32 if C <= 32 else (C + 63) // 64 * 64) if umma else C
     wp = ops.pack_weights(w, 0, ops.BF16 if umma else ops.F32, cp)
     To = T - kt + 1
     y = ops.Act.empty(B, To, H, W, N, torch.float32, DEV)
@@ -128,7 +128,7 @@ def test_conv_dgrad(cin, cout, kt, khw, T, umma):
     yref = F.conv3d(x, w, padding=(0, pad, pad))
     (dx_ref,) = torch.autograd.grad(yref, x, dy.permute(0, 4, 1, 2, 3))
     dx_ref = dx_ref.permute(0, 2, 3, 4, 1)
-    cp = (cout + 63) // 64 * 64 if umma else cout
+    cp = (32 if cout <= 32 else (cout + 63) // 64 * 64) if umma else cout
     wd = ops.pack_weights(w, 1, ops.BF16 if umma else ops.F32, cp)
     dya = _mk_act(ops, dy, dtype)
     dx = ops.Act.empty(B, T, H, W, cin, torch.float32, DEV)
