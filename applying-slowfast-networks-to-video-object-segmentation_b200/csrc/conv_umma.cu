@@ -5,17 +5,23 @@
 // GEMM view: D[M,N] = A[M,K] * B[K,N] with M = output pixels, N = output channels, K = taps * channels.
 //   * one M tile = TW x TH output pixels of one (clip, frame) (<=128 rows; the rest of the 128 UMMA rows are
 //     never stored); N is a single tile (<=256) so an activation tile is fetched once for all output channels
-//   * A is never materialised: for every tap (a,i,j) and 64-channel chunk the producer issues ONE 5-D TMA box
-//     {64ch, TW, TH, 1, 1} at the shifted coordinate; out-of-range rows/columns/frames are zero-filled by TMA,
-//     which is the convolution padding.  The box lands as 128-byte rows with the 128B swizzle = the canonical
-//     K-major UMMA operand layout.
-//   * B = pre-packed bf16 weights [N][taps*Cp], loaded as a 2-D TMA box {64, N} per K step
+//   * A is never materialised.  Two ways to feed it, both pure TMA (out-of-range rows / columns / frames are
+//     zero-filled by TMA = the convolution padding):
+//       per-tap mode : one 5-D box {BK ch, TW, TH, 1, 1} per (tap, channel chunk) at the shifted coordinate
+//       halo mode    : (3x3 spatial taps) ONE box {64 ch, 16, TH+2, 1, 1} per (temporal tap, channel chunk) holding
+//                      the tile plus its halo; the 9 spatial taps are 9 UMMA descriptors into that same buffer
+//                      (start += (i*16 + j) rows, stride between 8-row groups = one 16-pixel line = 2048 B, swizzle
+//                      phase carried in the descriptor's base-offset field).  TMA row requests per tap drop from
+//                      128 to 32 -- the L2->SMEM fill rate (~1 128-byte row / 2 clk / SM) is what bounds this kernel.
+//     Rows land as 128-byte (BK=64) or 64-byte (BK=32) swizzled rows = the canonical K-major UMMA operand layout.
+//   * B = pre-packed bf16 weights [N][taps*Cp], one 2-D TMA box {BK, N} per (tap, chunk), in its own smem ring
 //   * fp32 accumulators live in TMEM, double buffered (2*N columns) so the epilogue of tile i overlaps the
 //     MMAs of tile i+1; persistent CTAs, one per SM
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator,
 //     warps 4..7 = epilogue (TMEM -> registers -> per-channel affine/ReLU -> global), which also reduces the
 //     per-channel sum / sum-of-squares of the raw fp32 accumulators for train-mode BatchNorm.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,11 +31,13 @@ constexpr int BM = 128;
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
+constexpr int HALO_LP = 16;                 // pixels per halo line in smem (tile width 8 + 2 halo, padded to 16)
 
 struct ConvArgs {
     int B, To, H, W;
     int TW, TH, tiles_w, tiles_h, ntiles;
-    int N, kt, kh, kw, pad_t, pad_h, pad_w, cchunks, stages;
+    int N, kt, kh, kw, pad_t, pad_h, pad_w, cchunks;
+    int halo, use_bo, a_stages, b_stages, a_stage_bytes;
     uint32_t idesc, tmem_cols, a_tx_bytes;
     void* y;
     int y_bf16, relu, accumulate;
@@ -41,22 +49,23 @@ struct ConvArgs {
     int OH, OW, oy_mul, oy_off, ox_mul, ox_off;
 };
 
-// BK = channels per K step: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle; used for the
-// Cin = 32 fast-pathway layers so that no zero-filled half rows are ingested).
+// BK = channels per K step: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle; Cin = 32 layers).
 template <int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const ConvArgs a) {
-    constexpr int A_BYTES = BM * BK * 2;
     constexpr uint32_t LAYOUT = BK == 64 ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
-    constexpr uint32_t SBO = 8 * BK * 2;                      // 8 rows of one swizzle atom
+    constexpr uint32_t ROW = BK * 2;                          // bytes per smem row
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = a.N * BK * 2;
-    const int stage_bytes = A_BYTES + b_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
-    uint64_t* empty_bar = full_bar + a.stages;
-    uint64_t* tmem_full = empty_bar + a.stages;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + a.a_stages * a.a_stage_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + a.b_stages * b_bytes);
+    uint64_t* a_empty = a_full + a.a_stages;
+    uint64_t* b_full = a_empty + a.a_stages;
+    uint64_t* b_empty = b_full + a.b_stages;
+    uint64_t* tmem_full = b_empty + a.b_stages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
@@ -72,14 +81,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tma_prefetch_desc(&tmap_w);
     }
     if (warp == 1 && elect_one()) {
-        for (int i = 0; i < a.stages; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], EPI_THREADS);
-        }
+        for (int i = 0; i < a.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < a.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
@@ -94,14 +98,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int ksteps = a.kt * a.kh * a.kw * a.cchunks;
     const int tiles_per_frame = a.tiles_w * a.tiles_h;
+    // outer loop = A loads, inner loop = B loads sharing one A buffer (halo mode: the kh*kw spatial taps)
+    const int outer_h = a.halo ? 1 : a.kh, outer_w = a.halo ? 1 : a.kw;
+    const int inner_h = a.halo ? a.kh : 1, inner_w = a.halo ? a.kw : 1;
 
     if (warp == 0) {
         if (elect_one()) {
             // ------------------------------ TMA producer ------------------------------
-            int stage = 0;
-            uint32_t phase = 0;
+            int as = 0, bs = 0;
+            uint32_t aphase = 0, bphase = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const int frame = tile / tiles_per_frame;
                 const int rem = tile - frame * tiles_per_frame;
@@ -110,46 +116,62 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int b = frame / a.To;
                 const int t = frame - b * a.To;
                 const int h0 = th_i * a.TH, w0 = tw_i * a.TW;
-                int kcol = 0;
                 for (int ta = 0; ta < a.kt; ++ta)
-                    for (int ti = 0; ti < a.kh; ++ti)
-                        for (int tj = 0; tj < a.kw; ++tj)
+                    for (int oi = 0; oi < outer_h; ++oi)
+                        for (int oj = 0; oj < outer_w; ++oj)
                             for (int cc = 0; cc < a.cchunks; ++cc) {
-                                mbar_wait(&empty_bar[stage], phase ^ 1);
-                                uint8_t* sa = smem + stage * stage_bytes;
-                                mbar_arrive_expect_tx(&full_bar[stage], a.a_tx_bytes + b_bytes);
-                                tma_load_5d(sa, &tmap_x, &full_bar[stage], cc * BK, w0 + tj - a.pad_w,
-                                            h0 + ti - a.pad_h, t + ta - a.pad_t, b);
-                                tma_load_2d(sa + A_BYTES, &tmap_w, &full_bar[stage], kcol, 0);
-                                kcol += BK;
-                                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                                mbar_wait(&a_empty[as], aphase ^ 1);
+                                mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes);
+                                tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK,
+                                            w0 + oj - a.pad_w, h0 + oi - a.pad_h, t + ta - a.pad_t, b);
+                                if (++as == a.a_stages) { as = 0; aphase ^= 1; }
+                                for (int ii = 0; ii < inner_h; ++ii)
+                                    for (int ij = 0; ij < inner_w; ++ij) {
+                                        const int tap = (ta * a.kh + oi + ii) * a.kw + oj + ij;
+                                        mbar_wait(&b_empty[bs], bphase ^ 1);
+                                        mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+                                        tma_load_2d(smem_b + bs * b_bytes, &tmap_w, &b_full[bs], (tap * a.cchunks + cc) * BK, 0);
+                                        if (++bs == a.b_stages) { bs = 0; bphase ^= 1; }
+                                    }
                             }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             // ------------------------------ MMA issuer ------------------------------
-            int stage = 0;
-            uint32_t phase = 0;
+            int as = 0, bs = 0;
+            uint32_t aphase = 0, bphase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const int outer = a.kt * outer_h * outer_w * a.cchunks;
+            const uint32_t a_sbo = a.halo ? HALO_LP * ROW : 8 * ROW;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * a.N;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-                    const uint32_t b_addr = a_addr + A_BYTES;
+                uint32_t accum = 0;
+                for (int o = 0; o < outer; ++o) {
+                    mbar_wait(&a_full[as], aphase);
+                    const uint32_t a_addr = smem_u32(smem_a + as * a.a_stage_bytes);
+                    for (int ii = 0; ii < inner_h; ++ii)
+                        for (int ij = 0; ij < inner_w; ++ij) {
+                            mbar_wait(&b_full[bs], bphase);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(smem_b + bs * b_bytes);
+                            const uint32_t a_tap = a_addr + (ii * HALO_LP + ij) * ROW;      // == a_addr outside halo mode
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, SBO, LAYOUT);
-                        const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, SBO, LAYOUT);
-                        umma_bf16(d_tmem, adesc, bdesc, a.idesc, (ks | k) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[stage]);      // smem slot is free once these MMAs have read it
-                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                            for (int k = 0; k < BK / 16; ++k) {
+                                uint64_t adesc = umma_smem_desc(a_tap + k * 32, 16, a_sbo, LAYOUT);
+                                if (a.use_bo) adesc |= static_cast<uint64_t>((a_tap >> 7) & 7u) << 49;   // swizzle phase of a shifted start
+                                const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, 8 * ROW, LAYOUT);
+                                umma_bf16(d_tmem, adesc, bdesc, a.idesc, accum);
+                                accum = 1;
+                            }
+                            umma_commit(&b_empty[bs]);
+                            if (++bs == a.b_stages) { bs = 0; bphase ^= 1; }
+                        }
+                    umma_commit(&a_empty[as]);
+                    if (++as == a.a_stages) { as = 0; aphase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
                 acc ^= 1;
@@ -244,7 +266,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
 }
 
-void choose_tile(int H, int W, int* TW, int* TH) {
+double choose_tile(int H, int W, int* TW, int* TH) {
     double best = -1.0;
     int bw = 1, bh = 1;
     for (int tw = 1; tw <= W && tw <= BM; ++tw) {
@@ -258,6 +280,12 @@ void choose_tile(int H, int W, int* TW, int* TH) {
         }
     }
     *TW = bw; *TH = bh;
+    return best;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
 }
 
 }  // namespace
@@ -268,7 +296,6 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     SF_CHECK(p->N >= 32 && p->N <= 256 && p->N % 32 == 0, "conv_umma: N=%lld must be a multiple of 32 in [32,256]", (long long)p->N);
     SF_CHECK(p->Cp % 32 == 0 && p->Cp >= p->C, "conv_umma: Cp=%lld must be a multiple of 32 and >= C=%lld", (long long)p->Cp, (long long)p->C);
     const int BK = (p->Cp % 64 == 0) ? 64 : 32;
-    const int A_BYTES = BM * BK * 2;
     SF_CHECK(p->C % 8 == 0 && p->x_cstride % 8 == 0, "conv_umma: C and x_cstride must be multiples of 8");
     SF_CHECK(p->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0, "conv_umma: y must be 16-byte aligned with cstride %% 8 == 0");
     SF_CHECK(!(p->accumulate && p->y_dtype != SFVOS_F32), "conv_umma: accumulate needs an f32 output");
@@ -280,7 +307,15 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
 
     ConvArgs a;
     a.B = (int)p->B; a.To = (int)p->To; a.H = (int)p->H; a.W = (int)p->W;
-    choose_tile(a.H, a.W, &a.TW, &a.TH);
+    const double eff_tap = choose_tile(a.H, a.W, &a.TW, &a.TH);
+    // halo mode: 8 x 16 tiles; worth it when its tiling wastes little more than the per-tap tiling
+    a.halo = 0;
+    if (BK == 64 && p->kh == 3 && p->kw == 3 && env_int("SFVOS_HALO", 1)) {
+        const long long tiles = (long long)((a.W + 7) / 8) * ((a.H + 15) / 16);
+        const double eff_halo = (double)a.H * a.W / (double)(tiles * BM);
+        if (eff_halo >= eff_tap - 0.15) { a.halo = 1; a.TW = 8; a.TH = 16; }
+    }
+    a.use_bo = env_int("SFVOS_HALO_BO", 0);   // measured on B200: the swizzle XOR uses absolute smem address bits, so a shifted start needs NO base offset
     a.tiles_w = (a.W + a.TW - 1) / a.TW;
     a.tiles_h = (a.H + a.TH - 1) / a.TH;
     a.ntiles = a.B * a.To * a.tiles_w * a.tiles_h;
@@ -288,16 +323,30 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     a.kt = (int)p->kt; a.kh = (int)p->kh; a.kw = (int)p->kw;
     a.pad_t = (int)p->pad_t; a.pad_h = (int)p->pad_h; a.pad_w = (int)p->pad_w;
     a.cchunks = (int)(p->Cp / BK);
-    const int stage_bytes = A_BYTES + a.N * BK * 2;
+    const int b_bytes = a.N * BK * 2;
     const int smem_budget = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, scale/shift, stats*/;
-    a.stages = smem_budget / stage_bytes;
-    if (a.stages > 8) a.stages = 8;
-    SF_CHECK(a.stages >= 2, "conv_umma: not enough shared memory for 2 stages");
+    uint32_t abox_w, abox_h;
+    if (a.halo) {
+        abox_w = HALO_LP; abox_h = (uint32_t)(a.TH + 2);
+        a.a_stage_bytes = HALO_LP * (a.TH + 2) * 128;                       // 36 KB
+        a.b_stages = 4;
+        a.a_stages = (smem_budget - a.b_stages * b_bytes) / a.a_stage_bytes;
+        if (a.a_stages > 4) a.a_stages = 4;
+        if (a.a_stages > 2 && b_bytes <= 8192) { a.b_stages = 8; }
+        SF_CHECK(a.a_stages >= 2, "conv_umma: not enough shared memory for the halo pipeline");
+    } else {
+        abox_w = (uint32_t)a.TW; abox_h = (uint32_t)a.TH;
+        a.a_stage_bytes = BM * BK * 2;
+        int st = smem_budget / (a.a_stage_bytes + b_bytes);
+        if (st > 8) st = 8;
+        SF_CHECK(st >= 2, "conv_umma: not enough shared memory for 2 stages");
+        a.a_stages = a.b_stages = st;
+    }
+    a.a_tx_bytes = abox_w * abox_h * BK * 2;
     a.idesc = umma_idesc_bf16(BM, a.N, 0, 0);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * a.N)) cols <<= 1;
     a.tmem_cols = cols;
-    a.a_tx_bytes = (uint32_t)(a.TW * a.TH * BK * 2);
     a.y = p->y; a.y_bf16 = (p->y_dtype == SFVOS_BF16); a.relu = p->relu; a.accumulate = p->accumulate;
     a.y_cstride = p->y_cstride;
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
@@ -313,7 +362,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         const uint64_t ts = p->x_tstride ? (uint64_t)p->x_tstride : hs * p->H;
         const uint64_t bs = p->x_bstride ? (uint64_t)p->x_bstride : ts * p->T;
         uint64_t str[4] = {cs * 2, hs * 2, ts * 2, bs * 2};
-        uint32_t box[5] = {(uint32_t)BK, (uint32_t)a.TW, (uint32_t)a.TH, 1, 1};
+        uint32_t box[5] = {(uint32_t)BK, abox_w, abox_h, 1, 1};
         rc = sfvos_make_tmap(&tx, p->x, 5, dims, str, box, BK * 2);
         if (rc) return rc;
     }
@@ -325,13 +374,16 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         rc = sfvos_make_tmap(&tw, p->w, 2, dims, str, box, BK * 2);
         if (rc) return rc;
     }
-    const int smem_bytes = a.stages * stage_bytes + 1024 + 8192;
-    if (BK == 64) SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * b_bytes + 1024 + 8192;
     int grid = sfvos_num_sms();
     if (grid > a.ntiles) grid = a.ntiles;
-    if (BK == 64) conv_umma_kernel<64><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
-    else conv_umma_kernel<32><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
+    if (BK == 64) {
+        SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        conv_umma_kernel<64><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
+    } else {
+        SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        conv_umma_kernel<32><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
+    }
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -48,11 +48,12 @@ def main():
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step(); torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
-    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and ("umma" in e.name)]
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and ("umma" in e.name or "wgrad_stack" in e.name)]
     evs.sort(key=lambda e: e.time_range.start)
     print("per-launch timeline of the tensor-core kernels (us):")
     for i, e in enumerate(evs):
-        print(f"  {i:3d} {'wgrad' if 'wgrad' in e.name else 'conv '} {e.time_range.end - e.time_range.start:9.1f}")
+        kind = 'wstck' if 'stack' in e.name else 'wgrad' if 'wgrad' in e.name else 'conv '
+        print(f"  {i:3d} {kind} {e.time_range.end - e.time_range.start:9.1f}")
 
 if __name__ == "__main__":
     main()
