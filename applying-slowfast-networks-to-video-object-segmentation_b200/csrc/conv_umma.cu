@@ -37,7 +37,7 @@ struct ConvArgs {
     int B, To, H, W;
     int TW, TH, tiles_w, tiles_h, ntiles;
     int N, kt, kh, kw, pad_t, pad_h, pad_w, cchunks;
-    int halo, use_bo, a_stages, b_stages, a_stage_bytes;
+    int halo, use_bo, a_stages, b_stages, a_stage_bytes, b_group;     // b_group = taps per B stage
     uint32_t idesc, tmem_cols, a_tx_bytes;
     void* y;
     int y_bf16, relu, accumulate;
@@ -58,10 +58,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     constexpr uint32_t ROW = BK * 2;                          // bytes per smem row
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = a.N * BK * 2;
+    const int b_bytes = a.N * BK * 2;                         // one tap's weight tile
+    const int b_stage_bytes = a.b_group * b_bytes;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + a.a_stages * a.a_stage_bytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + a.b_stages * b_bytes);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + a.b_stages * b_stage_bytes);
     uint64_t* a_empty = a_full + a.a_stages;
     uint64_t* b_full = a_empty + a.a_stages;
     uint64_t* b_empty = b_full + a.b_stages;
@@ -99,15 +100,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_per_frame = a.tiles_w * a.tiles_h;
-    // outer loop = A loads, inner loop = B loads sharing one A buffer (halo mode: the kh*kw spatial taps)
-    const int outer_h = a.halo ? 1 : a.kh, outer_w = a.halo ? 1 : a.kw;
-    const int inner_h = a.halo ? a.kh : 1, inner_w = a.halo ? a.kw : 1;
 
     if (warp == 0) {
         if (elect_one()) {
             // ------------------------------ TMA producer ------------------------------
             int as = 0, bs = 0;
             uint32_t aphase = 0, bphase = 0;
+            const int taps_hw = a.kh * a.kw;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const int frame = tile / tiles_per_frame;
                 const int rem = tile - frame * tiles_per_frame;
@@ -116,24 +115,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int b = frame / a.To;
                 const int t = frame - b * a.To;
                 const int h0 = th_i * a.TH, w0 = tw_i * a.TW;
-                for (int ta = 0; ta < a.kt; ++ta)
-                    for (int oi = 0; oi < outer_h; ++oi)
-                        for (int oj = 0; oj < outer_w; ++oj)
-                            for (int cc = 0; cc < a.cchunks; ++cc) {
-                                mbar_wait(&a_empty[as], aphase ^ 1);
-                                mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes);
-                                tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK,
-                                            w0 + oj - a.pad_w, h0 + oi - a.pad_h, t + ta - a.pad_t, b);
-                                if (++as == a.a_stages) { as = 0; aphase ^= 1; }
-                                for (int ii = 0; ii < inner_h; ++ii)
-                                    for (int ij = 0; ij < inner_w; ++ij) {
-                                        const int tap = (ta * a.kh + oi + ii) * a.kw + oj + ij;
-                                        mbar_wait(&b_empty[bs], bphase ^ 1);
-                                        mbar_arrive_expect_tx(&b_full[bs], b_bytes);
-                                        tma_load_2d(smem_b + bs * b_bytes, &tmap_w, &b_full[bs], (tap * a.cchunks + cc) * BK, 0);
-                                        if (++bs == a.b_stages) { bs = 0; bphase ^= 1; }
-                                    }
+                if (!a.halo) {
+                    // per-tap mode: A tile and B tile of one K step share a stage and a barrier
+                    for (int ta = 0; ta < a.kt; ++ta)
+                        for (int ti = 0; ti < a.kh; ++ti)
+                            for (int tj = 0; tj < a.kw; ++tj)
+                                for (int cc = 0; cc < a.cchunks; ++cc) {
+                                    mbar_wait(&a_empty[as], aphase ^ 1);
+                                    mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes + b_bytes);
+                                    tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK,
+                                                w0 + tj - a.pad_w, h0 + ti - a.pad_h, t + ta - a.pad_t, b);
+                                    tma_load_3d(smem_b + as * b_bytes, &tmap_w, &a_full[as], cc * BK, 0,
+                                                (ta * a.kh + ti) * a.kw + tj);
+                                    if (++as == a.a_stages) { as = 0; aphase ^= 1; }
+                                }
+                } else {
+                    // halo mode: one A box (tile + halo) per (temporal tap, chunk); weights in groups of b_group taps
+                    for (int ta = 0; ta < a.kt; ++ta)
+                        for (int cc = 0; cc < a.cchunks; ++cc) {
+                            mbar_wait(&a_empty[as], aphase ^ 1);
+                            mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes);
+                            tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK, w0 - a.pad_w,
+                                        h0 - a.pad_h, t + ta - a.pad_t, b);
+                            if (++as == a.a_stages) { as = 0; aphase ^= 1; }
+                            for (int g = 0; g < taps_hw; g += a.b_group) {
+                                mbar_wait(&b_empty[bs], bphase ^ 1);
+                                mbar_arrive_expect_tx(&b_full[bs], b_stage_bytes);
+                                tma_load_3d(smem_b + bs * b_stage_bytes, &tmap_w, &b_full[bs], cc * BK, 0, ta * taps_hw + g);
+                                if (++bs == a.b_stages) { bs = 0; bphase ^= 1; }
                             }
+                        }
+                }
             }
         }
     } else if (warp == 1) {
@@ -143,8 +155,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint32_t aphase = 0, bphase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            const int outer = a.kt * outer_h * outer_w * a.cchunks;
-            const uint32_t a_sbo = a.halo ? HALO_LP * ROW : 8 * ROW;
+            const int taps_hw = a.kh * a.kw;
+            const int outer = a.halo ? a.kt * a.cchunks : a.kt * taps_hw * a.cchunks;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -153,23 +165,41 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int o = 0; o < outer; ++o) {
                     mbar_wait(&a_full[as], aphase);
                     const uint32_t a_addr = smem_u32(smem_a + as * a.a_stage_bytes);
-                    for (int ii = 0; ii < inner_h; ++ii)
-                        for (int ij = 0; ij < inner_w; ++ij) {
+                    if (!a.halo) {
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(smem_b + as * b_bytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, 8 * ROW, LAYOUT);
+                            const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, 8 * ROW, LAYOUT);
+                            umma_bf16(d_tmem, adesc, bdesc, a.idesc, accum);
+                            accum = 1;
+                        }
+                    } else {
+                        for (int g = 0; g < taps_hw; g += a.b_group) {
                             mbar_wait(&b_full[bs], bphase);
                             tc_fence_after();
-                            const uint32_t b_addr = smem_u32(smem_b + bs * b_bytes);
-                            const uint32_t a_tap = a_addr + (ii * HALO_LP + ij) * ROW;      // == a_addr outside halo mode
+                            const uint32_t b_base = smem_u32(smem_b + bs * b_stage_bytes);
+                            for (int tl = 0; tl < a.b_group; ++tl) {
+                                const int sp = g + tl;                      // spatial tap index i*kw + j
+                                const int ti = sp / a.kw, tj = sp - ti * a.kw;
+                                // the tap's A operand = the same halo buffer, start shifted by (i lines + j pixels);
+                                // consecutive 8-row groups are one 16-pixel line (HALO_LP rows) apart
+                                const uint32_t a_tap = a_addr + (ti * HALO_LP + tj) * ROW;
+                                const uint32_t b_addr = b_base + tl * b_bytes;
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                uint64_t adesc = umma_smem_desc(a_tap + k * 32, 16, a_sbo, LAYOUT);
-                                if (a.use_bo) adesc |= static_cast<uint64_t>((a_tap >> 7) & 7u) << 49;   // swizzle phase of a shifted start
-                                const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, 8 * ROW, LAYOUT);
-                                umma_bf16(d_tmem, adesc, bdesc, a.idesc, accum);
-                                accum = 1;
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    uint64_t adesc = umma_smem_desc(a_tap + k * 32, 16, HALO_LP * ROW, LAYOUT);
+                                    if (a.use_bo) adesc |= static_cast<uint64_t>((a_tap >> 7) & 7u) << 49;
+                                    const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, 16, 8 * ROW, LAYOUT);
+                                    umma_bf16(d_tmem, adesc, bdesc, a.idesc, accum);
+                                    accum = 1;
+                                }
                             }
                             umma_commit(&b_empty[bs]);
                             if (++bs == a.b_stages) { bs = 0; bphase ^= 1; }
                         }
+                    }
                     umma_commit(&a_empty[as]);
                     if (++as == a.a_stages) { as = 0; aphase ^= 1; }
                 }
@@ -310,7 +340,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     const double eff_tap = choose_tile(a.H, a.W, &a.TW, &a.TH);
     // halo mode: 8 x 16 tiles; worth it when its tiling wastes little more than the per-tap tiling
     a.halo = 0;
-    if (BK == 64 && p->kh == 3 && p->kw == 3 && env_int("SFVOS_HALO", 1)) {
+    if (p->kh == 3 && p->kw == 3 && env_int("SFVOS_HALO", 1)) {
         const long long tiles = (long long)((a.W + 7) / 8) * ((a.H + 15) / 16);
         const double eff_halo = (double)a.H * a.W / (double)(tiles * BM);
         if (eff_halo >= eff_tap - 0.15) { a.halo = 1; a.TW = 8; a.TH = 16; }
@@ -328,15 +358,19 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     uint32_t abox_w, abox_h;
     if (a.halo) {
         abox_w = HALO_LP; abox_h = (uint32_t)(a.TH + 2);
-        a.a_stage_bytes = HALO_LP * (a.TH + 2) * 128;                       // 36 KB
-        a.b_stages = 4;
-        a.a_stages = (smem_budget - a.b_stages * b_bytes) / a.a_stage_bytes;
+        a.a_stage_bytes = HALO_LP * (a.TH + 2) * BK * 2;                    // 36 KB (BK=64) / 18 KB (BK=32)
+        // narrow N: the MMA-issuing thread, not the tensor pipe, is the limiter -> all 9 taps' weights per barrier
+        a.b_group = (9 * b_bytes <= 72 * 1024 && a.N <= 64) ? 9 : 1;
+        const int b_stage = a.b_group * b_bytes;
+        a.b_stages = a.b_group == 9 ? 2 : 4;
+        a.a_stages = (smem_budget - a.b_stages * b_stage) / a.a_stage_bytes;
         if (a.a_stages > 4) a.a_stages = 4;
-        if (a.a_stages > 2 && b_bytes <= 8192) { a.b_stages = 8; }
+        if (a.b_group == 1 && a.a_stages > 2 && b_bytes <= 8192) a.b_stages = 8;
         SF_CHECK(a.a_stages >= 2, "conv_umma: not enough shared memory for the halo pipeline");
     } else {
         abox_w = (uint32_t)a.TW; abox_h = (uint32_t)a.TH;
         a.a_stage_bytes = BM * BK * 2;
+        a.b_group = 1;
         int st = smem_budget / (a.a_stage_bytes + b_bytes);
         if (st > 8) st = 8;
         SF_CHECK(st >= 2, "conv_umma: not enough shared memory for 2 stages");
@@ -367,14 +401,15 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         if (rc) return rc;
     }
     {
-        const uint64_t ktot = (uint64_t)(p->kt * p->kh * p->kw * p->Cp);
-        uint64_t dims[2] = {ktot, (uint64_t)p->N};
-        uint64_t str[1] = {ktot * 2};
-        uint32_t box[2] = {(uint32_t)BK, (uint32_t)p->N};
-        rc = sfvos_make_tmap(&tw, p->w, 2, dims, str, box, BK * 2);
+        // packed weights [N][taps][Cp] viewed as {Cp, N, taps}: a box {BK, N, G} lands as G consecutive [N x BK] tiles
+        const uint64_t taps = (uint64_t)(p->kt * p->kh * p->kw);
+        uint64_t dims[3] = {(uint64_t)p->Cp, (uint64_t)p->N, taps};
+        uint64_t str[2] = {taps * p->Cp * 2, (uint64_t)p->Cp * 2};
+        uint32_t box[3] = {(uint32_t)BK, (uint32_t)p->N, (uint32_t)a.b_group};
+        rc = sfvos_make_tmap(&tw, p->w, 3, dims, str, box, BK * 2);
         if (rc) return rc;
     }
-    const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * b_bytes + 1024 + 8192;
+    const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_group * b_bytes + 1024 + 8192;
     int grid = sfvos_num_sms();
     if (grid > a.ntiles) grid = a.ntiles;
     if (BK == 64) {
