@@ -91,7 +91,7 @@ __global__ void unpack_wgrad_kernel(const UnpackArgs a) {
 // ---- per-channel reductions -------------------------------------------------------------------------------------
 // Block of 256 threads: thread -> (pixel lane, 8-channel group).  G = C/8 groups, L = 256/G pixel lanes.
 constexpr int RED_THREADS = 256;
-constexpr int RED_PIX_PER_CTA = 2048;
+constexpr int RED_PIX_PER_CTA = 512;     // small chunks -> >= 1000 CTAs even for one frame of 192x336
 
 template <int NQ>
 __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NQ][8], int g, int lane_pix, int G, int L,
@@ -162,32 +162,52 @@ bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const flo
     block_reduce_to_global<2>(acc, g, lp, G, L, dst, red_smem);
 }
 
+// dx = k1*dm - k2 - k3*(x - mean) with k1 = gamma*rstd, k2 = k1*sum(dm)/n, k3 = k1*rstd*sum(dm*xhat)/n.
+// Thread -> (pixel lane, fixed 8-channel group): the per-channel constants live in registers for the whole pixel loop.
 template <typename DyT, typename DxT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, int relu, long long npix, int C,
                     const float* __restrict__ sums, DxT* dx, long long dx_cstride, float* dgamma, float* dbeta) {
-    const int G = C / 8;
+    const int G = C / 8, L = RED_THREADS / G;
+    const int g = threadIdx.x % G, lp = threadIdx.x / G;
     const float inv_n = 1.0f / (float)npix;
     if (blockIdx.x == 0 && dgamma != nullptr)
         for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] += sums[c]; dgamma[c] += sums[C + c]; }
-    const long long total = npix * G;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % G);
-        const long long p = idx / G;
-        float d[8], v[8], o[8];
-        load8(dy + p * dy_cstride + g * 8, d);
-        load8(x + p * x_cstride + g * 8, v);
+    if (lp >= L) return;
+    float sc[8], sh[8], mu[8], k1[8], k2[8], k3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = mean[c];
+        k1[j] = gamma[c] * rstd[c];
+        k2[j] = k1[j] * sums[c] * inv_n;
+        k3[j] = k1[j] * rstd[c] * sums[C + c] * inv_n;
+    }
+    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
+    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    for (long long p = p0 + lp; p < p1; p += 2 * L) {
+        const long long q = p + L;
+        const bool two = q < p1;
+        float d0[8], v0[8], d1[8], v1[8];
+        load8(dy + p * dy_cstride + g * 8, d0);
+        load8(x + p * x_cstride + g * 8, v0);
+        if (two) { load8(dy + q * dy_cstride + g * 8, d1); load8(x + q * x_cstride + g * 8, v1); }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = g * 8 + j;
-            const float dm = (relu && fmaf(v[j], scale[c], shift[c]) <= 0.f) ? 0.f : d[j];
-            const float xh = (v[j] - mean[c]) * rstd[c];
-            o[j] = gamma[c] * rstd[c] * (dm - sums[c] * inv_n - xh * sums[C + c] * inv_n);
+            const float dm = (relu && fmaf(v0[j], sc[j], sh[j]) <= 0.f) ? 0.f : d0[j];
+            d0[j] = fmaf(k1[j], dm, -k2[j]) - k3[j] * (v0[j] - mu[j]);
         }
-        store8(dx + p * dx_cstride + g * 8, o);
+        store8(dx + p * dx_cstride + g * 8, d0);
+        if (two) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dm = (relu && fmaf(v1[j], sc[j], sh[j]) <= 0.f) ? 0.f : d1[j];
+                d1[j] = fmaf(k1[j], dm, -k2[j]) - k3[j] * (v1[j] - mu[j]);
+            }
+            store8(dx + q * dx_cstride + g * 8, d1);
+        }
     }
 }
 
@@ -217,23 +237,31 @@ relu_bwd_kernel(const DyT* __restrict__ dy, long long dy_cstride, const YT* __re
 }
 
 template <typename XT, typename YT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RED_THREADS)
 affine_act_kernel(const XT* __restrict__ x, long long x_cstride, YT* y, long long y_cstride, const float* __restrict__ scale,
                   const float* __restrict__ shift, int relu, long long npix, int C) {
-    const int G = C / 8;
-    const long long total = npix * G;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % G);
-        const long long p = idx / G;
-        float v[8];
-        load8(x + p * x_cstride + g * 8, v);
+    const int G = C / 8, L = RED_THREADS / G;
+    const int g = threadIdx.x % G, lp = threadIdx.x / G;
+    if (lp >= L) return;
+    float sc[8], sh[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float r = fmaf(v[j], scale[g * 8 + j], shift[g * 8 + j]);
-            v[j] = relu ? fmaxf(r, 0.f) : r;
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j]; }
+    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
+    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    for (long long p = p0 + lp; p < p1; p += 2 * L) {
+        const long long q = p + L;
+        const bool two = q < p1;
+        float v0[8], v1[8];
+        load8(x + p * x_cstride + g * 8, v0);
+        if (two) load8(x + q * x_cstride + g * 8, v1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float r = fmaf(v0[j], sc[j], sh[j]); v0[j] = relu ? fmaxf(r, 0.f) : r; }
+        store8(y + p * y_cstride + g * 8, v0);
+        if (two) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float r = fmaf(v1[j], sc[j], sh[j]); v1[j] = relu ? fmaxf(r, 0.f) : r; }
+            store8(y + q * y_cstride + g * 8, v1);
         }
-        store8(y + p * y_cstride + g * 8, v);
     }
 }
 
@@ -271,29 +299,56 @@ __global__ void bn_fold_eval_kernel(const float* conv_bias, const float* gamma, 
 }
 
 // ---- layout -----------------------------------------------------------------------------------------------------
-// [F][C][HW] f32 -> [F][HW][cstride]; tile = 64 channels x 32 pixels, block (32, 8)
+// [F][C][HW] f32 -> [F][HW][cstride]; tile = 64 channels x 128 pixels, 256 threads.
+// Load: 8 independent float4 (16 B) loads per thread along the pixel axis (512 B per warp row).  Store: each thread
+// writes 8 consecutive channels of one pixel (16 B bf16 / 32 B f32), 8 threads cover the tile's 64 channels.
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, long long src_fstride, OutT* dst, long long dst_cstride, int C, long long HW) {
-    __shared__ float tile[64][33];
+    __shared__ float tile[64][129];
     const int f = blockIdx.z;
-    const long long p0 = (long long)blockIdx.x * 32;
+    const long long p0 = (long long)blockIdx.x * 128;
     const int c0 = blockIdx.y * 64;
     const float* s = src + (long long)f * src_fstride;
-    for (int cy = threadIdx.y; cy < 64; cy += 8) {
-        const long long p = p0 + threadIdx.x;
-        const int c = c0 + cy;
-        tile[cy][threadIdx.x] = (c < C && p < HW) ? s[(long long)c * HW + p] : 0.f;
+    const int t = threadIdx.x;
+    const int lp4 = (t & 31) * 4, lc = t >> 5;
+    const bool vec_ok = (HW % 4 == 0);
+    float4 buf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + lc + 8 * i;
+        const long long p = p0 + lp4;
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+            const float* r = s + (long long)c * HW + p;
+            if (vec_ok && p + 3 < HW) buf[i] = __ldg(reinterpret_cast<const float4*>(r));
+            else {
+                if (p < HW) buf[i].x = r[0];
+                if (p + 1 < HW) buf[i].y = r[1];
+                if (p + 2 < HW) buf[i].z = r[2];
+                if (p + 3 < HW) buf[i].w = r[3];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float* row = &tile[lc + 8 * i][lp4];
+        row[0] = buf[i].x; row[1] = buf[i].y; row[2] = buf[i].z; row[3] = buf[i].w;
     }
     __syncthreads();
-    for (int py = threadIdx.y; py < 32; py += 8) {
-        const long long p = p0 + py;
-        const int c = c0 + 2 * threadIdx.x;
+    const int cg = t & 7, pl = t >> 3;                 // 8 channel groups x 32 pixels per pass
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const int pp = pass * 32 + pl;
+        const long long p = p0 + pp;
+        const int c = c0 + cg * 8;
         if (p < HW && c < C) {
-            const float v0 = tile[2 * threadIdx.x][py], v1 = tile[2 * threadIdx.x + 1][py];
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = tile[cg * 8 + j][pp];
             OutT* d = dst + ((long long)f * HW + p) * dst_cstride + c;
-            if constexpr (sizeof(OutT) == 2) *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(v0, v1);
-            else *reinterpret_cast<float2*>(d) = make_float2(v0, v1);
+            if (c + 8 <= C) store8(d, v);
+            else for (int j = 0; j < 8 && c + j < C; ++j) d[j] = static_cast<OutT>(v[j]);
         }
     }
 }
@@ -414,9 +469,9 @@ extern "C" int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstrid
     CHECK_C8(C);
     SF_CHECK(x_cstride % 8 == 0 && y_cstride % 8 == 0, "affine_act: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int grid = grid_for(npix * (C / 8), 256);
+    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
     using bf = __nv_bfloat16;
-#define LAUNCH(XT, YT) affine_act_kernel<XT, YT><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const XT*>(x), x_cstride, reinterpret_cast<YT*>(y), y_cstride, scale, shift, relu, npix, (int)C)
+#define LAUNCH(XT, YT) affine_act_kernel<XT, YT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const XT*>(x), x_cstride, reinterpret_cast<YT*>(y), y_cstride, scale, shift, relu, npix, (int)C)
     if (x_dtype == SFVOS_F32 && y_dtype == SFVOS_F32) LAUNCH(float, float);
     else if (x_dtype == SFVOS_F32) LAUNCH(float, bf);
     else if (y_dtype == SFVOS_F32) LAUNCH(bf, float);
@@ -450,9 +505,9 @@ extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_c
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0 && dx_cstride % 8 == 0, "bn_bwd_apply: strides must be multiples of 8");
     SF_CHECK((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply: dgamma and dbeta go together");
     if (npix == 0) return SFVOS_OK;
-    const int grid = grid_for(npix * (C / 8), 256);
+    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
     using bf = __nv_bfloat16;
-#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta)
+#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta)
     if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float);
     else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf);
     else if (dx_dtype == SFVOS_F32) LAUNCH(bf, float);
@@ -483,10 +538,10 @@ extern "C" int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstri
 
 extern "C" int sfvos_nchw_to_nhwc(const float* src, int64_t src_fstride, void* dst, int32_t dst_dtype, int64_t dst_cstride,
                                   int64_t F, int64_t C, int64_t HW, sfvos_stream stream) {
-    SF_CHECK(C % 2 == 0 && dst_cstride % 2 == 0, "nchw_to_nhwc: C and cstride must be even");
+    SF_CHECK(C % 8 == 0 && dst_cstride % 8 == 0, "nchw_to_nhwc: C and cstride must be multiples of 8");
     SF_CHECK(F <= 65535, "nchw_to_nhwc: too many frames in one call");
     if (F == 0 || HW == 0) return SFVOS_OK;
-    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)F), block(32, 8);
+    dim3 grid((unsigned)((HW + 127) / 128), (unsigned)((C + 63) / 64), (unsigned)F), block(256);
     if (dst_dtype == SFVOS_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, CS(stream)>>>(src, src_fstride, reinterpret_cast<__nv_bfloat16*>(dst), dst_cstride, (int)C, HW);
     else nchw_to_nhwc_kernel<float><<<grid, block, 0, CS(stream)>>>(src, src_fstride, reinterpret_cast<float*>(dst), dst_cstride, (int)C, HW);
     SF_LAUNCH_CHECK();
