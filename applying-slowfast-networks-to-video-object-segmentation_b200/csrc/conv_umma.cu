@@ -320,6 +320,10 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+// conv_tstack_umma.cu: temporally-stacked kernel for the Cout = 32 layers
+int sfvos_conv_tstack_applicable(const sfvos_conv_params* p);
+int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream);
+
 extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     SF_CHECK(p != nullptr, "conv_umma: null params");
@@ -334,6 +338,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     SF_CHECK(p->B * p->To * p->H * p->W < (1LL << 31), "conv_umma: too many output pixels");
     int rc = sfvos_device_check();
     if (rc) return rc;
+    if (sfvos_conv_tstack_applicable(p)) return sfvos_conv_tstack_launch(p, stream);
 
     ConvArgs a;
     a.B = (int)p->B; a.To = (int)p->To; a.H = (int)p->H; a.W = (int)p->W;

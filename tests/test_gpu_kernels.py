@@ -42,6 +42,10 @@ CONV_CASES = [
     (1, 2, 48, 84, 256, 224, 2, 3, "slow3-like N=224 kt=2"),
     (3, 1, 14, 14, 256, 256, 1, 3, "mask-head 14x14 N=256"),
     (1, 3, 7, 5, 64, 96, 2, 3, "tiny odd"),
+    (1, 16, 12, 21, 256, 32, 6, 3, "fast1 (2,16): kt=6, 11 output frames in 2 groups"),
+    (1, 32, 8, 9, 64, 32, 11, 3, "fast1 (4,32): kt=11, 22 output frames, 4 tap groups"),
+    (2, 12, 12, 21, 32, 32, 12, 3, "fast3 (4,32): kt=12 -> 1 frame, Cin=32"),
+    (2, 4, 40, 23, 32, 32, 4, 3, "fast3 (1,8): kt=4 -> 1 frame, ragged"),
 ]
 
 
@@ -111,7 +115,8 @@ def test_conv_epilogue_options_and_channel_slices(umma):
 
 
 @pytest.mark.parametrize("umma", [True, False], ids=["umma", "simt"])
-@pytest.mark.parametrize("cin,cout,kt,khw,T", [(256, 192, 2, 3, 4), (32, 64, 3, 1, 5), (256, 224, 1, 3, 1), (32, 32, 3, 3, 6)])
+@pytest.mark.parametrize("cin,cout,kt,khw,T", [(256, 192, 2, 3, 4), (32, 64, 3, 1, 5), (256, 224, 1, 3, 1), (32, 32, 3, 3, 6),
+                                                (32, 32, 4, 3, 4), (32, 32, 11, 3, 22), (32, 32, 6, 3, 11)])
 def test_conv_dgrad(cin, cout, kt, khw, T, umma):
     """Data gradient = the same kernel on dy with flipped/transposed packed weights and 'full' temporal padding."""
     ops = _ops()
