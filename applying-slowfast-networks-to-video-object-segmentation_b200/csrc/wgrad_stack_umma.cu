@@ -193,7 +193,7 @@ int sfvos_wgrad_stack_launch(const sfvos_wgrad_params* p, cudaStream_t stream) {
     a.tg = (a.taps + a.groups - 1) / a.groups;                // balanced groups, <= 14 taps each
     a.mblks = (a.C + 127) / 128;
     const int base_items = a.groups * a.mblks;
-    int splits = (2 * sfvos_num_sms() + base_items - 1) / base_items;
+    int splits = (2 * sfvos_num_sms()) / base_items;          // 1 CTA per SM: keep the grid within whole waves
     int max_splits = (a.ntiles + 7) / 8;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -175,6 +175,10 @@ void choose_ktile(int H, int W, int* PW, int* PH) {
 }  // namespace
 
 int sfvos_wgrad_stack_launch(const sfvos_wgrad_params* p, cudaStream_t stream);   // wgrad_stack_umma.cu
+int sfvos_wgrad_halo_applicable(const sfvos_wgrad_params* p);                     // wgrad_halo_umma.cu
+int sfvos_wgrad_halo_launch(const sfvos_wgrad_params* p, cudaStream_t stream);
+int sfvos_wgrad_c32_applicable(const sfvos_wgrad_params* p);                      // wgrad_c32_umma.cu
+int sfvos_wgrad_c32_launch(const sfvos_wgrad_params* p, cudaStream_t stream);
 
 extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -185,6 +189,8 @@ extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream
     SF_CHECK(p->B > 0 && p->To > 0 && p->H > 0 && p->W > 0, "wgrad_umma: empty tensor");
     int rc = sfvos_device_check();
     if (rc) return rc;
+    if (sfvos_wgrad_c32_applicable(p)) return sfvos_wgrad_c32_launch(p, stream);
+    if (sfvos_wgrad_halo_applicable(p)) return sfvos_wgrad_halo_launch(p, stream);
     if (p->N == 32 && getenv("SFVOS_NO_WGRAD_STACK") == nullptr)
         return sfvos_wgrad_stack_launch(p, stream);     // narrow fast-pathway GEMMs: taps stacked along N
 
@@ -200,7 +206,7 @@ extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream
     a.nb_atoms = (a.N + 63) / 64;
     const int taps = a.kt * a.kh * a.kw;
     const int base_items = taps * a.mblks;
-    int splits = (4 * sfvos_num_sms() + base_items - 1) / base_items;
+    int splits = (4 * sfvos_num_sms()) / base_items;          // 1 CTA per SM: keep the grid within whole waves
     int max_splits = (a.ntiles + 7) / 8;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

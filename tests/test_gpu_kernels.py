@@ -143,7 +143,9 @@ def test_conv_dgrad(cin, cout, kt, khw, T, umma):
 
 @pytest.mark.parametrize("umma", [True, False], ids=["umma", "simt"])
 @pytest.mark.parametrize("cin,cout,kt,khw,T,H,W", [(256, 192, 1, 3, 1, 16, 16), (256, 32, 3, 3, 5, 12, 21), (32, 64, 4, 1, 6, 12, 21),
-                                                   (32, 32, 3, 3, 5, 24, 42), (256, 224, 2, 3, 3, 12, 21), (256, 256, 1, 3, 1, 14, 14)])
+                                                   (32, 32, 3, 3, 5, 24, 42), (256, 224, 2, 3, 3, 12, 21), (256, 256, 1, 3, 1, 14, 14),
+                                                   (32, 32, 4, 3, 4, 40, 23), (32, 32, 6, 3, 11, 12, 21), (32, 32, 12, 3, 12, 9, 10),
+                                                   (256, 32, 6, 3, 16, 9, 21), (64, 32, 2, 3, 3, 7, 5)])
 def test_wgrad(cin, cout, kt, khw, T, H, W, umma):
     ops = _ops()
     B = 2

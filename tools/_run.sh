@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider -x > gpurun_out/t_kernels.log 2>&1; echo "kernels exit $?"; tail -15 gpurun_out/t_kernels.log
-for G in 1 2 3; do for LP in 16 10; do SFVOS_TSTACK_G=$G SFVOS_TSTACK_LP=$LP timeout 120 python tools/bench_conv.py fast1 2>&1 | tail -1; done; done
-SFVOS_TSTACK=0 timeout 120 python tools/bench_conv.py fast1 fast2 fast3 fast2+d fast3+d 2>&1 | tail -5
-timeout 120 python tools/bench_conv.py fast2 fast3 fast2+d fast3+d 2>&1 | tail -4
-SFVOS_TSTACK_LP=10 timeout 120 python tools/bench_conv.py fast2 fast3 fast2+d fast3+d 2>&1 | tail -4
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider -k "wgrad" > gpurun_out/t_kernels.log 2>&1; echo "kernels exit $?"; tail -15 gpurun_out/t_kernels.log
+timeout 120 python tools/bench_conv.py fast1+w fast2+w fast3+w slow1+w slow3+w f2s1+w 2>&1 | tail -6
+SFVOS_WGRAD_C32=0 timeout 120 python tools/bench_conv.py fast2+w fast3+w 2>&1 | tail -2
