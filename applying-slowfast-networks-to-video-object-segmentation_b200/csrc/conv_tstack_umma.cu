@@ -26,7 +26,7 @@ constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
 constexpr int TW = 8, TH = 16;              // spatial tile (8 wide x 16 tall = 128 accumulator rows)
-constexpr int NSP = 9;                      // 3x3 spatial taps
+constexpr int MAX_NSP = 9;                  // 3x3 spatial taps (or 1: k_t x 1 x 1 lateral convolutions)
 
 struct TsArgs {
     int B, To, Ti, H, W;
@@ -68,12 +68,14 @@ __device__ __forceinline__ void tau_range(const TsArgs& a, const Item& it, int t
     *hi = min(a.Ti - 1, it.t1 - 1 + ta0 + gn - 1 - a.pad_t);
 }
 
-template <int BK>
+template <int BK, int NSP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const TsArgs a) {
     constexpr uint32_t LAYOUT = BK == 64 ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
     constexpr uint32_t ROW = BK * 2;                          // bytes per smem row
+    constexpr int HALO = NSP == 9 ? 1 : 0;
+    constexpr int KW = NSP == 9 ? 3 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -132,8 +134,8 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                         for (int tau = lo; tau <= hi; ++tau) {
                             mbar_wait(&a_empty[as], aphase ^ 1);
                             mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes);
-                            tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK, it.w0 - 1,
-                                        it.h0 - 1, tau, it.b);
+                            tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK, it.w0 - HALO,
+                                        it.h0 - HALO, tau, it.b);
                             if (++as == a.a_stages) { as = 0; aphase ^= 1; }
                         }
                 }
@@ -198,7 +200,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                             const uint32_t a_addr = smem_u32(smem_a + as * a.a_stage_bytes);
 #pragma unroll
                             for (int s = 0; s < NSP; ++s) {
-                                const int ti = s / 3, tj = s - ti * 3;
+                                const int ti = s / KW, tj = s - ti * KW;
                                 if (tau == lo) mbar_wait(&b_full[s], bphase);
                                 tc_fence_after();
                                 const uint64_t adesc = adesc0 + ((a_addr + (ti * a.LP + tj) * ROW) >> 4);
@@ -327,7 +329,10 @@ int env_int(const char* name, int dflt) {
 // 1 if sfvos_conv_umma should hand this problem to the temporally-stacked kernel.
 int sfvos_conv_tstack_applicable(const sfvos_conv_params* p) {
     if (!env_int("SFVOS_TSTACK", 1)) return 0;
-    if (p->N != NC || p->kh != 3 || p->kw != 3 || p->pad_h != 1 || p->pad_w != 1) return 0;
+    if (p->N != NC) return 0;
+    const bool k3 = p->kh == 3 && p->kw == 3 && p->pad_h == 1 && p->pad_w == 1;
+    const bool k1 = p->kh == 1 && p->kw == 1 && p->pad_h == 0 && p->pad_w == 0 && p->kt > 1;    // lateral dgrad
+    if (!k3 && !k1) return 0;
     if ((p->OH && p->OH != p->H) || (p->OW && p->OW != p->W)) return 0;
     if ((p->oy_mul && p->oy_mul != 1) || (p->ox_mul && p->ox_mul != 1) || p->oy_off || p->ox_off) return 0;
     if (p->kt > 64 || p->To > 4096) return 0;
@@ -337,6 +342,8 @@ int sfvos_conv_tstack_applicable(const sfvos_conv_params* p) {
 int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     const int BK = (p->Cp % 64 == 0) ? 64 : 32;
     const int ROW = BK * 2;
+    const int NSP = (int)(p->kh * p->kw);                   // 9 or 1
+    const int HALO = NSP == 9 ? 1 : 0;
     TsArgs a;
     a.B = (int)p->B; a.To = (int)p->To; a.Ti = (int)p->T; a.H = (int)p->H; a.W = (int)p->W;
     a.tiles_w = (a.W + TW - 1) / TW;
@@ -354,9 +361,9 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.tmem_cols = cols;
     a.nitems = a.B * a.nfg * a.tiles_per_frame;
     // halo line pitch in smem rows: 10 = exact (tile + 2), 16 = padded
-    a.LP = env_int("SFVOS_TSTACK_LP", 10);
-    SF_CHECK(a.LP >= TW + 2 && a.LP <= 16, "conv_tstack: SFVOS_TSTACK_LP=%d out of range", a.LP);
-    a.a_tx_bytes = (uint32_t)(a.LP * (TH + 2) * ROW);
+    a.LP = HALO ? env_int("SFVOS_TSTACK_LP", 10) : TW;
+    SF_CHECK(a.LP >= TW + 2 * HALO && a.LP <= 16, "conv_tstack: SFVOS_TSTACK_LP=%d out of range", a.LP);
+    a.a_tx_bytes = (uint32_t)(a.LP * (TH + 2 * HALO) * ROW);
     a.a_stage_bytes = (int)((a.a_tx_bytes + 1023u) & ~1023u);
     // temporal taps stacked per MMA: all 9 spatial pieces of a (tap group, chunk) stay resident next to >= 2 (3) A stages
     const int smem_budget = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers, scale/shift, stats*/;
@@ -384,7 +391,7 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
         const uint64_t ts = p->x_tstride ? (uint64_t)p->x_tstride : hs * p->H;
         const uint64_t bs = p->x_bstride ? (uint64_t)p->x_bstride : ts * p->T;
         uint64_t str[4] = {cs * 2, hs * 2, ts * 2, bs * 2};
-        uint32_t box[5] = {(uint32_t)BK, (uint32_t)a.LP, (uint32_t)(TH + 2), 1, 1};
+        uint32_t box[5] = {(uint32_t)BK, (uint32_t)a.LP, (uint32_t)(TH + 2 * HALO), 1, 1};
         rc = sfvos_make_tmap(&tx, p->x, 5, dims, str, box, ROW);
         if (rc) return rc;
     }
@@ -400,13 +407,17 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     const int smem_bytes = a.a_stages * a.a_stage_bytes + NSP * a.piece_bytes + 1024 + 2048;
     int grid = sfvos_num_sms();
     if (grid > a.nitems) grid = a.nitems;
-    if (BK == 64) {
-        SF_CUDA(cudaFuncSetAttribute(conv_tstack_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        conv_tstack_kernel<64><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
-    } else {
-        SF_CUDA(cudaFuncSetAttribute(conv_tstack_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        conv_tstack_kernel<32><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
-    }
+#define SF_TSTACK_LAUNCH(BK_, NSP_)                                                                                  \
+    do {                                                                                                             \
+        SF_CUDA(cudaFuncSetAttribute(conv_tstack_kernel<BK_, NSP_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     227 * 1024));                                                                   \
+        conv_tstack_kernel<BK_, NSP_><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);                         \
+    } while (0)
+    if (BK == 64 && NSP == 9) SF_TSTACK_LAUNCH(64, 9);
+    else if (BK == 32 && NSP == 9) SF_TSTACK_LAUNCH(32, 9);
+    else if (BK == 64) SF_TSTACK_LAUNCH(64, 1);
+    else SF_TSTACK_LAUNCH(32, 1);
+#undef SF_TSTACK_LAUNCH
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

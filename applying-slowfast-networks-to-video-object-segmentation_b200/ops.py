@@ -189,10 +189,12 @@ def affine_act(x, y, scale, shift, relu):
          int(relu), x.npix, x.C, stream())
 
 
-def bn_bwd(dy, raw, bn4, gamma, relu, dx, dgamma, dbeta):
-    """dy, raw (f32), dx: Acts over the same pixels; bn4 = (scale, shift, mean, rstd) [4,C]."""
+def bn_bwd(dy, raw, bn4, gamma, relu, dx, dgamma, dbeta, sums=None):
+    """dy, raw (f32), dx: Acts over the same pixels; bn4 = (scale, shift, mean, rstd) [4,C]; ``sums``: optional
+    zero-filled f32 [2C] scratch."""
     C = raw.C
-    sums = torch.zeros(2 * C, dtype=torch.float32, device=raw.buf.device)
+    if sums is None:
+        sums = torch.zeros(2 * C, dtype=torch.float32, device=raw.buf.device)
     sc, sh, mu, rs = _p(bn4), _p(bn4, C * 4), _p(bn4, 2 * C * 4), _p(bn4, 3 * C * 4)
     call("sfvos_bn_bwd_reduce", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), raw.cstride, sc, sh, mu, rs, int(relu),
          raw.npix, C, _p(sums), stream())

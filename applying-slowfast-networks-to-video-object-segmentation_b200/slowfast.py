@@ -155,18 +155,21 @@ class SlowFastLayers(nn.Module):
     def temporally_enhance_features(self, slow_features, fast_features):
         """list (len B) of {level: [T,256,H,W]} -> OrderedDict{level: [B,256,H,W]} (model.py:151-165)."""
         dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
-        merged = OrderedDict()
         params = self._param_list()
-        for key in slow_features[0].keys():
-            slow_list = [d[key].to(dev) for d in slow_features]
-            fast_list = [d[key].to(dev) for d in fast_features]
-            needs_grad = any(t.requires_grad for t in slow_list + fast_list) and torch.is_grad_enabled()
-            if needs_grad:
-                s = torch.stack(slow_list).transpose(1, 2)
-                f = torch.stack(fast_list).transpose(1, 2)
-                merged[key] = _SlowFastLevelFn.apply(self, True, None, None, s, f, *params)
-            else:
-                merged[key] = _SlowFastLevelFn.apply(self, torch.is_grad_enabled(), slow_list, fast_list, None, None, *params)
+        keys = list(slow_features[0].keys())
+        slow_lists = [[d[key].to(dev) for d in slow_features] for key in keys]
+        fast_lists = [[d[key].to(dev) for d in fast_features] for key in keys]
+        merged = OrderedDict()
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for lst in slow_lists + fast_lists for t in lst)
+        if not needs_grad:
+            outs = _SlowFastPyramidFn.apply(self, torch.is_grad_enabled(), slow_lists, fast_lists, *params)
+            for key, out in zip(keys, outs):
+                merged[key] = out
+            return merged
+        for key, slow_list, fast_list in zip(keys, slow_lists, fast_lists):     # inputs carry gradient: per-level nodes
+            s = torch.stack(slow_list).transpose(1, 2)
+            f = torch.stack(fast_list).transpose(1, 2)
+            merged[key] = _SlowFastLevelFn.apply(self, True, None, None, s, f, *params)
         return merged
 
 
@@ -196,6 +199,16 @@ def _clips_to_act(clips, dtype):
     return act
 
 
+def _lists_to_acts(slow_list, fast_list, dt_act):
+    """Per-clip [T,256,H,W] tensors -> (fast Act, slow Act); the slow window aliases the fast buffer when it is a frame
+    range of it (what the reference's _slice_features yields)."""
+    fast_in = _clips_to_act(fast_list, dt_act)
+    off = _alias_offset(slow_list, fast_list)
+    if off is not None:
+        return fast_in, fast_in.frames(off, off + slow_list[0].shape[0])
+    return fast_in, _clips_to_act(slow_list, dt_act)
+
+
 def _alias_offset(slow_list, fast_list):
     """If every slow clip is a contiguous frame range of its fast clip (the reference's _slice_features,
     model.py:242-248, yields exactly such views) return the common first-frame offset, else None."""
@@ -216,7 +229,26 @@ def _alias_offset(slow_list, fast_list):
     return off
 
 
-def _conv_bn_forward(mod, spec, x, out, training, saved):
+class _Scratch:
+    """Bump allocator over ONE zero-filled f32 tensor: every small statistics / gradient buffer of a step is a view
+    of it, so a step issues one fill instead of hundreds (each torch.zeros is a kernel launch plus host overhead)."""
+
+    def __init__(self, n, device):
+        self.buf = torch.zeros(n, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, n):
+        v = self.buf[self.off:self.off + n]
+        assert v.numel() == n, "scratch exhausted"
+        self.off += (n + 3) // 4 * 4            # keep every view 16-byte aligned (vector atomics)
+        return v
+
+
+def _fwd_scratch_size(mod, n_levels):
+    return n_levels * sum(6 * s.cout + 8 for s in mod._specs.values())
+
+
+def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
     """conv -> BN (-> ReLU) of one layer, writing into ``out`` (an Act, possibly a channel slice)."""
     conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
     umma = mod._umma
@@ -226,13 +258,13 @@ def _conv_bn_forward(mod, spec, x, out, training, saved):
     pad = (0, spec.pad, spec.pad)
     if training:
         raw = Act.empty(x.B, to, x.H, x.W, spec.cout, torch.float32, dev)
-        stats = torch.zeros(2 * spec.cout, dtype=torch.float32, device=dev)
+        stats = scratch.take(2 * spec.cout) if scratch is not None else torch.zeros(2 * spec.cout, dtype=torch.float32, device=dev)
         if umma:
             ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=True, stats=stats)
         else:
             ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=False)
             ops.channel_stats(raw, stats)
-        bn4 = torch.empty(4 * spec.cout, dtype=torch.float32, device=dev)
+        bn4 = scratch.take(4 * spec.cout) if scratch is not None else torch.empty(4 * spec.cout, dtype=torch.float32, device=dev)
         track = bn.track_running_stats and bn.running_mean is not None
         ops.bn_finalize(stats, raw.npix, conv.bias, bn.weight, bn.bias, bn.running_mean if track else None,
                         bn.running_var if track else None, bn.num_batches_tracked if track else None,
@@ -247,7 +279,7 @@ def _conv_bn_forward(mod, spec, x, out, training, saved):
                  shift=fold[spec.cout:])
 
 
-def _level_forward(mod, slow_in, fast_in, training, saved):
+def _level_forward(mod, slow_in, fast_in, training, saved, scratch=None):
     """One pyramid level (model.py:118-149 + the concat of :162).  Returns the merged f32 Act [B,1,H,W,256]."""
     sp = mod._specs
     dt_act = mod._act_dtype
@@ -258,25 +290,56 @@ def _level_forward(mod, slow_in, fast_in, training, saved):
     # layer 1 (+ lateral 1 straight into channels 192..255 of the slow buffer)
     f1 = Act.empty(B, t1f, H, W, 32, dt_act, dev)
     s1 = Act.empty(B, t1s, H, W, 256, dt_act, dev)
-    _conv_bn_forward(mod, sp["slow_conv1"], slow_in, s1.slice(0, 192), training, saved)
-    _conv_bn_forward(mod, sp["fast_conv1"], fast_in, f1, training, saved)
-    _conv_bn_forward(mod, sp["conv_f2s1"], f1, s1.slice(192, 64), training, saved)
+    _conv_bn_forward(mod, sp["slow_conv1"], slow_in, s1.slice(0, 192), training, saved, scratch)
+    _conv_bn_forward(mod, sp["fast_conv1"], fast_in, f1, training, saved, scratch)
+    _conv_bn_forward(mod, sp["conv_f2s1"], f1, s1.slice(192, 64), training, saved, scratch)
     # layer 2
     f2 = Act.empty(B, t2f, H, W, 32, dt_act, dev)
     s2 = Act.empty(B, t2s, H, W, 256, dt_act, dev)
-    _conv_bn_forward(mod, sp["slow_conv2"], s1, s2.slice(0, 192), training, saved)
-    _conv_bn_forward(mod, sp["fast_conv2"], f1, f2, training, saved)
-    _conv_bn_forward(mod, sp["conv_f2s2"], f2, s2.slice(192, 64), training, saved)
+    _conv_bn_forward(mod, sp["slow_conv2"], s1, s2.slice(0, 192), training, saved, scratch)
+    _conv_bn_forward(mod, sp["fast_conv2"], f1, f2, training, saved, scratch)
+    _conv_bn_forward(mod, sp["conv_f2s2"], f2, s2.slice(192, 64), training, saved, scratch)
     # layer 3: both pathways land in one f32 [B,H,W,256] buffer = cat([slow, fast], 1).squeeze(2)
     out = Act.empty(B, 1, H, W, 256, torch.float32, dev)
-    _conv_bn_forward(mod, sp["slow_conv3"], s2, out.slice(0, 224), training, saved)
-    _conv_bn_forward(mod, sp["fast_conv3"], f2, out.slice(224, 32), training, saved)
+    _conv_bn_forward(mod, sp["slow_conv3"], s2, out.slice(0, 224), training, saved, scratch)
+    _conv_bn_forward(mod, sp["fast_conv3"], f2, out.slice(224, 32), training, saved, scratch)
     if saved is not None:
         saved["_acts"] = dict(slow_in=slow_in, fast_in=fast_in, f1=f1, s1=s1, f2=f2, s2=s2)
     return out
 
 
-def _layer_backward(mod, spec, dy, x_in, saved, grads, dx=None, dx_accumulate=False, need_dx=True):
+class _GradBank:
+    """Every parameter gradient of the module as a view of ONE zero-filled f32 buffer, plus the packed weight-gradient
+    accumulators and the BN-backward sums.  All pyramid levels accumulate into the same views inside the kernels
+    (atomics / ``+=``), so the 5 levels cost no per-parameter torch.add and one fill."""
+
+    def __init__(self, mod, n_levels, device):
+        specs = list(mod._specs.values())
+        n = 0
+        for s in specs:
+            conv = getattr(mod, s.conv)
+            taps = s.kt * s.khw * s.khw
+            n += 2 * (conv.weight.numel() + 4) + 3 * (s.cout + 4) + n_levels * (2 * s.cout + 4)
+        self.scratch = _Scratch(n, device)
+        self.grads, self.dwp = {}, {}
+        for s in specs:
+            conv, bn = getattr(mod, s.conv), getattr(mod, s.bn)
+            if conv.weight.requires_grad:
+                self.grads[s.conv + ".weight"] = self.scratch.take(conv.weight.numel()).view(conv.weight.shape)
+                self.dwp[s.conv] = self.scratch.take(s.kt * s.khw * s.khw * s.cin * s.cout)
+            if conv.bias is not None:
+                # a per-channel constant added before train-mode BN has exactly zero gradient
+                self.grads[s.conv + ".bias"] = self.scratch.take(s.cout)
+            self.grads[s.bn + ".weight"] = self.scratch.take(s.cout)
+            self.grads[s.bn + ".bias"] = self.scratch.take(s.cout)
+
+    def finish(self, mod):
+        for name, dwp in self.dwp.items():
+            ops.unpack_wgrad(dwp, self.grads[name + ".weight"], 0)
+        return self.grads
+
+
+def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=False, need_dx=True):
     """BN(+ReLU) backward -> weight gradient -> (optionally) data gradient of one layer.
     dy: Act gradient wrt the layer's post-activation output; returns dx Act (f32) or None."""
     conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
@@ -284,21 +347,11 @@ def _layer_backward(mod, spec, dy, x_in, saved, grads, dx=None, dx_accumulate=Fa
     raw, bn4 = saved[spec.conv]
     dev = raw.buf.device
     dconv = Act.empty(raw.B, raw.T, raw.H, raw.W, spec.cout, mod._act_dtype, dev)
-    dgamma = torch.zeros_like(bn.weight)
-    dbeta = torch.zeros_like(bn.bias)
-    ops.bn_bwd(dy, raw, bn4, bn.weight, spec.relu, dconv, dgamma, dbeta)
-    grads[spec.bn + ".weight"], grads[spec.bn + ".bias"] = dgamma, dbeta
+    ops.bn_bwd(dy, raw, bn4, bn.weight, spec.relu, dconv, bank.grads[spec.bn + ".weight"], bank.grads[spec.bn + ".bias"],
+               sums=bank.scratch.take(2 * spec.cout))
     pad = (0, spec.pad, spec.pad)
     if conv.weight.requires_grad:
-        taps = spec.kt * spec.khw * spec.khw
-        dwp = torch.zeros(taps * spec.cin * spec.cout, dtype=torch.float32, device=dev)
-        ops.wgrad(x_in, dconv, spec.k, pad, dwp, umma=umma)
-        gw = torch.zeros_like(conv.weight)
-        ops.unpack_wgrad(dwp, gw, 0)
-        grads[spec.conv + ".weight"] = gw
-    if conv.bias is not None:
-        # a per-channel constant added before train-mode BN has exactly zero gradient
-        grads[spec.conv + ".bias"] = torch.zeros_like(conv.bias)
+        ops.wgrad(x_in, dconv, spec.k, pad, bank.dwp[spec.conv], umma=umma)
     if not need_dx:
         return None
     wd, cpd = mod._packed(spec.conv, 1)
@@ -309,20 +362,40 @@ def _layer_backward(mod, spec, dy, x_in, saved, grads, dx=None, dx_accumulate=Fa
     return dx
 
 
-def _level_backward(mod, saved, g_out, need_input_grad):
-    """g_out: f32 Act [B,1,H,W,256] = gradient of the merged output.  Returns ({param name: grad}, d_slow, d_fast)."""
+def _level_backward(mod, saved, g_out, need_input_grad, bank):
+    """g_out: f32 Act [B,1,H,W,256] = gradient of the merged output; parameter gradients accumulate into ``bank``.
+    Returns (d_slow, d_fast)."""
     sp = mod._specs
     a = saved["_acts"]
-    grads = {}
-    d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, grads)
-    d_f2 = _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, grads)
-    _layer_backward(mod, sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], saved, grads, dx=d_f2, dx_accumulate=True)
-    d_s1 = _layer_backward(mod, sp["slow_conv2"], d_s2.slice(0, 192), a["s1"], saved, grads)
-    d_f1 = _layer_backward(mod, sp["fast_conv2"], d_f2, a["f1"], saved, grads)
-    _layer_backward(mod, sp["conv_f2s1"], d_s1.slice(192, 64), a["f1"], saved, grads, dx=d_f1, dx_accumulate=True)
-    d_slow = _layer_backward(mod, sp["slow_conv1"], d_s1.slice(0, 192), a["slow_in"], saved, grads, need_dx=need_input_grad)
-    d_fast = _layer_backward(mod, sp["fast_conv1"], d_f1, a["fast_in"], saved, grads, need_dx=need_input_grad)
-    return grads, d_slow, d_fast
+    d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, bank)
+    d_f2 = _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, bank)
+    _layer_backward(mod, sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], saved, bank, dx=d_f2, dx_accumulate=True)
+    d_s1 = _layer_backward(mod, sp["slow_conv2"], d_s2.slice(0, 192), a["s1"], saved, bank)
+    d_f1 = _layer_backward(mod, sp["fast_conv2"], d_f2, a["f1"], saved, bank)
+    _layer_backward(mod, sp["conv_f2s1"], d_s1.slice(192, 64), a["f1"], saved, bank, dx=d_f1, dx_accumulate=True)
+    d_slow = _layer_backward(mod, sp["slow_conv1"], d_s1.slice(0, 192), a["slow_in"], saved, bank, need_dx=need_input_grad)
+    d_fast = _layer_backward(mod, sp["fast_conv1"], d_f1, a["fast_in"], saved, bank, need_dx=need_input_grad)
+    return d_slow, d_fast
+
+
+def _grad_to_act(g):
+    b, c, h, w = g.shape
+    gl = g.permute(0, 2, 3, 1)
+    if gl.is_contiguous() and g.dtype == torch.float32:
+        return Act(gl.reshape(-1), b, 1, h, w, c, c, 0)
+    g_act = Act.empty(b, 1, h, w, c, torch.float32, g.device)
+    ops.nchw_to_nhwc(g.float().contiguous(), g_act)
+    return g_act
+
+
+def _param_names(mod):
+    names = []
+    for s in mod._specs.values():
+        names.append(s.conv + ".weight")
+        if getattr(mod, s.conv).bias is not None:
+            names.append(s.conv + ".bias")
+        names.extend([s.bn + ".weight", s.bn + ".bias"])
+    return names
 
 
 def _act_to_ncdhw(act):
@@ -342,25 +415,15 @@ class _SlowFastLevelFn(torch.autograd.Function):
             fast_in = _to_act(fast5, dt_act)
             slow_in = _to_act(slow5, dt_act)
         else:
-            fast_in = _clips_to_act(fast_list, dt_act)
-            off = _alias_offset(slow_list, fast_list)
-            if off is not None:
-                slow_in = fast_in.frames(off, off + slow_list[0].shape[0])
-            else:
-                slow_in = _clips_to_act(slow_list, dt_act)
+            fast_in, slow_in = _lists_to_acts(slow_list, fast_list, dt_act)
         training = mod.training
         want_grad = training and grad_enabled and (
             any(p.requires_grad for p in params) or (fast5 is not None and (fast5.requires_grad or slow5.requires_grad)))
         saved = {} if want_grad else None
-        out = _level_forward(mod, slow_in, fast_in, training, saved)
+        scratch = _Scratch(_fwd_scratch_size(mod, 1), fast_in.buf.device) if training else None
+        out = _level_forward(mod, slow_in, fast_in, training, saved, scratch)
         ctx.mod, ctx.saved_acts = mod, saved
         ctx.need_input_grad = fast5 is not None and (fast5.requires_grad or slow5.requires_grad)
-        ctx.names = []
-        for s in mod._specs.values():
-            ctx.names.append(s.conv + ".weight")
-            if getattr(mod, s.conv).bias is not None:
-                ctx.names.append(s.conv + ".bias")
-            ctx.names.extend([s.bn + ".weight", s.bn + ".bias"])
         merged = out.as_nchw()                      # [B,256,H,W] f32 view, channels_last strides
         if saved is None:
             ctx.mark_non_differentiable(merged)
@@ -371,15 +434,49 @@ class _SlowFastLevelFn(torch.autograd.Function):
         mod, saved = ctx.mod, ctx.saved_acts
         if saved is None:
             raise RuntimeError("SlowFastLayers: backward needs a train-mode forward with grad enabled")
-        b, c, h, w = g.shape
-        gl = g.permute(0, 2, 3, 1)
-        if gl.is_contiguous() and g.dtype == torch.float32:
-            g_act = Act(gl.reshape(-1), b, 1, h, w, c, c, 0)
-        else:
-            g_act = Act.empty(b, 1, h, w, c, torch.float32, g.device)
-            ops.nchw_to_nhwc(g.float().contiguous(), g_act)
-        grads, d_slow, d_fast = _level_backward(mod, saved, g_act, ctx.need_input_grad)
+        bank = _GradBank(mod, 1, g.device)
+        d_slow, d_fast = _level_backward(mod, saved, _grad_to_act(g), ctx.need_input_grad, bank)
+        grads = bank.finish(mod)
         ctx.saved_acts = None
         g_slow = _act_to_ncdhw(d_slow) if d_slow is not None else None
         g_fast = _act_to_ncdhw(d_fast) if d_fast is not None else None
-        return (None, None, None, None, g_slow, g_fast) + tuple(grads.get(n) for n in ctx.names)
+        return (None, None, None, None, g_slow, g_fast) + tuple(grads.get(n) for n in _param_names(mod))
+
+
+class _SlowFastPyramidFn(torch.autograd.Function):
+    """All pyramid levels of temporally_enhance_features (model.py:151-165) in ONE autograd node: the levels share the
+    statistics scratch and accumulate their parameter gradients in-kernel into one buffer (no per-level torch.add)."""
+
+    @staticmethod
+    def forward(ctx, mod, grad_enabled, slow_lists, fast_lists, *params):
+        ops.device_check()
+        ctx.set_materialize_grads(False)
+        dt_act = mod._act_dtype
+        training = mod.training
+        want_grad = training and grad_enabled and any(p.requires_grad for p in params)
+        dev = fast_lists[0][0].device
+        scratch = _Scratch(_fwd_scratch_size(mod, len(fast_lists)), dev) if training else None
+        outs, saved_all = [], []
+        for slow_list, fast_list in zip(slow_lists, fast_lists):
+            fast_in, slow_in = _lists_to_acts(slow_list, fast_list, dt_act)
+            saved = {} if want_grad else None
+            outs.append(_level_forward(mod, slow_in, fast_in, training, saved, scratch).as_nchw())
+            saved_all.append(saved)
+        ctx.mod, ctx.saved_all = mod, (saved_all if want_grad else None)
+        if not want_grad:
+            ctx.mark_non_differentiable(*outs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        mod, saved_all = ctx.mod, ctx.saved_all
+        if saved_all is None:
+            raise RuntimeError("SlowFastLayers: backward needs a train-mode forward with grad enabled")
+        live = [i for i, g in enumerate(gs) if g is not None]
+        bank = _GradBank(mod, max(1, len(live)), gs[live[0]].device)
+        for i in reversed(live):
+            _level_backward(mod, saved_all[i], _grad_to_act(gs[i]), False, bank)
+            saved_all[i] = None
+        grads = bank.finish(mod)
+        ctx.saved_all = None
+        return (None, None, None, None) + tuple(grads.get(n) for n in _param_names(mod))

@@ -116,7 +116,8 @@ def test_conv_epilogue_options_and_channel_slices(umma):
 
 @pytest.mark.parametrize("umma", [True, False], ids=["umma", "simt"])
 @pytest.mark.parametrize("cin,cout,kt,khw,T", [(256, 192, 2, 3, 4), (32, 64, 3, 1, 5), (256, 224, 1, 3, 1), (32, 32, 3, 3, 6),
-                                                (32, 32, 4, 3, 4), (32, 32, 11, 3, 22), (32, 32, 6, 3, 11)])
+                                                (32, 32, 4, 3, 4), (32, 32, 11, 3, 22), (32, 32, 6, 3, 11),
+                                                (32, 64, 6, 1, 6), (32, 64, 20, 1, 22)])
 def test_conv_dgrad(cin, cout, kt, khw, T, umma):
     """Data gradient = the same kernel on dy with flipped/transposed packed weights and 'full' temporal padding."""
     ops = _ops()
@@ -139,6 +140,10 @@ def test_conv_dgrad(cin, cout, kt, khw, T, umma):
     dx = ops.Act.empty(B, T, H, W, cin, torch.float32, DEV)
     ops.conv(dya, wd, cp, cin, (kt, khw, khw), (kt - 1, khw - 1 - pad, khw - 1 - pad), T, dx, umma=umma)
     assert _err(_read_act(dx), dx_ref) < 2e-5
+    # accumulate into an existing f32 gradient (how the lateral path merges into the fast pathway's gradient)
+    dx.buf.fill_(0.25)
+    ops.conv(dya, wd, cp, cin, (kt, khw, khw), (kt - 1, khw - 1 - pad, khw - 1 - pad), T, dx, umma=umma, accumulate=True)
+    assert _err(_read_act(dx), dx_ref + 0.25) < 2e-5
 
 
 @pytest.mark.parametrize("umma", [True, False], ids=["umma", "simt"])

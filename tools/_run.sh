@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider -k "wgrad" > gpurun_out/t_kernels.log 2>&1; echo "kernels exit $?"; tail -15 gpurun_out/t_kernels.log
-timeout 120 python tools/bench_conv.py fast1+w fast2+w fast3+w slow1+w slow3+w f2s1+w 2>&1 | tail -6
-SFVOS_WGRAD_C32=0 timeout 120 python tools/bench_conv.py fast2+w fast3+w 2>&1 | tail -2
+bash tools/gpu_tests.sh test_gpu_kernels test_gpu_slowfast test_gpu_roi_mask > gpurun_out/tests.log 2>&1; grep -E "^===|^exit|passed|failed|Error|error" gpurun_out/tests.log | head -30
+timeout 120 python tools/bench_conv.py f2s1+d f2s2+d 2>&1 | tail -2
+python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_v8.json 2> gpurun_out/bench_v8.err; echo "bench exit $?"; cat gpurun_out/bench_v8.json; tail -3 gpurun_out/bench_v8.err
+python tools/profile_step.py --rows 24 > gpurun_out/prof_step_v8.txt 2>&1; echo "prof exit $?"; head -36 gpurun_out/prof_step_v8.txt | cut -c1-75,120-230
