@@ -68,7 +68,7 @@ _SIGS = {
     "sfvos_axpby": [vp, vp, f32, f32, i64, vp],
 }
 
-EXPORTED = sorted(list(_SIGS) + ["sfvos_last_error"])
+EXPORTED = sorted(list(_SIGS) + ["sfvos_last_error", "sfvos_last_kernel"])
 _lib = None
 
 
@@ -87,6 +87,8 @@ def load():
         fn.restype = ctypes.c_int
     lib.sfvos_last_error.argtypes = []
     lib.sfvos_last_error.restype = ctypes.c_char_p
+    lib.sfvos_last_kernel.argtypes = []
+    lib.sfvos_last_kernel.restype = ctypes.c_char_p
     _lib = lib
     return lib
 
@@ -97,6 +99,10 @@ def check(rc):
 
 
 LAUNCHES = 0   # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+
+
+def last_kernel():
+    return load().sfvos_last_kernel().decode()
 
 
 def call(name, *args):

@@ -29,6 +29,7 @@ void sfvos_set_error(const char* fmt, ...);
         return SFVOS_ERR_CUDA; } } while (0)
 
 int sfvos_num_sms();
+void sfvos_set_kernel(const char* name);      // records which kernel an entry point dispatched to (sfvos_last_kernel)
 
 // Tensor-map (TMA descriptor) construction, tmap.cu.  dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1.  swizzle: 0 none, 64, 128.

@@ -197,6 +197,7 @@ extern "C" int sfvos_conv_simt(const sfvos_conv_params* p, sfvos_stream stream_)
     if (a.npix == 0) return SFVOS_OK;
     dim3 grid((unsigned)((a.npix + TM - 1) / TM), (unsigned)((a.N + TN - 1) / TN));
     conv_simt_kernel<<<grid, 256, 0, stream>>>(a);
+    sfvos_set_kernel("conv_simt");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -235,6 +236,7 @@ extern "C" int sfvos_wgrad_simt(const sfvos_wgrad_params* p, sfvos_stream stream
     splits = (a.npix + a.pix_per_split - 1) / a.pix_per_split;
     dim3 grid((unsigned)(a.ctiles * ntn), (unsigned)taps, (unsigned)splits);
     wgrad_simt_kernel<<<grid, 256, 0, stream>>>(a);
+    sfvos_set_kernel("wgrad_simt");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -418,6 +418,7 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     else if (BK == 64) SF_TSTACK_LAUNCH(64, 1);
     else SF_TSTACK_LAUNCH(32, 1);
 #undef SF_TSTACK_LAUNCH
+    sfvos_set_kernel("conv_tstack");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -424,6 +424,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         conv_umma_kernel<32><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);
     }
+    sfvos_set_kernel("conv_umma");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

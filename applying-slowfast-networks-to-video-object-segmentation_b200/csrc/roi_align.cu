@@ -8,6 +8,8 @@
 // each lane owns 8 consecutive channels, so every bilinear tap is one contiguous row read of C*elem bytes
 // (512 B for bf16, 1 KB for f32 at C=256) with 16-byte vector loads.  Backward scatters with 16-byte vector
 // atomics (red.global.add.v4.f32) into f32 gradient maps.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -175,6 +177,203 @@ __global__ void __launch_bounds__(256) roi_align_bwd_kernel(const RoiArgs a) {
     }
 }
 
+
+// ---- sampling_ratio == 2 fast path -------------------------------------------------------------------------------
+// The bilinear weights of a sample factor into a row part and a column part, and so does the sum over the 2 x 2
+// sampling grid of a bin:  out = 1/4 * sum_r sum_c Wy[r] * Wx[c] * F[r][c]  with Wy / Wx the per-axis weights of the
+// two samples merged by feature row / column.  Neighbouring samples are usually < 2 cells apart, so the 4 x 4 = 16
+// taps of the reference loop collapse to ~3 x 3 distinct cells: fewer L2 reads forward, fewer atomics backward.
+// (Same rule set per sample: -1 / L range test, clamp at 0, lo >= L-1 -> lo = hi = L-1.)
+struct Axis {
+    int idx[4];
+    float w[4];
+    int n;
+};
+
+__device__ __forceinline__ void axis_add(Axis& a, int i, float w) {
+    bool found = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (e < a.n && a.idx[e] == i) { a.w[e] += w; found = true; }
+    if (!found) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (e == a.n) { a.idx[e] = i; a.w[e] = w; }
+        a.n++;
+    }
+}
+
+__device__ __forceinline__ Axis make_axis2(float start, float bin, int L) {
+    Axis a;
+    a.n = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { a.idx[e] = 0; a.w[e] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float v = start + ((float)i + 0.5f) * bin / 2.0f;
+        if (v < -1.0f || v > (float)L) continue;
+        if (v <= 0.f) v = 0.f;
+        int lo = (int)v, hi;
+        if (lo >= L - 1) { hi = lo = L - 1; v = (float)lo; } else { hi = lo + 1; }
+        const float l = v - lo, h = 1.f - l;
+        axis_add(a, lo, h);
+        axis_add(a, hi, l);
+    }
+    return a;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+
+// One CTA per ROI.  The merged taps depend only on (roi, ph) for rows and (roi, pw) for columns, so the first 2P
+// threads build the 2P axis records once into shared memory; the 8 warps then walk the P*P bins (one warp per bin, lane l
+// owns channels [c0 + 4l, c0 + 4l + 4) of every 128-channel chunk c0: each tap is one fully coalesced 512 B (f32) /
+// 256 B (bf16) warp access) with no geometry arithmetic on their critical path.
+constexpr int MAX_P = 16;
+
+struct AxisRec {
+    int off[4];         // rows: feature row * W; columns: feature column
+    float w[4];         // 0 for unused entries (never loaded / never added)
+};
+
+struct RoiPlan {
+    AxisRec y[MAX_P], x[MAX_P];
+    int lvl, b, H, W;
+};
+
+__device__ __forceinline__ void build_plan(const RoiArgs& a, long long k, RoiPlan* plan) {
+    const int t = threadIdx.x;
+    if (t < 2 * a.P) {
+        const bool is_x = t >= a.P;
+        const int i = is_x ? t - a.P : t;
+        const BinGeom g = bin_geom(a, k, is_x ? 0 : i, is_x ? i : 0);
+        const Axis ax = is_x ? make_axis2(g.x0, g.bw, g.W) : make_axis2(g.y0, g.bh, g.H);
+        AxisRec r;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            r.off[e] = e < ax.n ? (is_x ? ax.idx[e] : ax.idx[e] * g.W) : 0;
+            r.w[e] = e < ax.n ? ax.w[e] : 0.f;
+        }
+        if (is_x) plan->x[i] = r; else plan->y[i] = r;
+        if (t == 0) { plan->lvl = g.lvl; plan->b = g.b; plan->H = g.H; plan->W = g.W; }
+    }
+}
+
+// Pooled value of one bin for channels [c, c+4): the distinct cells (<= 16, typically 9) are fetched with independent
+// predicated loads, all in flight together, ahead of the FMAs.
+template <typename FT>
+__device__ __forceinline__ float4 pool_bin4(const FT* base, const AxisRec& ry, const AxisRec& rx, long long cstride, int c) {
+    float4 v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            v[r][q] = (ry.w[r] != 0.f && rx.w[q] != 0.f) ? ld4(base + (long long)(ry.off[r] + rx.off[q]) * cstride + c)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float w = ry.w[r] * rx.w[q];
+            acc.x = fmaf(w, v[r][q].x, acc.x); acc.y = fmaf(w, v[r][q].y, acc.y);
+            acc.z = fmaf(w, v[r][q].z, acc.z); acc.w = fmaf(w, v[r][q].w, acc.w);
+        }
+    acc.x *= 0.25f; acc.y *= 0.25f; acc.z *= 0.25f; acc.w *= 0.25f;
+    return acc;
+}
+
+// NCHW = false: output [K,P,P,C] written straight from registers (coalesced rows).
+// NCHW = true : output [K,C,P,P] (what the torch box head flattens) staged as a [C][P*P] tile in shared memory and
+//               written as one contiguous, fully coalesced C*P*P block.
+template <typename FT, bool NCHW>
+__global__ void __launch_bounds__(256, 2) roi_align_fwd2_kernel(const RoiArgs a) {
+    extern __shared__ float s_tile[];                     // NCHW only: [C][P*P]
+    __shared__ RoiPlan plan;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long k = blockIdx.x;
+    const int pp = a.P * a.P;
+    build_plan(a, k, &plan);
+    __syncthreads();
+    const FT* base = reinterpret_cast<const FT*>(a.feat[plan.lvl]) + (long long)plan.b * plan.H * plan.W * a.cstride;
+    for (int b = warp; b < pp; b += nwarp) {
+        const int ph = b / a.P, pw = b - ph * a.P;
+        const AxisRec ry = plan.y[ph], rx = plan.x[pw];
+        for (int c = lane * 4; c < a.C; c += 128) {
+            const float4 acc = pool_bin4(base, ry, rx, a.cstride, c);
+            if (NCHW) {
+                s_tile[(c + 0) * pp + b] = acc.x; s_tile[(c + 1) * pp + b] = acc.y;
+                s_tile[(c + 2) * pp + b] = acc.z; s_tile[(c + 3) * pp + b] = acc.w;
+            } else {
+                const long long o = (k * pp + b) * a.C + c;
+                if (a.out_bf16) {
+                    uint2 u;
+                    u.x = pack_bf16x2(acc.x, acc.y); u.y = pack_bf16x2(acc.z, acc.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = u;
+                } else {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o) = acc;
+                }
+            }
+        }
+    }
+    if (NCHW) {
+        __syncthreads();
+        const long long o = k * a.C * pp;
+        for (int i = threadIdx.x; i < a.C * pp; i += blockDim.x) {
+            if (a.out_bf16) reinterpret_cast<__nv_bfloat16*>(a.out)[o + i] = __float2bfloat16(s_tile[i]);
+            else reinterpret_cast<float*>(a.out)[o + i] = s_tile[i];
+        }
+    }
+}
+
+// Backward: one warp per bin (the atomics are fire-and-forget, so what counts is how many warps issue them); the
+// merged taps cut the 16 vector atomics per bin and channel chunk of the reference loop to ~9.
+__global__ void __launch_bounds__(256) roi_align_bwd2_kernel(const RoiArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long bin = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nbins = a.K * a.P * a.P;
+    if (bin >= nbins) return;
+    const int pw = (int)(bin % a.P), ph = (int)((bin / a.P) % a.P);
+    const long long k = bin / ((long long)a.P * a.P);
+    const BinGeom g = bin_geom(a, k, ph, pw);
+    const Axis ay = make_axis2(g.y0, g.bh, g.H), ax = make_axis2(g.x0, g.bw, g.W);
+    float* base = a.dfeat[g.lvl] + (long long)g.b * g.H * g.W * a.cstride;
+    const long long pp = (long long)a.P * a.P;
+    for (int c = lane * 4; c < a.C; c += 128) {
+        float4 go;
+        if (!a.out_nchw) {
+            go = a.out_bf16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(a.out) + bin * a.C + c)
+                            : ld4(reinterpret_cast<const float*>(a.out) + bin * a.C + c);
+        } else {
+            float v4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long o = (k * a.C + c + j) * pp + ph * a.P + pw;
+                v4[j] = a.out_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.out)[o])
+                                   : reinterpret_cast<const float*>(a.out)[o];
+            }
+            go = make_float4(v4[0], v4[1], v4[2], v4[3]);
+        }
+        go.x *= 0.25f; go.y *= 0.25f; go.z *= 0.25f; go.w *= 0.25f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (r >= ay.n) break;
+            float* row = base + (long long)ay.idx[r] * g.W * a.cstride + c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q >= ax.n) break;
+                const float w = ay.w[r] * ax.w[q];
+                atomicAdd(reinterpret_cast<float4*>(row + (long long)ax.idx[q] * a.cstride),
+                          make_float4(w * go.x, w * go.y, w * go.z, w * go.w));
+            }
+        }
+    }
+}
+
 __global__ void roi_levels_kernel(const float* rois, long long K, int k_min, int k_max, int* levels) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
@@ -186,10 +385,14 @@ __global__ void roi_levels_kernel(const float* rois, long long K, int k_min, int
     levels[k] = (int)lv - k_min;
 }
 
-// project_masks_on_boxes: single-channel u8 image, spatial_scale 1, adaptive grid = ceil(roi_size / M)
-__global__ void mask_targets_kernel(const uint8_t* __restrict__ masks, int n_obj, int H, int W, const float* __restrict__ rois,
-                                    long long K, int M, float* out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// project_masks_on_boxes: single-channel u8 image, spatial_scale 1, adaptive grid = ceil(roi_size / M).
+// One WARP per output bin: a 700-pixel box has 25 x 25 samples per bin, so the lanes stride over the sampling grid
+// (a thread per bin leaves the whole launch waiting on the few largest boxes).
+__global__ void __launch_bounds__(256)
+mask_targets_kernel(const uint8_t* __restrict__ masks, int n_obj, int H, int W, const float* __restrict__ rois,
+                    long long K, int M, float* out) {
+    const int lane = threadIdx.x & 31;
+    const long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (idx >= K * M * M) return;
     const int pw = (int)(idx % M), ph = (int)((idx / M) % M);
     const long long k = idx / ((long long)M * M);
@@ -203,17 +406,17 @@ __global__ void mask_targets_kernel(const uint8_t* __restrict__ masks, int n_obj
     const uint8_t* img = masks + (long long)obj * H * W;
     float acc = 0.f;
     if (obj >= 0 && obj < n_obj)
-        for (int iy = 0; iy < gh; ++iy) {
+        for (int s = lane; s < gh * gw; s += 32) {
+            const int iy = s / gw, ix = s - iy * gw;
             const float y = sh + ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
-            for (int ix = 0; ix < gw; ++ix) {
-                const float x = sw + pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
-                const Tap t = make_tap(y, x, H, W);
-                if (!t.valid) continue;
-                acc += t.w[0] * (float)img[t.off[0]] + t.w[1] * (float)img[t.off[1]] +
-                       t.w[2] * (float)img[t.off[2]] + t.w[3] * (float)img[t.off[3]];
-            }
+            const float x = sw + pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+            const Tap t = make_tap(y, x, H, W);
+            if (!t.valid) continue;
+            acc += t.w[0] * (float)img[t.off[0]] + t.w[1] * (float)img[t.off[1]] +
+                   t.w[2] * (float)img[t.off[2]] + t.w[3] * (float)img[t.off[3]];
         }
-    out[idx] = acc / count;
+    acc = warp_sum(acc);
+    if (lane == 0) out[idx] = acc / count;
 }
 
 int fill_args(const sfvos_roi_params* p, RoiArgs* a, bool bwd) {
@@ -251,10 +454,28 @@ extern "C" int sfvos_roi_align_fwd(const sfvos_roi_params* p, sfvos_stream strea
     int rc = fill_args(p, &a, false);
     if (rc) return rc;
     if (a.K == 0) return SFVOS_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long nbins = a.K * a.P * a.P;
-    const int grid = (int)((nbins + 7) / 8);
-    if (a.feat_bf16) roi_align_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
-    else roi_align_fwd_kernel<float><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    const size_t tile_bytes = a.out_nchw ? (size_t)a.C * a.P * a.P * sizeof(float) : 0;
+    const bool fast = a.sr == 2 && a.C % 4 == 0 && a.P <= MAX_P && tile_bytes <= 160 * 1024 && a.K < (1LL << 31) &&
+                      getenv("SFVOS_ROI_GENERIC") == nullptr;
+    if (fast) {
+#define SF_ROI_FWD(FT, NCHW)                                                                                           \
+    do {                                                                                                               \
+        SF_CUDA(cudaFuncSetAttribute(roi_align_fwd2_kernel<FT, NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)tile_bytes));                                                                \
+        roi_align_fwd2_kernel<FT, NCHW><<<(int)a.K, 256, tile_bytes, st>>>(a);                                         \
+    } while (0)
+        if (a.feat_bf16 && a.out_nchw) SF_ROI_FWD(__nv_bfloat16, true);
+        else if (a.feat_bf16) SF_ROI_FWD(__nv_bfloat16, false);
+        else if (a.out_nchw) SF_ROI_FWD(float, true);
+        else SF_ROI_FWD(float, false);
+#undef SF_ROI_FWD
+    } else {
+        const int grid = (int)((nbins + 7) / 8);
+        if (a.feat_bf16) roi_align_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+        else roi_align_fwd_kernel<float><<<grid, 256, 0, st>>>(a);
+    }
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -264,9 +485,16 @@ extern "C" int sfvos_roi_align_bwd(const sfvos_roi_params* p, sfvos_stream strea
     int rc = fill_args(p, &a, true);
     if (rc) return rc;
     if (a.K == 0) return SFVOS_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long nbins = a.K * a.P * a.P;
-    const int grid = (int)((nbins + 7) / 8);
-    roi_align_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    const size_t tile_bytes = a.out_nchw ? (size_t)a.C * a.P * a.P * sizeof(float) : 0;
+    const bool fast = a.sr == 2 && a.C % 4 == 0 && a.P <= MAX_P && tile_bytes <= 160 * 1024 && a.K < (1LL << 31) &&
+                      getenv("SFVOS_ROI_GENERIC") == nullptr;
+    if (fast) {
+        roi_align_bwd2_kernel<<<(int)((nbins + 7) / 8), 256, 0, st>>>(a);
+    } else {
+        roi_align_bwd_kernel<<<(int)((nbins + 7) / 8), 256, 0, st>>>(a);
+    }
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -275,7 +503,7 @@ extern "C" int sfvos_mask_targets(const uint8_t* masks, int64_t n_obj, int64_t H
                                   int32_t M, float* out, sfvos_stream stream) {
     if (K == 0) return SFVOS_OK;
     const long long total = K * M * M;
-    mask_targets_kernel<<<(int)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(masks, (int)n_obj, (int)H, (int)W, rois, K, M, out);
+    mask_targets_kernel<<<(int)((total + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(masks, (int)n_obj, (int)H, (int)W, rois, K, M, out);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

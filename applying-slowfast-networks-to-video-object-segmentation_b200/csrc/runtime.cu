@@ -13,7 +13,11 @@ void sfvos_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local const char* g_kernel = "";
+void sfvos_set_kernel(const char* name) { g_kernel = name; }
+
 extern "C" const char* sfvos_last_error(void) { return g_err; }
+extern "C" const char* sfvos_last_kernel(void) { return g_kernel; }
 extern "C" int sfvos_version(void) { return 100; }
 
 extern "C" int sfvos_device_check(void) {

@@ -251,6 +251,7 @@ int sfvos_wgrad_c32_launch(const sfvos_wgrad_params* p, cudaStream_t stream) {
     const int smem_bytes = a.x_stages * X_BYTES + 2 * a.dy_bytes + 1024 + 1024;
     SF_CUDA(cudaFuncSetAttribute(wgrad_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     wgrad_c32_kernel<<<a.ngroups * splits, NUM_THREADS, smem_bytes, stream>>>(tx, tdy, a);
+    sfvos_set_kernel("wgrad_c32");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -222,6 +222,7 @@ int sfvos_wgrad_halo_launch(const sfvos_wgrad_params* p, cudaStream_t stream) {
     const int smem_bytes = a.stages * STAGE_BYTES + 1024 + 1024;
     SF_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     wgrad_halo_kernel<<<base_items * splits, NUM_THREADS, smem_bytes, stream>>>(tx, tdy, a);
+    sfvos_set_kernel("wgrad_halo");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -235,6 +235,7 @@ int sfvos_wgrad_stack_launch(const sfvos_wgrad_params* p, cudaStream_t stream) {
     const int smem_bytes = a.stages * stage_bytes + 1024 + 1024;
     SF_CUDA(cudaFuncSetAttribute(wgrad_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     wgrad_stack_kernel<<<base_items * splits, NUM_THREADS, smem_bytes, stream>>>(tx, tdy, a);
+    sfvos_set_kernel("wgrad_stack");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

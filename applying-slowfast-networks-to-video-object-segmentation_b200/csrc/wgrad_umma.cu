@@ -248,6 +248,7 @@ extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream
     SF_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = base_items * splits;
     wgrad_umma_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tdy, a);
+    sfvos_set_kernel("wgrad_umma");
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -23,7 +23,7 @@ def _timed_call(kernel, flops, name, params):
     e0.record()
     call(name, ctypes.byref(params), stream())
     e1.record()
-    TIMING.append((kernel, flops, e0, e1))
+    TIMING.append((_lib.last_kernel() or kernel, flops, e0, e1))
 
 
 def dt(t):
@@ -246,14 +246,26 @@ def _roi_params(feats, dfeats, shapes, scales, N, C, cstride, feat_dtype, rois, 
     return p
 
 
+def _timed_plain(kernel, name, params):
+    """bench.py timing hook for the non-GEMM kernels (work = 0: bench.py knows their algorithmic bytes)."""
+    if TIMING is None:
+        call(name, ctypes.byref(params), stream())
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, ctypes.byref(params), stream())
+    e1.record()
+    TIMING.append((kernel, 0.0, e0, e1))
+
+
 def roi_align_fwd(feats, shapes, scales, N, C, rois, levels, P, sr, out, out_nchw):
     p = _roi_params(feats, None, shapes, scales, N, C, C, dt(feats[0]), rois, levels, P, sr, out, out_nchw)
-    call("sfvos_roi_align_fwd", ctypes.byref(p), stream())
+    _timed_plain(f"roi_align_fwd_p{P}", "sfvos_roi_align_fwd", p)
 
 
 def roi_align_bwd(dfeats, shapes, scales, N, C, rois, levels, P, sr, gout, out_nchw):
     p = _roi_params(None, dfeats, shapes, scales, N, C, C, F32, rois, levels, P, sr, gout, out_nchw)
-    call("sfvos_roi_align_bwd", ctypes.byref(p), stream())
+    _timed_plain(f"roi_align_bwd_p{P}", "sfvos_roi_align_bwd", p)
 
 
 def mask_targets(masks_u8, rois, M):

@@ -336,8 +336,16 @@ def maskrcnn_loss(mask_logits, proposals, gt_masks, gt_labels, mask_matched_idxs
     """Same signature and value as torchvision's maskrcnn_loss (TV roi_heads.py:100-129)."""
     M = mask_logits.shape[-1]
     labels = torch.cat([gl[idxs] for gl, idxs in zip(gt_labels, mask_matched_idxs)], dim=0)
-    targets = [project_masks_on_boxes(m, p, i, M) for m, p, i in zip(gt_masks, proposals, mask_matched_idxs)]
-    targets = torch.cat(targets, dim=0)
+    if len(gt_masks) > 1 and all(m.shape[1:] == gt_masks[0].shape[1:] for m in gt_masks):
+        # same-sized images: one launch for the whole batch (object indices offset into the concatenated masks)
+        offs, n = [], 0
+        for m in gt_masks:
+            offs.append(n)
+            n += m.shape[0]
+        idx = torch.cat([i + o for i, o in zip(mask_matched_idxs, offs)])
+        targets = project_masks_on_boxes(torch.cat(gt_masks), torch.cat(proposals), idx, M)
+    else:
+        targets = torch.cat([project_masks_on_boxes(m, p, i, M) for m, p, i in zip(gt_masks, proposals, mask_matched_idxs)], dim=0)
     if targets.numel() == 0:
         return mask_logits.sum() * 0
     return _MaskBceFn.apply(mask_logits, labels.to(torch.int64).contiguous(), targets.contiguous())

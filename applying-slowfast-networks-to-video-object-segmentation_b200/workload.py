@@ -76,6 +76,32 @@ def conv_flops(sp, fp, levels=LEVELS, fwd_only=False):
     return fwd if fwd_only else 3.0 * fwd - first
 
 
+def roi_align_bytes(boxes, P, e_in, e_out, backward=False, C=256, image_hw=IMAGE_HW, levels=LEVELS):
+    """Algorithmic bytes of one multi-level ROIAlign launch: the output (or its gradient), the UNIQUE
+    feature footprint of every ROI at its level -- C * min(H_l, ceil(h)+1) * min(W_l, ceil(w)+1) elements, no credit
+    for re-reads -- and 20 bytes of ROI record.  Backward reads the output gradient and read-modify-writes the f32
+    footprint (2x); the zero-fill of the gradient maps is a separate kernel and not counted.  boxes: list of [K_i,4]
+    tensors in image pixels (any device)."""
+    names = [k for k in levels if k in POOL_LEVELS]
+    shapes = [levels[k] for k in names]
+    scales = [2.0 ** float(round(math.log2(h / float(image_hw[0])))) for h, _ in shapes]
+    k_min, k_max = int(-math.log2(scales[0])), int(-math.log2(scales[-1]))
+    b = torch.cat([x.detach().float().cpu() for x in boxes])
+    K = b.shape[0]
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lvl = torch.floor(4.0 + torch.log2(torch.sqrt(area) / 224.0) + 1e-6).clamp(k_min, k_max).long() - k_min
+    sc = torch.tensor(scales)[lvl]
+    Hl = torch.tensor([float(s[0]) for s in shapes])[lvl]
+    Wl = torch.tensor([float(s[1]) for s in shapes])[lvl]
+    h = torch.clamp((b[:, 3] - b[:, 1]) * sc, min=1.0)
+    w = torch.clamp((b[:, 2] - b[:, 0]) * sc, min=1.0)
+    cells = (torch.minimum(Hl, torch.ceil(h) + 1) * torch.minimum(Wl, torch.ceil(w) + 1)).sum().item()
+    out_bytes = K * C * P * P * e_out
+    if backward:
+        return out_bytes + 2.0 * cells * C * 4 + K * 20
+    return out_bytes + cells * C * e_in + K * 20
+
+
 MASK_HEAD_FLOPS_PER_ROI = 2.0 * 196 * 256 * 2304 * 4 + 2.0 * 196 * 256 * 1024 + 2.0 * 784 * 2 * 256   # fwd
 
 

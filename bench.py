@@ -214,26 +214,50 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 
-    # ---- roofline of the tensor-core conv kernels from the per-launch CUDA events of the timed region ----
+    # ---- rooflines from the per-launch CUDA events of the timed region ----
+    # tensor-core GEMM kernels: work = algorithmic FLOPs of the launch (no padding / halo / zero-tap FLOPs);
+    # ROIAlign: work = algorithmic bytes of the launch (workload.roi_align_bytes).
+    roi_bytes = {"roi_align_fwd_p7": wl.roi_align_bytes(step.box_props, 7, 4, 4),
+                 "roi_align_fwd_p14": wl.roi_align_bytes(step.mask_props, 14, 4, 2),
+                 "roi_align_bwd_p7": wl.roi_align_bytes(step.box_props, 7, 4, 4, backward=True),
+                 "roi_align_bwd_p14": wl.roi_align_bytes(step.mask_props, 14, 4, 2, backward=True)}
     fam = {}
     for name, flops, a, b in timing:
         d = fam.setdefault(name, [0.0, 0.0, 0])
-        d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
+        d[0] += roi_bytes.get(name, flops); d[1] += a.elapsed_time(b); d[2] += 1
+    tensor = {k: v for k, v in fam.items() if k not in roi_bytes}
     kernels = {k: {"tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1) if v[1] else None, "ms_per_step": round(v[1] / args.steps, 3),
-                   "launches_per_step": v[2] // args.steps, "share_of_step": round(v[1] / args.steps / ms, 3)} for k, v in fam.items()}
-    tot_f = sum(v[0] for v in fam.values()); tot_ms = sum(v[1] for v in fam.values())
-    achieved = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms else 0.0
+                   "launches_per_step": v[2] // args.steps, "share_of_step": round(v[1] / args.steps / ms, 3)}
+               for k, v in sorted(tensor.items(), key=lambda kv: -kv[1][1])}
+    tot_f = sum(v[0] for v in tensor.values()); tot_ms = sum(v[1] for v in tensor.values())
+    achieved_all = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms else 0.0
+    dom = max(tensor, key=lambda k: tensor[k][1]) if tensor else None          # the kernel with the largest share of the step
+    dom_f, dom_ms, dom_n = tensor[dom] if dom else (0.0, 0.0, 0)
+    achieved = dom_f / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("conv_umma_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get(f"{dom}_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "conv_umma + wgrad_umma (all Conv3d/mask-conv fprop, dgrad, wgrad launches)",
+    roofline = {"bound": "tensor", "kernel": f"{dom}_kernel ({dom_n // max(1, args.steps)} launches/step: the dominant kernel by time)",
                 "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
-                "flops_per_step": tot_f / args.steps, "kernel_ms_per_step": round(tot_ms / args.steps, 3), "per_kernel": kernels}
+                "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": traffic,
+                "peak_source": peaks["source"] + ", sustained bf16",
+                "flops_per_launch": dom_f / max(1, dom_n), "us_per_launch": round(dom_ms * 1e3 / max(1, dom_n), 1),
+                "all_tensor_kernels": {"achieved": round(achieved_all, 1), "frac": round(achieved_all / peaks["bf16_sustained"], 4),
+                                       "flops_per_step": tot_f / args.steps, "kernel_ms_per_step": round(tot_ms / args.steps, 3)},
+                "per_kernel": kernels}
+    roi = {}
+    for tag in ("fwd", "bwd"):
+        by = sum(v[0] for k, v in fam.items() if k.startswith("roi_align_" + tag))
+        t = sum(v[1] for k, v in fam.items() if k.startswith("roi_align_" + tag))
+        if t:
+            roi["roi_align_" + tag] = {"bound": "hbm", "achieved": round(by / (t * 1e-3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                       "frac": round(by / (t * 1e-3) / 1e9 / peaks["hbm"], 4), "bytes_per_step": by / args.steps,
+                                       "ms_per_step": round(t / args.steps, 3)}
+    roofline["roi_align"] = roi
 
     # ---- end to end through the public API from pinned host buffers ----
     # Every step's inputs come from pinned HOST memory and every step's loss goes back to the host, all inside the

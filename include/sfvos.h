@@ -37,6 +37,10 @@ int sfvos_version(void);
 const char* sfvos_last_error(void);
 /* 0 iff the current CUDA device is compute capability 10.x (B200).  No fallback exists. */
 int sfvos_device_check(void);
+/* Name of the kernel the last sfvos_conv_* / sfvos_wgrad_* call on this thread dispatched to ("conv_umma",
+ * "conv_tstack", "wgrad_umma", "wgrad_halo", "wgrad_c32", "wgrad_stack", ...): used by the benchmark to attribute
+ * measured launch times to kernels. */
+const char* sfvos_last_kernel(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution (fprop and dgrad share one kernel).
