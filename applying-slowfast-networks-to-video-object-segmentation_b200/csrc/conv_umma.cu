@@ -323,6 +323,9 @@ int env_int(const char* name, int dflt) {
 // conv_tstack_umma.cu: temporally-stacked kernel for the Cout = 32 layers
 int sfvos_conv_tstack_applicable(const sfvos_conv_params* p);
 int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream);
+// conv_pair_umma.cu: CTA-pair (cta_group::2) kernel for the wide 3x3 layers
+int sfvos_conv_pair_applicable(const sfvos_conv_params* p);
+int sfvos_conv_pair_launch(const sfvos_conv_params* p, cudaStream_t stream);
 
 extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -339,6 +342,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     int rc = sfvos_device_check();
     if (rc) return rc;
     if (sfvos_conv_tstack_applicable(p)) return sfvos_conv_tstack_launch(p, stream);
+    if (sfvos_conv_pair_applicable(p)) return sfvos_conv_pair_launch(p, stream);
 
     ConvArgs a;
     a.B = (int)p->B; a.To = (int)p->To; a.H = (int)p->H; a.W = (int)p->W;
