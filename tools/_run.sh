@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider -x -k "conv and umma" > gpurun_out/t_kernels.log 2>&1; echo "kernels exit $?"; tail -15 gpurun_out/t_kernels.log
-timeout 120 python tools/bench_conv.py slow1 slow3 slow2+d 2>&1 | tail -3
-SFVOS_PAIR=0 timeout 120 python tools/bench_conv.py slow1 slow3 slow2+d 2>&1 | tail -3
+bash tools/gpu_tests.sh test_gpu_model test_gpu_roi_mask > gpurun_out/tests.log 2>&1; grep -E "^===|^exit|passed|failed|Error|error|assert" gpurun_out/tests.log | head -30
+python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_v11.json 2> gpurun_out/bench_v11.err; echo "bench exit $?"; cut -c1-200 gpurun_out/bench_v11.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_v11.json')); print(d['value'], d['ms_per_step'], d['e2e']['value']); print(json.dumps(d['roofline'], indent=0)[:1800])"
