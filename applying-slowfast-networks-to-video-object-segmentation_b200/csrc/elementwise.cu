@@ -91,7 +91,13 @@ __global__ void unpack_wgrad_kernel(const UnpackArgs a) {
 // ---- per-channel reductions -------------------------------------------------------------------------------------
 // Block of 256 threads: thread -> (pixel lane, 8-channel group).  G = C/8 groups, L = 256/G pixel lanes.
 constexpr int RED_THREADS = 256;
-constexpr int RED_PIX_PER_CTA = 512;     // small chunks -> >= 1000 CTAs even for one frame of 192x336
+// Pixels per CTA: >= 32 pixel iterations per thread, so the per-channel constants a thread loads into registers are
+// amortised also for the 32-channel fast-pathway tensors (C = 32 -> 2048 px, C >= 128 -> 512 px); small chunks keep
+// >= 1000 CTAs even for one frame of 192x336.
+__host__ __device__ inline int red_ppc(int C) {
+    const int p = 65536 / C;
+    return p < 512 ? 512 : p;
+}
 
 template <int NQ>
 __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NQ][8], int g, int lane_pix, int G, int L,
@@ -117,8 +123,8 @@ channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long lo
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
     float acc[2][8] = {};
-    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
-    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * red_ppc(C);
+    long long p1 = p0 + red_ppc(C); if (p1 > npix) p1 = npix;
     if (lp < L)
         for (long long p = p0 + lp; p < p1; p += L) {
             float v[8];
@@ -144,18 +150,29 @@ bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const flo
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j]; mu[j] = mean[g * 8 + j]; rs[j] = rstd[g * 8 + j]; }
     }
-    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
-    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * red_ppc(C);
+    long long p1 = p0 + red_ppc(C); if (p1 > npix) p1 = npix;
     if (lp < L)
-        for (long long p = p0 + lp; p < p1; p += L) {
-            float d[8], v[8];
-            load8(dy + p * dy_cstride + g * 8, d);
-            load8(x + p * x_cstride + g * 8, v);
+        for (long long p = p0 + lp; p < p1; p += 2 * L) {
+            const long long q = p + L;
+            const bool two = q < p1;
+            float d0[8], v0[8], d1[8], v1[8];
+            load8(dy + p * dy_cstride + g * 8, d0);
+            load8(x + p * x_cstride + g * 8, v0);
+            if (two) { load8(dy + q * dy_cstride + g * 8, d1); load8(x + q * x_cstride + g * 8, v1); }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float dm = (relu && fmaf(v[j], sc[j], sh[j]) <= 0.f) ? 0.f : d[j];
+                const float dm = (relu && fmaf(v0[j], sc[j], sh[j]) <= 0.f) ? 0.f : d0[j];
                 acc[0][j] += dm;
-                acc[1][j] = fmaf(dm, (v[j] - mu[j]) * rs[j], acc[1][j]);
+                acc[1][j] = fmaf(dm, (v0[j] - mu[j]) * rs[j], acc[1][j]);
+            }
+            if (two) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float dm = (relu && fmaf(v1[j], sc[j], sh[j]) <= 0.f) ? 0.f : d1[j];
+                    acc[0][j] += dm;
+                    acc[1][j] = fmaf(dm, (v1[j] - mu[j]) * rs[j], acc[1][j]);
+                }
             }
         }
     float* const dst[2] = {sums, sums + C};
@@ -185,8 +202,8 @@ bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const floa
         k2[j] = k1[j] * sums[c] * inv_n;
         k3[j] = k1[j] * rstd[c] * sums[C + c] * inv_n;
     }
-    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
-    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * 512;
+    long long p1 = p0 + 512; if (p1 > npix) p1 = npix;
     for (long long p = p0 + lp; p < p1; p += 2 * L) {
         const long long q = p + L;
         const bool two = q < p1;
@@ -219,8 +236,8 @@ relu_bwd_kernel(const DyT* __restrict__ dy, long long dy_cstride, const YT* __re
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
     float acc[1][8] = {};
-    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
-    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * red_ppc(C);
+    long long p1 = p0 + red_ppc(C); if (p1 > npix) p1 = npix;
     if (lp < L)
         for (long long p = p0 + lp; p < p1; p += L) {
             float d[8], v[8];
@@ -246,8 +263,8 @@ affine_act_kernel(const XT* __restrict__ x, long long x_cstride, YT* y, long lon
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j]; }
-    const long long p0 = (long long)blockIdx.x * RED_PIX_PER_CTA;
-    long long p1 = p0 + RED_PIX_PER_CTA; if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * 512;
+    long long p1 = p0 + 512; if (p1 > npix) p1 = npix;
     for (long long p = p0 + lp; p < p1; p += 2 * L) {
         const long long q = p + L;
         const bool two = q < p1;
@@ -438,7 +455,7 @@ extern "C" int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int6
     CHECK_C8(C);
     SF_CHECK(cstride % 4 == 0, "channel_stats: cstride must be a multiple of 4");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    const int grid = (int)((npix + red_ppc((int)C) - 1) / red_ppc((int)C));
     channel_stats_kernel<<<grid, RED_THREADS, red_smem_bytes(2, (int)C), CS(stream)>>>(x, npix, (int)C, cstride, sum, sumsq);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
@@ -469,7 +486,7 @@ extern "C" int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstrid
     CHECK_C8(C);
     SF_CHECK(x_cstride % 8 == 0 && y_cstride % 8 == 0, "affine_act: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    const int grid = (int)((npix + 511) / 512);
     using bf = __nv_bfloat16;
 #define LAUNCH(XT, YT) affine_act_kernel<XT, YT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const XT*>(x), x_cstride, reinterpret_cast<YT*>(y), y_cstride, scale, shift, relu, npix, (int)C)
     if (x_dtype == SFVOS_F32 && y_dtype == SFVOS_F32) LAUNCH(float, float);
@@ -487,7 +504,7 @@ extern "C" int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_
     CHECK_C8(C);
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0, "bn_bwd_reduce: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    const int grid = (int)((npix + red_ppc((int)C) - 1) / red_ppc((int)C));
     const size_t sm = red_smem_bytes(2, (int)C);
     if (dy_dtype == SFVOS_F32)
         bn_bwd_reduce_kernel<float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums);
@@ -505,7 +522,7 @@ extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_c
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0 && dx_cstride % 8 == 0, "bn_bwd_apply: strides must be multiples of 8");
     SF_CHECK((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply: dgamma and dbeta go together");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    const int grid = (int)((npix + 511) / 512);
     using bf = __nv_bfloat16;
 #define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta)
     if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float);
@@ -523,7 +540,7 @@ extern "C" int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstri
     CHECK_C8(C);
     SF_CHECK(dy_cstride % 8 == 0 && y_cstride % 8 == 0 && dx_cstride % 8 == 0, "relu_bwd: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + RED_PIX_PER_CTA - 1) / RED_PIX_PER_CTA);
+    const int grid = (int)((npix + red_ppc((int)C) - 1) / red_ppc((int)C));
     const size_t sm = red_smem_bytes(1, (int)C);
     using bf = __nv_bfloat16;
 #define LAUNCH(DT, YT, XT) relu_bwd_kernel<DT, YT, XT><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, reinterpret_cast<const YT*>(y), y_cstride, reinterpret_cast<XT*>(dx), dx_cstride, dbias, npix, (int)C)

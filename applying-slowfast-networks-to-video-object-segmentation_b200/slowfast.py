@@ -115,6 +115,10 @@ class SlowFastLayers(nn.Module):
         kc = spec.cin if mode == 0 else spec.cout
         cp = (32 if kc <= 32 else _round_up(kc, 64)) if self._umma else kc     # 32-wide K steps for Cin = 32 layers
         key = (name, mode, self._umma)
+        if w.is_cuda and torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture the packing kernel must be part of the graph (a replay has to see the
+            # parameter values of ITS step), so the cache is bypassed
+            return ops.pack_weights(w, mode, BF16 if self._umma else F32, cp), cp
         tag = (w.data_ptr(), w._version, str(w.device))
         hit = self._pack_cache.get(key)
         if hit is None or hit[0] != tag:
@@ -339,9 +343,9 @@ class _GradBank:
         return self.grads
 
 
-def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=False, need_dx=True):
+def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=False, need_dx=True, dx_dtype=torch.float32):
     """BN(+ReLU) backward -> weight gradient -> (optionally) data gradient of one layer.
-    dy: Act gradient wrt the layer's post-activation output; returns dx Act (f32) or None."""
+    dy: Act gradient wrt the layer's post-activation output; returns dx Act (``dx_dtype``) or None."""
     conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
     umma = mod._umma
     raw, bn4 = saved[spec.conv]
@@ -356,7 +360,7 @@ def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=Fal
         return None
     wd, cpd = mod._packed(spec.conv, 1)
     if dx is None:
-        dx = Act.empty(x_in.B, x_in.T, x_in.H, x_in.W, spec.cin, torch.float32, dev)
+        dx = Act.empty(x_in.B, x_in.T, x_in.H, x_in.W, spec.cin, dx_dtype, dev)
     dpad = (spec.kt - 1, spec.khw - 1 - spec.pad, spec.khw - 1 - spec.pad)
     ops.conv(dconv, wd, cpd, spec.cin, spec.k, dpad, x_in.T, dx, umma=umma, accumulate=dx_accumulate)
     return dx
@@ -367,10 +371,13 @@ def _level_backward(mod, saved, g_out, need_input_grad, bank):
     Returns (d_slow, d_fast)."""
     sp = mod._specs
     a = saved["_acts"]
-    d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, bank)
+    # the slow pathway's data gradients are consumed once, by the BN-backward passes of the layer below, which round
+    # to the activation dtype anyway: store them in it (bf16 on the product path) -- half the bytes of three passes
+    gdt = mod._act_dtype
+    d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, bank, dx_dtype=gdt)
     d_f2 = _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, bank)
     _layer_backward(mod, sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], saved, bank, dx=d_f2, dx_accumulate=True)
-    d_s1 = _layer_backward(mod, sp["slow_conv2"], d_s2.slice(0, 192), a["s1"], saved, bank)
+    d_s1 = _layer_backward(mod, sp["slow_conv2"], d_s2.slice(0, 192), a["s1"], saved, bank, dx_dtype=gdt)
     d_f1 = _layer_backward(mod, sp["fast_conv2"], d_f2, a["f1"], saved, bank)
     _layer_backward(mod, sp["conv_f2s1"], d_s1.slice(192, 64), a["f1"], saved, bank, dx=d_f1, dx_accumulate=True)
     d_slow = _layer_backward(mod, sp["slow_conv1"], d_s1.slice(0, 192), a["slow_in"], saved, bank, need_dx=need_input_grad)

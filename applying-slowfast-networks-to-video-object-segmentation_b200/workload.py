@@ -160,6 +160,30 @@ class HotPathStep:
                 p.grad = None
         return loss
 
+    def capture(self, features, warmup=2, pool=None):
+        """Capture one forward+backward on ``features`` (static device buffers) into a CUDA graph: ~430 kernel launches
+        become one graph launch, which removes the launch gaps between the (many short) kernels of the small pyramid
+        levels.  Returns (graph, loss): ``graph.replay()`` recomputes ``loss`` and every ``p.grad`` in place from the
+        current contents of ``features`` and the current parameter values (weight packing is part of the graph)."""
+        params = self.parameters()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(features)
+        torch.cuda.current_stream().wait_stream(side)
+        for p in params:
+            p.grad = None
+        graph = torch.cuda.CUDAGraph()
+        try:    # the parameters' AccumulateGrad nodes were created on another stream than the capture stream: expected here
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
+        with torch.cuda.graph(graph, pool=pool):
+            loss, _ = self.forward(features)
+            loss.backward()
+        return graph, loss
+
     def flops_per_step(self):
         conv = conv_flops(self.sp, self.fp, self.levels) * self.B
         mask = 3.0 * MASK_HEAD_FLOPS_PER_ROI * self.k_mask * self.B
