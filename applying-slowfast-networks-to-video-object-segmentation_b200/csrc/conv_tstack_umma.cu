@@ -34,7 +34,7 @@ struct TsArgs {
     int kt, pad_t, G, ngroups, Fg, nfg, cchunks;
     int LP, a_stages, a_stage_bytes, piece_bytes;
     uint32_t a_tx_bytes, tmem_cols;
-    int nbuf;
+    int nbuf, b_resident;
     void* y;
     int y_bf16, relu, accumulate;
     long long y_cstride;
@@ -144,6 +144,8 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     } else if (warp == 3) {
         if (elect_one()) {
             // ------------------------------ weight producer ------------------------------
+            // resident mode (one tap group, one channel chunk, e.g. the Cin = 32 layers): the 9 pieces ARE the whole
+            // weight set, loaded once per CTA; otherwise they are re-streamed per (item, tap group, chunk)
             uint32_t bphase = 0;
             for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
                 const Item it = decode_item(a, item);
@@ -161,6 +163,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                         bphase ^= 1;
                     }
                 }
+                if (a.b_resident) break;
             }
         }
     } else if (warp == 1) {
@@ -174,6 +177,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             const uint64_t adesc0 = umma_smem_desc(0, 16, a.LP * ROW, LAYOUT);
             const uint64_t bdesc0 = umma_smem_desc(0, 16, 8 * ROW, LAYOUT);
             const uint32_t b_base = smem_u32(smem_b);
+            bool b_loaded = false;                      // resident mode: the weights have been waited for once
             for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
                 const Item it = decode_item(a, item);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -201,7 +205,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 #pragma unroll
                             for (int s = 0; s < NSP; ++s) {
                                 const int ti = s / KW, tj = s - ti * KW;
-                                if (tau == lo) mbar_wait(&b_full[s], bphase);
+                                if (tau == lo && !(a.b_resident && b_loaded)) mbar_wait(&b_full[s], bphase);
                                 tc_fence_after();
                                 const uint64_t adesc = adesc0 + ((a_addr + (ti * a.LP + tj) * ROW) >> 4);
                                 const uint64_t bdesc = bdesc0 + ((b_base + s * a.piece_bytes + b_row0) >> 4);
@@ -222,9 +226,10 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
                                     }
                                 }
-                                if (tau == hi) umma_commit(&b_empty[s]);
+                                if (tau == hi && !a.b_resident) umma_commit(&b_empty[s]);
                             }
                             touched |= range;
+                            b_loaded = true;
                             umma_commit(&a_empty[as]);
                             if (++as == a.a_stages) { as = 0; aphase ^= 1; }
                         }
@@ -375,6 +380,7 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.G = (a.kt + a.ngroups - 1) / a.ngroups;
     a.ngroups = (a.kt + a.G - 1) / a.G;
     a.piece_bytes = a.G * NC * ROW;
+    a.b_resident = (a.ngroups == 1 && a.cchunks == 1) ? 1 : 0;
     a.a_stages = (smem_budget - NSP * a.piece_bytes) / a.a_stage_bytes;
     if (a.a_stages > 8) a.a_stages = 8;
     SF_CHECK(a.a_stages >= 2, "conv_tstack: not enough shared memory");

@@ -177,6 +177,8 @@ void choose_ktile(int H, int W, int* PW, int* PH) {
 int sfvos_wgrad_stack_launch(const sfvos_wgrad_params* p, cudaStream_t stream);   // wgrad_stack_umma.cu
 int sfvos_wgrad_halo_applicable(const sfvos_wgrad_params* p);                     // wgrad_halo_umma.cu
 int sfvos_wgrad_halo_launch(const sfvos_wgrad_params* p, cudaStream_t stream);
+int sfvos_wgrad_pair_applicable(const sfvos_wgrad_params* p);                     // wgrad_pair_umma.cu
+int sfvos_wgrad_pair_launch(const sfvos_wgrad_params* p, cudaStream_t stream);
 int sfvos_wgrad_c32_applicable(const sfvos_wgrad_params* p);                      // wgrad_c32_umma.cu
 int sfvos_wgrad_c32_launch(const sfvos_wgrad_params* p, cudaStream_t stream);
 
@@ -189,6 +191,7 @@ extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream
     SF_CHECK(p->B > 0 && p->To > 0 && p->H > 0 && p->W > 0, "wgrad_umma: empty tensor");
     int rc = sfvos_device_check();
     if (rc) return rc;
+    if (sfvos_wgrad_pair_applicable(p)) return sfvos_wgrad_pair_launch(p, stream);
     if (sfvos_wgrad_c32_applicable(p)) return sfvos_wgrad_c32_launch(p, stream);
     if (sfvos_wgrad_halo_applicable(p)) return sfvos_wgrad_halo_launch(p, stream);
     if (p->N == 32 && getenv("SFVOS_NO_WGRAD_STACK") == nullptr)

@@ -23,6 +23,26 @@ def main():
         name = case
         if case.endswith("+d"): mode, name = "d", case[:-2]
         if case.endswith("+w"): mode, name = "w", case[:-2]
+        if name == "convt":            # one tap of the mask predictor's ConvTranspose2d(256,256,2,2): 1x1 GEMM + scatter to 28x28
+            K, Hm = 1024, 14
+            x = ops.Act(torch.randn(K * Hm * Hm * 256, device=dev).bfloat16(), K, 1, Hm, Hm, 256)
+            wt = torch.randn(256, 256, 2, 2, device=dev) / 16
+            wp = ops.pack_weights(wt, 2, ops.BF16, 256, (0, 0))
+            up = ops.Act.empty(K, 1, 2 * Hm, 2 * Hm, 256, torch.bfloat16, dev)
+            bias = torch.zeros(256, device=dev)
+            fn = lambda: ops.conv(x, wp, 256, 256, (1, 1, 1), (0, 0, 0), 1, up, umma=True, relu=True, shift=bias, scatter=(2 * Hm, 2 * Hm, 2, 0, 2, 0))
+            flops = 2.0 * K * Hm * Hm * 256 * 256
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(a.reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sorted(ts)[len(ts) // 2]
+            print(f"{case:12s} 1024 ROIs 14x14: {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s", flush=True)
+            continue
         T, cin, cout, kt, khw = CASES[name]
         pad = 1 if khw == 3 else 0
         To = T - kt + 1
