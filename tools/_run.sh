@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider -x -k "wgrad and umma" > gpurun_out/t_kernels.log 2>&1; echo "kernels exit $?"; tail -3 gpurun_out/t_kernels.log
-timeout 120 python tools/bench_conv.py slow1+w slow3+w 2>&1 | tail -2
-SFVOS_WGRAD_PAIR=0 timeout 120 python tools/bench_conv.py slow1+w slow3+w 2>&1 | tail -2
-timeout 600 python -m pytest tests/test_gpu_roi_mask.py tests/test_gpu_slowfast.py -m gpu -q --no-header -p no:cacheprovider -x 2>&1 | tail -3
+SFVOS_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain_bench.log 2>&1 && SFVOS_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 1700 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_bench.log 2>&1
+echo "ncu list exit $?"; tail -1 gpurun_out/plain_bench.log | cut -c1-200; wc -l gpurun_out/launches_r1c.csv
