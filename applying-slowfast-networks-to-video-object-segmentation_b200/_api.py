@@ -2,7 +2,7 @@
 from . import _lib, ops  # noqa: F401
 from .slowfast import SlowFastLayers  # noqa: F401
 from .roi_heads import (MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, RoIHeads, install,  # noqa: F401
-                        maskrcnn_inference, maskrcnn_loss, project_masks_on_boxes)
+                        maskrcnn_inference, maskrcnn_loss, pool_pair, project_masks_on_boxes)
 
 __all__ = ["SlowFastLayers", "MultiScaleRoIAlign", "MaskRCNNHeads", "MaskRCNNPredictor", "RoIHeads", "install",
-           "maskrcnn_loss", "maskrcnn_inference", "project_masks_on_boxes", "ops", "_lib"]
+           "maskrcnn_loss", "maskrcnn_inference", "project_masks_on_boxes", "pool_pair", "ops", "_lib"]

@@ -419,6 +419,90 @@ mask_targets_kernel(const uint8_t* __restrict__ masks, int n_obj, int H, int W, 
     if (lane == 0) out[idx] = acc / count;
 }
 
+
+// Separable formulation of project_masks_on_boxes: the sampling grid of a bin is dense (spacing <= 1 pixel), so the sum
+// over its gh x gw bilinear samples is  sum_r sum_c Wy[ph][r] * Wx[pw][c] * img[r][c]  with per-axis weights accumulated
+// once per ROI.  One CTA per ROI: (1) 2M threads build the row / column weight tables, (2) T[r][pw] = sum_c Wx[pw][c] *
+// img[r][c] for every image row the ROI touches, (3) out[ph][pw] = sum_r Wy[ph][r] * T[r][pw] / count.  Every mask pixel is
+// read ~once instead of once per sample and tap (4 gh gw byte loads per bin in the reference loop).
+constexpr int MT_SPAN = 64;      // max image rows / columns under one bin (+2): boxes up to M * 62 pixels
+
+struct MtAxis {
+    float w[MT_SPAN];
+    int base, len;
+};
+
+__global__ void __launch_bounds__(256)
+mask_targets_sep_kernel(const uint8_t* __restrict__ masks, int n_obj, int H, int W, const float* __restrict__ rois, int M,
+                        int max_rows, float* out) {
+    extern __shared__ float mt_smem[];
+    MtAxis* ax = reinterpret_cast<MtAxis*>(mt_smem);            // [2][M]: y tables then x tables
+    float* T = reinterpret_cast<float*>(ax + 2 * M);              // [max_rows][M]
+    const long long k = blockIdx.x;
+    const float* r = rois + k * 5;
+    const int obj = (int)r[0];
+    const float sw = r[1], sh = r[2];
+    const float rw = fmaxf(r[3] - r[1], 1.0f), rh = fmaxf(r[4] - r[2], 1.0f);
+    const float bh = rh / (float)M, bw = rw / (float)M;
+    const int gh = (int)ceilf(rh / (float)M), gw = (int)ceilf(rw / (float)M);
+    const float inv_count = 1.0f / fmaxf((float)(gh * gw), 1.0f);
+    float* o = out + k * M * M;
+    if (obj < 0 || obj >= n_obj) {
+        for (int i = threadIdx.x; i < M * M; i += blockDim.x) o[i] = 0.f;
+        return;
+    }
+    if (threadIdx.x < 2 * M) {
+        const bool is_x = threadIdx.x >= M;
+        const int p = is_x ? threadIdx.x - M : threadIdx.x;
+        MtAxis& a = ax[threadIdx.x];
+        const float start = is_x ? sw + p * bw : sh + p * bh, bin = is_x ? bw : bh;
+        const int g = is_x ? gw : gh, L = is_x ? W : H;
+        for (int i = 0; i < MT_SPAN; ++i) a.w[i] = 0.f;
+        int base = -1, last = -1;
+        for (int i = 0; i < g; ++i) {
+            float v = start + ((float)i + 0.5f) * bin / (float)g;
+            if (v < -1.0f || v > (float)L) continue;
+            if (v <= 0.f) v = 0.f;
+            int lo = (int)v, hi;
+            if (lo >= L - 1) { hi = lo = L - 1; v = (float)lo; } else { hi = lo + 1; }
+            const float l = v - lo, h = 1.f - l;
+            if (base < 0) base = lo;
+            if (hi - base < MT_SPAN) { a.w[lo - base] += h; a.w[hi - base] += l; last = hi; }
+        }
+        a.base = base < 0 ? 0 : base;
+        a.len = base < 0 ? 0 : last - base + 1;
+    }
+    __syncthreads();
+    const MtAxis* ay = ax;
+    const MtAxis* axx = ax + M;
+    // rows touched by the ROI
+    int rbase = 1 << 30, rend = 0;
+    for (int p = 0; p < M; ++p)
+        if (ay[p].len > 0) { rbase = min(rbase, ay[p].base); rend = max(rend, ay[p].base + ay[p].len); }
+    int nrows = rend > rbase ? rend - rbase : 0;
+    if (nrows > max_rows) nrows = max_rows;
+    const uint8_t* img = masks + (long long)obj * H * W;
+    for (int i = threadIdx.x; i < nrows * M; i += blockDim.x) {
+        const int row = i / M, pw = i - row * M;
+        const MtAxis& a = axx[pw];
+        const uint8_t* src = img + (long long)(rbase + row) * W + a.base;
+        float acc = 0.f;
+        for (int c = 0; c < a.len; ++c) acc = fmaf(a.w[c], (float)src[c], acc);
+        T[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+        const int ph = i / M, pw = i - ph * M;
+        const MtAxis& a = ay[ph];
+        float acc = 0.f;
+        for (int j = 0; j < a.len; ++j) {
+            const int row = a.base - rbase + j;
+            if (row < nrows) acc = fmaf(a.w[j], T[row * M + pw], acc);
+        }
+        o[i] = acc * inv_count;
+    }
+}
+
 int fill_args(const sfvos_roi_params* p, RoiArgs* a, bool bwd) {
     SF_CHECK(p != nullptr, "roi_align: null params");
     SF_CHECK(p->n_levels >= 1 && p->n_levels <= 4, "roi_align: n_levels must be 1..4");
@@ -502,8 +586,18 @@ extern "C" int sfvos_roi_align_bwd(const sfvos_roi_params* p, sfvos_stream strea
 extern "C" int sfvos_mask_targets(const uint8_t* masks, int64_t n_obj, int64_t H, int64_t W, const float* rois, int64_t K,
                                   int32_t M, float* out, sfvos_stream stream) {
     if (K == 0) return SFVOS_OK;
-    const long long total = K * M * M;
-    mask_targets_kernel<<<(int)((total + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(masks, (int)n_obj, (int)H, (int)W, rois, K, M, out);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // separable kernel: a bin may cover at most MT_SPAN - 2 pixels per axis, and the ROI's row band must fit shared memory
+    const int max_dim = (int)(H > W ? H : W);
+    const int max_rows = (int)H + 2;
+    const size_t smem = (size_t)2 * M * sizeof(MtAxis) + (size_t)max_rows * M * sizeof(float);
+    if (getenv("SFVOS_MASK_TARGETS_GENERIC") == nullptr && M <= 64 && max_dim / M + 3 <= MT_SPAN && smem <= 200 * 1024 && K < (1LL << 31)) {
+        SF_CUDA(cudaFuncSetAttribute(mask_targets_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mask_targets_sep_kernel<<<(int)K, 256, smem, st>>>(masks, (int)n_obj, (int)H, (int)W, rois, M, max_rows, out);
+    } else {
+        const long long total = K * M * M;
+        mask_targets_kernel<<<(int)((total + 7) / 8), 256, 0, st>>>(masks, (int)n_obj, (int)H, (int)W, rois, K, M, out);
+    }
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -129,7 +129,8 @@ class MultiScaleRoIAlign(nn.Module):
         self.k_min = int(-math.log2(self.scales[0]))
         self.k_max = int(-math.log2(self.scales[-1]))
 
-    def forward(self, x: Dict[str, Tensor], boxes: List[Tensor], image_shapes: List[Tuple[int, int]]) -> Tensor:
+    def _prepare(self, x, boxes, image_shapes):
+        """-> (feature maps, rois [K,5] = (image idx, x1, y1, x2, y2), level ids)."""
         feats = [v for k, v in x.items() if k in self.featmap_names]
         if self.scales is None:
             self._setup_scales(feats, image_shapes)
@@ -137,9 +138,76 @@ class MultiScaleRoIAlign(nn.Module):
         ids = torch.cat([torch.full((b.shape[0], 1), float(i), dtype=torch.float32, device=dev) for i, b in enumerate(boxes)])
         rois = torch.cat([ids, torch.cat(boxes).to(device=dev, dtype=torch.float32)], dim=1).contiguous()
         levels = ops.roi_levels(rois, self.k_min, self.k_max) if len(feats) > 1 else None
+        return feats, rois, levels
+
+    def _out_spec(self):
         nchw = self.out_layout == "nchw"
-        out_dtype = torch.float32 if nchw else _act_dtype(self.precision)
+        return nchw, (torch.float32 if nchw else _act_dtype(self.precision))
+
+    def forward(self, x: Dict[str, Tensor], boxes: List[Tensor], image_shapes: List[Tuple[int, int]]) -> Tensor:
+        feats, rois, levels = self._prepare(x, boxes, image_shapes)
+        nchw, out_dtype = self._out_spec()
         return _RoiAlignFn.apply(rois, levels, self.scales, self.output_size[0], self.sampling_ratio, nchw, out_dtype, *feats)
+
+
+class _RoiAlignPairFn(torch.autograd.Function):
+    """Two ROI poolings of the SAME feature maps (the box and the mask branch of a training step) as one autograd node:
+    their backward passes scatter into ONE zero-filled set of gradient maps, instead of two sets that autograd then has
+    to add (a fill plus a read-read-write pass over every pyramid level saved)."""
+
+    @staticmethod
+    def forward(ctx, specs, *feats):
+        ops.device_check()
+        ctx.set_materialize_grads(False)
+        N, C = feats[0].shape[:2]
+        shapes = [tuple(f.shape[-2:]) for f in feats]
+        cl = []
+        for f in feats:
+            if _is_channels_last(f) and f.dtype == torch.float32:
+                cl.append(f.permute(0, 2, 3, 1))
+            else:
+                a = Act.empty(N, 1, f.shape[2], f.shape[3], C, torch.float32, f.device)
+                ops.nchw_to_nhwc(f.float().contiguous(), a)
+                cl.append(a.buf)
+        outs = []
+        for rois, levels, scales, P, sr, nchw, out_dtype in specs:
+            K = rois.shape[0]
+            out = torch.empty((K, C, P, P) if nchw else (K, P, P, C), dtype=out_dtype, device=rois.device)
+            if K:
+                ops.roi_align_fwd(cl, shapes, scales, N, C, rois, levels, P, sr, out, nchw)
+            outs.append(out if nchw else out.permute(0, 3, 1, 2))
+        ctx.specs = specs
+        ctx.meta = (shapes, N, C, [f.dtype for f in feats])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        shapes, N, C, dtypes = ctx.meta
+        dev = next(g for g in gs if g is not None).device
+        dfeats = [torch.zeros(N, h, w, C, dtype=torch.float32, device=dev) for (h, w) in shapes]
+        for g, (rois, levels, scales, P, sr, nchw, _) in zip(gs, ctx.specs):
+            if g is None or rois.shape[0] == 0:
+                continue
+            if nchw:
+                gg = (g if g.dtype in (torch.float32, torch.bfloat16) else g.float()).contiguous()
+            else:
+                gl = g.permute(0, 2, 3, 1)
+                gg = gl if gl.is_contiguous() else gl.contiguous()
+            ops.roi_align_bwd(dfeats, shapes, scales, N, C, rois, levels, P, sr, gg, nchw)
+        return (None,) + tuple(d.permute(0, 3, 1, 2).to(dt) for d, dt in zip(dfeats, dtypes))
+
+
+def pool_pair(pool_a: "MultiScaleRoIAlign", pool_b: "MultiScaleRoIAlign", x, boxes_a, boxes_b, image_shapes):
+    """``(pool_a(x, boxes_a, image_shapes), pool_b(x, boxes_b, image_shapes))`` with a shared backward (see _RoiAlignPairFn)."""
+    feats, rois_a, lv_a = pool_a._prepare(x, boxes_a, image_shapes)
+    feats_b, rois_b, lv_b = pool_b._prepare(x, boxes_b, image_shapes)
+    if len(feats) != len(feats_b) or any(fa is not fb for fa, fb in zip(feats, feats_b)):
+        return pool_a(x, boxes_a, image_shapes), pool_b(x, boxes_b, image_shapes)
+    specs = []
+    for pool, rois, lv in ((pool_a, rois_a, lv_a), (pool_b, rois_b, lv_b)):
+        nchw, out_dtype = pool._out_spec()
+        specs.append((rois, lv, pool.scales, pool.output_size[0], pool.sampling_ratio, nchw, out_dtype))
+    return _RoiAlignPairFn.apply(tuple(specs), *feats)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -374,7 +442,20 @@ class RoIHeads(tv_roi_heads.RoIHeads):
             proposals, matched_idxs, labels, regression_targets = self.select_training_samples(proposals, targets)
         else:
             labels = regression_targets = matched_idxs = None
-        box_features = self.box_roi_pool(features, proposals, image_shapes)
+        mask_features = mask_proposals = pos_matched_idxs = None
+        if (self.training and self.has_mask() and isinstance(self.box_roi_pool, MultiScaleRoIAlign)
+                and isinstance(self.mask_roi_pool, MultiScaleRoIAlign)):
+            # training: the mask branch's proposals (the positives) are known up front, so both poolings share one
+            # autograd node and one set of gradient maps
+            mask_proposals, pos_matched_idxs = [], []
+            for img_id in range(len(proposals)):
+                pos = torch.where(labels[img_id] > 0)[0]
+                mask_proposals.append(proposals[img_id][pos])
+                pos_matched_idxs.append(matched_idxs[img_id][pos])
+            box_features, mask_features = pool_pair(self.box_roi_pool, self.mask_roi_pool, features, proposals, mask_proposals,
+                                                    image_shapes)
+        else:
+            box_features = self.box_roi_pool(features, proposals, image_shapes)
         box_features = self.box_head(box_features)
         class_logits, box_regression = self.box_predictor(box_features)
 
@@ -389,15 +470,15 @@ class RoIHeads(tv_roi_heads.RoIHeads):
                 result.append({"boxes": boxes[i], "labels": labels[i], "scores": scores[i]})
 
         if self.has_mask():
-            mask_proposals = [p["boxes"] for p in result]
-            pos_matched_idxs = None
-            if self.training:
-                mask_proposals, pos_matched_idxs = [], []
-                for img_id in range(len(proposals)):
-                    pos = torch.where(labels[img_id] > 0)[0]
-                    mask_proposals.append(proposals[img_id][pos])
-                    pos_matched_idxs.append(matched_idxs[img_id][pos])
-            mask_features = self.mask_roi_pool(features, mask_proposals, image_shapes)
+            if mask_features is None:
+                mask_proposals = [p["boxes"] for p in result]
+                if self.training:
+                    mask_proposals, pos_matched_idxs = [], []
+                    for img_id in range(len(proposals)):
+                        pos = torch.where(labels[img_id] > 0)[0]
+                        mask_proposals.append(proposals[img_id][pos])
+                        pos_matched_idxs.append(matched_idxs[img_id][pos])
+                mask_features = self.mask_roi_pool(features, mask_proposals, image_shapes)
             mask_features = self.mask_head(mask_features)
             mask_logits = self.mask_predictor(mask_features)
             if self.training:

@@ -9,7 +9,7 @@ from collections import OrderedDict
 import torch
 
 from . import ops
-from .roi_heads import MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, maskrcnn_loss
+from .roi_heads import MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, maskrcnn_loss, pool_pair
 from .slowfast import SlowFastLayers
 
 # 480x854 DAVIS frame -> GeneralizedRCNNTransform -> 749x1333 -> padded 768x1344 -> FPN strides 4..64
@@ -145,9 +145,10 @@ class HotPathStep:
         lo = self.fp // 2 - self.sp // 2
         slow = [OrderedDict((k, v[lo:lo + self.sp]) for k, v in f.items()) for f in features]
         merged = self.slow_fast.temporally_enhance_features(slow, features)
-        box_feats = self.box_roi_pool(merged, self.box_props, self.image_shapes)
+        # both poolings in one autograd node, as RoIHeads.forward does in training (one set of gradient maps)
+        box_feats, mask_feats = pool_pair(self.box_roi_pool, self.mask_roi_pool, merged, self.box_props, self.mask_props,
+                                          self.image_shapes)
         loss_box = box_feats.square().mean()                          # stand-in for the torch box head + losses
-        mask_feats = self.mask_roi_pool(merged, self.mask_props, self.image_shapes)
         logits = self.mask_predictor(self.mask_head(mask_feats))
         loss_mask = maskrcnn_loss(logits, self.mask_props, self.gt_masks, self.gt_labels, self.matched)
         return loss_mask + loss_box, merged

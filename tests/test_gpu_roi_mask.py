@@ -87,6 +87,37 @@ def test_multiscale_roi_align_matches_torchvision_fwd_bwd(P):
     assert o2.shape == r2.shape and _nerr(o2, r2) < 1e-5
 
 
+def test_pool_pair_equals_two_separate_poolings():
+    """The shared-backward pair (box + mask branch of a training step in ONE autograd node) must give the outputs of
+    the two separate poolings and the SUM of their feature gradients."""
+    from sfvos_b200 import MultiScaleRoIAlign, pool_pair
+    boxes = [b.cuda() for b in ro.synthetic_rois(2, 60, image_hw=(187, 333), seed=11, lo=4.0, hi=300.0)]
+    boxes[0] = torch.cat([boxes[0], _edge_boxes().cuda()])
+    sub = [b[:17] for b in boxes]
+    shapes = [(187, 333)] * 2
+    pa = MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, out_layout="nchw", precision="fp32")
+    pb = MultiScaleRoIAlign(["0", "1", "2", "3"], 14, 2, out_layout="nhwc", precision="fp32")
+    f1 = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in _feats(seed=4).items())
+    f2 = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in _feats(seed=4).items())
+    oa, ob = pool_pair(pa, pb, f1, boxes, sub, shapes)
+    ra, rb = pa(f2, boxes, shapes), pb(f2, sub, shapes)
+    assert torch.equal(oa, ra) and torch.equal(ob, rb)
+    g = torch.Generator().manual_seed(1)
+    wa, wb = torch.randn(oa.shape, generator=g).cuda(), torch.randn(ob.shape, generator=g).cuda()
+    ((oa * wa).sum() + (ob * wb).sum()).backward()
+    ((ra * wa).sum() + (rb * wb).sum()).backward()
+    for k in f1:
+        assert _nerr(f1[k].grad, f2[k].grad) < 1e-5, k
+    # only one branch used: the other's gradient is simply absent
+    f3 = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in _feats(seed=4).items())
+    oa3, _ = pool_pair(pa, pb, f3, boxes, sub, shapes)
+    (oa3 * wa).sum().backward()
+    f4 = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in _feats(seed=4).items())
+    (pa(f4, boxes, shapes) * wa).sum().backward()
+    for k in f3:
+        assert _nerr(f3[k].grad, f4[k].grad) < 1e-5, k
+
+
 def test_roi_and_mask_golden_fixture():
     from sfvos_b200 import MultiScaleRoIAlign, MaskRCNNHeads, MaskRCNNPredictor, maskrcnn_loss
     gold = np.load(os.path.join(GOLDEN, "roi_mask.npz"))

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-SFVOS_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain_bench.log 2>&1 && SFVOS_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 1700 --csv --log-file gpurun_out/launches_r1c.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_bench.log 2>&1
-echo "ncu list exit $?"; tail -1 gpurun_out/plain_bench.log | cut -c1-200; wc -l gpurun_out/launches_r1c.csv
+python tools/ncu_kernels.py > gpurun_out/plain_k.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"conv_pair|conv_umma|conv_tstack|wgrad|roi_align" -c 40 -o gpurun_out/prof_kernels_r1c python tools/ncu_kernels.py > gpurun_out/ncu_k.log 2>&1
+echo "ncu exit $?"; tail -3 gpurun_out/ncu_k.log; ls -la gpurun_out/*.ncu-rep
