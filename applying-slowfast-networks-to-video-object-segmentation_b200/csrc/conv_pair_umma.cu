@@ -225,6 +225,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int r = q * 32 + lane;
         const int hl = r / TW, wl = r - hl * TW;
         const bool do_stats = (a.sum != nullptr);
+        const bool affine = (a.scale != nullptr) || (a.shift != nullptr);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int pair = pair0; pair < a.npairs; pair += pair_stride) {
@@ -255,10 +256,24 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 if (valid) {
                     float o[32];
+                    if (affine) {           // per-channel scale / shift from shared memory, 16 bytes per load
+                        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
+                        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
-                        o[j] = a.relu ? fmaxf(x, 0.0f) : x;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 sc = sc4[j], sh = sh4[j];
+                            o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+                            o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+                            o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+                            o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+                    }
+                    if (a.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.0f);
                     }
                     if (a.y_bf16) {
                         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride + c0);

@@ -147,7 +147,6 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
             const int ncl = min(2, n_cls - cls0);
             float wv[2][8], dwacc[2][8] = {};
             for (int q = 0; q < ncl; ++q) ld8(w + (long long)(cls0 + q) * C + c8 * 8, wv[q]);
-#pragma unroll 4
             for (int p = warp; p < ss; p += 8) {
                 float v[8], o[8];
                 ld8(x + (k * ss + p) * C + c8 * 8, v);
