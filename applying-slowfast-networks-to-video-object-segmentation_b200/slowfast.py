@@ -373,7 +373,7 @@ def _level_backward(mod, saved, g_out, need_input_grad, bank):
     a = saved["_acts"]
     # the slow pathway's data gradients are consumed once, by the BN-backward passes of the layer below, which round
     # to the activation dtype anyway: store them in it (bf16 on the product path) -- half the bytes of three passes
-    gdt = mod._act_dtype
+    gdt = mod._act_dtype if os.environ.get("SFVOS_BF16_DGRAD", "1") != "0" else torch.float32
     d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, bank, dx_dtype=gdt)
     d_f2 = _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, bank)
     _layer_backward(mod, sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], saved, bank, dx=d_f2, dx_accumulate=True)

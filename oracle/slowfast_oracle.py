@@ -105,9 +105,31 @@ def param_count(sp, fp):
                if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
 
 
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 and back, gradient passed straight through (used by the bf16 EMULATION mode below)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+# bf16 emulation: the SAME reference graph with the two operands of every convolution (activations and weights) rounded
+# to bf16 and everything else -- accumulation, BatchNorm, gradients -- in fp32.  This is what "bf16 with fp32
+# accumulation" means for this module in plain PyTorch; the GPU bf16 path is compared against it with a tight tolerance,
+# because the ~5e-3 forward rounding flips ~0.3 % of the ReLU masks and that alone moves weight gradients by 5-8 %
+# (relative L2) away from the fp32 reference in ANY bf16 implementation.
+EMULATE_BF16 = False
+
+
 def _conv_bn(sd, conv, bn, x, training, relu, spatial_pad):
     w = sd[conv + ".weight"]
     b = sd.get(conv + ".bias")
+    if EMULATE_BF16:
+        w, x = _RoundBF16.apply(w), _RoundBF16.apply(x)
     y = F.conv3d(x, w, b, padding=(0, spatial_pad, spatial_pad))
     rm, rv = sd[bn + ".running_mean"], sd[bn + ".running_var"]
     if training:
@@ -176,8 +198,18 @@ def module_loss(merged):
     return total
 
 
-def grads_of(sd, slow_features, fast_features, loss_fn=module_loss):
-    """Train-mode forward + backward through the functional graph; returns (merged, loss, {param: grad})."""
+def grads_of(sd, slow_features, fast_features, loss_fn=module_loss, emulate_bf16=False):
+    """Train-mode forward + backward through the functional graph; returns (merged, loss, {param: grad}, buffers).
+    ``emulate_bf16``: see EMULATE_BF16 above."""
+    global EMULATE_BF16
+    prev, EMULATE_BF16 = EMULATE_BF16, bool(emulate_bf16)
+    try:
+        return _grads_of(sd, slow_features, fast_features, loss_fn)
+    finally:
+        EMULATE_BF16 = prev
+
+
+def _grads_of(sd, slow_features, fast_features, loss_fn):
     leaves = {}
     work = OrderedDict()
     for k, v in sd.items():

@@ -1,1 +1,7 @@
-timeout 200 python tools/bench_conv.py --reps 9 fast2 fast3 fast2+d fast3+d f2s1+d f2s2+d f2s1 f2s2 convt 2>&1 | tail -9
+timeout 600 python -m pytest tests/test_gpu_slowfast.py -m gpu -q --no-header -p no:cacheprovider -k "emulated" 2>&1 | grep -E "assert|Error|passed|failed" | head
+python - <<'PY'
+import sys; sys.path.insert(0,'tools'); sys.path.insert(0,'.')
+from collections import OrderedDict
+from grad_err_report import run
+run(2, 16, "bf16", OrderedDict([("0", (8, 12)), ("pool", (4, 6))]), emulate=True)
+PY

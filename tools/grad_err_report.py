@@ -6,11 +6,11 @@ import torch
 from oracle import slowfast_oracle as so
 from sfvos_b200 import SlowFastLayers
 
-def run(sp, fp, precision, levels, n_clips=2):
+def run(sp, fp, precision, levels, n_clips=2, emulate=False):
     fast = [so.synthetic_clip(levels, fp, seed=1234 + 100 * c, zero_left=(fp // 2 if c == 1 else 0)) for c in range(n_clips)]
     slow = [so.slice_window(f, fp // 2, sp) for f in fast]
     sd = so.init_state_dict(sp, fp, seed=63)
-    ref_out, ref_loss, grads, _ = so.grads_of(sd, slow, fast)
+    ref_out, ref_loss, grads, _ = so.grads_of(sd, slow, fast, emulate_bf16=emulate)
     torch.manual_seed(63)
     m = SlowFastLayers(256, torch.device("cuda"), sp, fp).cuda().train()
     m.precision = precision
@@ -18,7 +18,7 @@ def run(sp, fp, precision, levels, n_clips=2):
     sc = [so.slice_window(f, fp // 2, sp) for f in fc]
     out = m.temporally_enhance_features(sc, fc)
     so.module_loss(out).backward()
-    print(f"--- sp={sp} fp={fp} {precision} levels={dict(levels)}")
+    print(f"--- sp={sp} fp={fp} {precision} levels={dict(levels)} vs {'bf16-emulated' if emulate else 'fp32'} oracle")
     for k in out:
         d = out[k].detach().cpu() - ref_out[k].detach()
         print(f"  out[{k}] maxnorm {d.abs().max()/ref_out[k].abs().max():.3e}  relL2 {d.norm()/ref_out[k].norm():.3e}")
