@@ -1,0 +1,129 @@
+"""Parity at BASELINE.json's FULL sizes (level 0 = 192x336 of a 480x854 DAVIS frame), where the CPU oracle is too slow
+to run: size-independent properties of the domain, cross-checks between the two independent kernel families
+(tcgen05 bf16 vs fp32 CUDA-core validation mode) and torchvision's own CUDA ROIAlign on the bench's ROI set."""
+import math
+from collections import OrderedDict
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+H0, W0 = 192, 336
+
+
+def _nerr(a, b):
+    return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-12)
+
+
+def _act(ops, B, T, H, W, C, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return ops.Act(torch.randn(B * T * H * W * C, device=DEV, generator=g).bfloat16(), B, T, H, W, C)
+
+
+@pytest.mark.parametrize("name,T,cin,cout,kt", [("fast_conv1 -> conv_tstack", 8, 256, 32, 3), ("slow_conv2 -> conv_pair", 1, 256, 192, 1),
+                                                ("fast_conv2 -> conv_tstack<32>", 6, 32, 32, 3)])
+def test_conv_scaling_is_exact_at_full_size(name, T, cin, cout, kt):
+    """conv(2x) == 2 conv(x) BIT FOR BIT (a power-of-two scale is exact in bf16 and in the fp32 accumulators), and the
+    fused BN statistics scale by 2 and 4: exercises every tile, tap and temporal group of a full 192x336 launch."""
+    from sfvos_b200 import ops
+    B = 2
+    x = _act(ops, B, T, H0, W0, cin, 1)
+    x2 = ops.Act((x.buf.float() * 2).bfloat16(), B, T, H0, W0, cin)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    w = torch.randn(cout, cin, kt, 3, 3, device=DEV, generator=g) / math.sqrt(cin * kt * 9)
+    cp = 32 if cin <= 32 else cin
+    wp = ops.pack_weights(w, 0, ops.BF16, cp)
+    To = T - kt + 1
+    ys, stats = [], []
+    for inp in (x, x2):
+        y = ops.Act.empty(B, To, H0, W0, cout, torch.float32, DEV)
+        st = torch.zeros(2 * cout, device=DEV)
+        ops.conv(inp, wp, cp, cout, (kt, 3, 3), (0, 1, 1), To, y, umma=True, stats=st)
+        ys.append(y.buf); stats.append(st)
+    assert torch.equal(ys[1], ys[0] * 2)
+    assert ys[0].abs().max().item() > 0.1
+    assert _nerr(stats[1][:cout], 2 * stats[0][:cout]) < 1e-5 and _nerr(stats[1][cout:], 4 * stats[0][cout:]) < 1e-5
+
+
+@pytest.mark.parametrize("name,T,cin,cout,kt", [("fast_conv1 -> wgrad_halo", 8, 256, 32, 3), ("slow_conv1 -> wgrad_pair", 1, 256, 192, 1),
+                                                ("fast_conv2 -> wgrad_c32", 6, 32, 32, 3)])
+def test_wgrad_is_linear_in_dy_at_full_size(name, T, cin, cout, kt):
+    """dw(x, 2 dy) == 2 dw(x, dy) up to the order of the split-K atomics, and dw accumulates (+=) across calls."""
+    from sfvos_b200 import ops
+    B = 2
+    To = T - kt + 1
+    x = _act(ops, B, T, H0, W0, cin, 3)
+    dy = _act(ops, B, To, H0, W0, cout, 4)
+    dy2 = ops.Act((dy.buf.float() * 2).bfloat16(), B, To, H0, W0, cout)
+    n = kt * 9 * cin * cout
+    a, b = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ops.wgrad(x, dy, (kt, 3, 3), (0, 1, 1), a, umma=True)
+    ops.wgrad(x, dy2, (kt, 3, 3), (0, 1, 1), b, umma=True)
+    assert a.abs().max().item() > 1.0
+    assert _nerr(b, 2 * a) < 1e-5
+    ops.wgrad(x, dy, (kt, 3, 3), (0, 1, 1), b, umma=True)
+    assert _nerr(b, 3 * a) < 1e-5
+
+
+def test_module_full_size_bf16_vs_fp32_validation_mode_and_bn_invariants():
+    """One full-size level (192x336, B = 2 clips of 8 frames): the tcgen05 bf16 path against the independent fp32
+    CUDA-core path (itself pinned to the oracle at small sizes), plus the invariants train-mode BatchNorm gives the
+    output of layer 3 at ANY size: per-channel mean 0 and variance 1 (gamma = 1, beta = 0 at init)."""
+    from sfvos_b200 import SlowFastLayers
+    sp, fp, B = 1, 8, 2
+    g = torch.Generator(device=DEV).manual_seed(5)
+    fast = [OrderedDict([("0", torch.randn(fp, 256, H0, W0, device=DEV, generator=g))]) for _ in range(B)]
+    fast[1]["0"][:4] = 0                                           # sequence start: zero-padded frames
+    slow = [OrderedDict((k, v[fp // 2:fp // 2 + sp]) for k, v in f.items()) for f in fast]
+    outs, grads = {}, {}
+    for prec in ("bf16", "fp32"):
+        torch.manual_seed(63)
+        m = SlowFastLayers(256, torch.device(DEV), sp, fp).to(DEV).train()
+        m.precision = prec
+        out = m.temporally_enhance_features(slow, fast)["0"]
+        proj = torch.randn(out.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(7))
+        (out * proj).mean().backward()
+        outs[prec] = out.detach()
+        grads[prec] = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+        del m
+    assert outs["bf16"].shape == (B, 256, H0, W0)
+    assert _nerr(outs["bf16"], outs["fp32"]) <= 1e-2
+    for prec in outs:
+        flat = outs[prec].permute(1, 0, 2, 3).reshape(256, -1).double()
+        assert flat.mean(1).abs().max().item() < 1e-4, prec
+        assert (flat.var(1, unbiased=False) - 1).abs().max().item() < 1e-3, prec
+    for n in grads["fp32"]:
+        a, b = grads["bf16"][n].float(), grads["fp32"][n].float()
+        if n.endswith(("conv1.bias", "conv2.bias", "conv3.bias")):
+            assert a.abs().max().item() == 0 and b.abs().max().item() == 0        # exactly zero through train-mode BN
+        elif n.startswith(("fast_conv3", "slow_conv3", "bn_f3", "bn_s3")):
+            assert _nerr(a, b) <= 3e-2, (n, _nerr(a, b))
+        else:
+            rel = (a - b).norm().item() / (b.norm().item() + 1e-20)
+            assert rel <= 0.2, (n, rel)
+
+
+@pytest.mark.parametrize("P,k_per_clip", [(7, 512), (14, 128)])
+def test_roi_align_bench_rois_match_torchvision_cuda_op(P, k_per_clip):
+    """The bench's ROI set (8 clips, all 4 pyramid levels at full size) against torchvision's own multi-level pooler
+    running its CUDA roi_align kernel: forward values and feature gradients, ROI order identical."""
+    from torchvision.ops import MultiScaleRoIAlign as TVPool
+    from sfvos_b200 import MultiScaleRoIAlign, workload as wl
+    B = 8
+    g = torch.Generator(device=DEV).manual_seed(9)
+    names = wl.POOL_LEVELS
+    feats = OrderedDict((k, torch.randn(B, h, w, 256, device=DEV, generator=g).permute(0, 3, 1, 2)) for k, (h, w) in wl.LEVELS.items() if k in names)
+    boxes = [b[:k_per_clip].to(DEV) for b in wl.synthetic_rois(B, 512)]
+    shapes = [wl.IMAGE_HW] * B
+    f_a = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in feats.items())
+    f_b = OrderedDict((k, v.contiguous().clone().requires_grad_(True)) for k, v in feats.items())
+    ours = MultiScaleRoIAlign(names, P, 2, out_layout="nchw", precision="fp32")(f_a, boxes, shapes)
+    ref = TVPool(names, P, 2)(f_b, boxes, shapes)
+    assert ours.shape == ref.shape == (B * k_per_clip, 256, P, P)
+    assert _nerr(ours, ref) < 2e-6
+    wgt = torch.randn(ref.shape, device=DEV, generator=g)
+    (ours * wgt).sum().backward()
+    (ref * wgt).sum().backward()
+    for k in names:
+        assert _nerr(f_a[k].grad, f_b[k].grad) < 1e-5, k
