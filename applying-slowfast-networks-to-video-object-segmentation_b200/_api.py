@@ -1,8 +1,9 @@
 """Public API of the product package (re-exported by the ``sfvos_b200`` alias)."""
 from . import _lib, ops  # noqa: F401
 from .slowfast import SlowFastLayers  # noqa: F401
-from .roi_heads import (MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, RoIHeads, install,  # noqa: F401
-                        maskrcnn_inference, maskrcnn_loss, pool_pair, project_masks_on_boxes)
+from .roi_heads import (FastRCNNPredictor, MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, RoIHeads,  # noqa: F401
+                        TwoMLPHead, fastrcnn_loss, install, maskrcnn_inference, maskrcnn_loss, pool_pair,
+                        project_masks_on_boxes)
 
-__all__ = ["SlowFastLayers", "MultiScaleRoIAlign", "MaskRCNNHeads", "MaskRCNNPredictor", "RoIHeads", "install",
+__all__ = ["SlowFastLayers", "MultiScaleRoIAlign", "MaskRCNNHeads", "MaskRCNNPredictor", "RoIHeads", "TwoMLPHead", "FastRCNNPredictor", "fastrcnn_loss", "install",
            "maskrcnn_loss", "maskrcnn_inference", "project_masks_on_boxes", "pool_pair", "ops", "_lib"]

@@ -37,6 +37,7 @@ struct ConvArgs {
     int B, To, H, W;
     int TW, TH, tiles_w, tiles_h, ntiles;
     int N, kt, kh, kw, pad_t, pad_h, pad_w, cchunks;
+    int nchunks;                                // N tiles of one pixel tile (wide fc layers: Cout = nchunks * 256)
     int halo, use_bo, a_stages, b_stages, a_stage_bytes, b_group;     // b_group = taps per B stage
     uint32_t idesc, tmem_cols, a_tx_bytes;
     void* y;
@@ -107,7 +108,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             int as = 0, bs = 0;
             uint32_t aphase = 0, bphase = 0;
             const int taps_hw = a.kh * a.kw;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < a.ntiles * a.nchunks; item += gridDim.x) {
+                // consecutive items = the N chunks of one pixel tile: concurrent CTAs share the activation tile in L2
+                const int tile = item / a.nchunks;
+                const int n0 = (item - tile * a.nchunks) * a.N;
                 const int frame = tile / tiles_per_frame;
                 const int rem = tile - frame * tiles_per_frame;
                 const int th_i = rem / a.tiles_w;
@@ -125,7 +129,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                     mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes + b_bytes);
                                     tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK,
                                                 w0 + tj - a.pad_w, h0 + ti - a.pad_h, t + ta - a.pad_t, b);
-                                    tma_load_3d(smem_b + as * b_bytes, &tmap_w, &a_full[as], cc * BK, 0,
+                                    tma_load_3d(smem_b + as * b_bytes, &tmap_w, &a_full[as], cc * BK, n0,
                                                 (ta * a.kh + ti) * a.kw + tj);
                                     if (++as == a.a_stages) { as = 0; aphase ^= 1; }
                                 }
@@ -141,7 +145,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             for (int g = 0; g < taps_hw; g += a.b_group) {
                                 mbar_wait(&b_empty[bs], bphase ^ 1);
                                 mbar_arrive_expect_tx(&b_full[bs], b_stage_bytes);
-                                tma_load_3d(smem_b + bs * b_stage_bytes, &tmap_w, &b_full[bs], cc * BK, 0, ta * taps_hw + g);
+                                tma_load_3d(smem_b + bs * b_stage_bytes, &tmap_w, &b_full[bs], cc * BK, n0, ta * taps_hw + g);
                                 if (++bs == a.b_stages) { bs = 0; bphase ^= 1; }
                             }
                         }
@@ -157,7 +161,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint32_t acc_phase = 0;
             const int taps_hw = a.kh * a.kw;
             const int outer = a.halo ? a.kt * a.cchunks : a.kt * taps_hw * a.cchunks;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < a.ntiles * a.nchunks; item += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * a.N;
@@ -218,7 +222,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const bool affine = (a.scale != nullptr) || (a.shift != nullptr);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < a.ntiles * a.nchunks; item += gridDim.x) {
+            const int tile = item / a.nchunks;
+            const int nbase = (item - tile * a.nchunks) * a.N;     // first output channel of this N chunk
             const int frame = tile / tiles_per_frame;
             const int rem = tile - frame * tiles_per_frame;
             const int th_i = rem / a.tiles_w;
@@ -246,7 +252,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 if (valid) {
                     float o[32];
-                    if (affine) {           // per-channel scale / shift from shared memory, 16 bytes per load
+                    if (affine && a.nchunks > 1) {      // wide fc layers: bias (and scale) straight from global memory
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float sc = a.scale ? __ldg(a.scale + nbase + c0 + j) : 1.0f;
+                            const float sh = a.shift ? __ldg(a.shift + nbase + c0 + j) : 0.0f;
+                            o[j] = fmaf(__uint_as_float(v[j]), sc, sh);
+                        }
+                    } else if (affine) {    // per-channel scale / shift from shared memory, 16 bytes per load
                         const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
                         const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
 #pragma unroll
@@ -266,7 +279,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.0f);
                     }
                     if (a.y_bf16) {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride + c0);
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride + nbase + c0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint4 u;
@@ -277,7 +290,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             dst[j] = u;
                         }
                     } else {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + pix * a.y_cstride + c0);
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + pix * a.y_cstride + nbase + c0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 u = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -345,7 +358,9 @@ int sfvos_conv_pair_launch(const sfvos_conv_params* p, cudaStream_t stream);
 extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     SF_CHECK(p != nullptr, "conv_umma: null params");
-    SF_CHECK(p->N >= 32 && p->N <= 256 && p->N % 32 == 0, "conv_umma: N=%lld must be a multiple of 32 in [32,256]", (long long)p->N);
+    SF_CHECK(p->N >= 32 && p->N % 32 == 0 && (p->N <= 256 || p->N % 256 == 0),
+             "conv_umma: N=%lld must be a multiple of 32 in [32,256] or a multiple of 256", (long long)p->N);
+    SF_CHECK(p->N <= 256 || p->sum == nullptr, "conv_umma: fused statistics need N <= 256");
     SF_CHECK(p->Cp % 32 == 0 && p->Cp >= p->C, "conv_umma: Cp=%lld must be a multiple of 32 and >= C=%lld", (long long)p->Cp, (long long)p->C);
     const int BK = (p->Cp % 64 == 0) ? 64 : 32;
     SF_CHECK(p->C % 8 == 0 && p->x_cstride % 8 == 0, "conv_umma: C and x_cstride must be multiples of 8");
@@ -373,7 +388,8 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     a.tiles_w = (a.W + a.TW - 1) / a.TW;
     a.tiles_h = (a.H + a.TH - 1) / a.TH;
     a.ntiles = a.B * a.To * a.tiles_w * a.tiles_h;
-    a.N = (int)p->N;
+    a.nchunks = p->N > 256 ? (int)(p->N / 256) : 1;
+    a.N = p->N > 256 ? 256 : (int)p->N;
     a.kt = (int)p->kt; a.kh = (int)p->kh; a.kw = (int)p->kw;
     a.pad_t = (int)p->pad_t; a.pad_h = (int)p->pad_h; a.pad_w = (int)p->pad_w;
     a.cchunks = (int)(p->Cp / BK);
@@ -429,13 +445,13 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         const uint64_t taps = (uint64_t)(p->kt * p->kh * p->kw);
         uint64_t dims[3] = {(uint64_t)p->Cp, (uint64_t)p->N, taps};
         uint64_t str[2] = {taps * p->Cp * 2, (uint64_t)p->Cp * 2};
-        uint32_t box[3] = {(uint32_t)BK, (uint32_t)p->N, (uint32_t)a.b_group};
+        uint32_t box[3] = {(uint32_t)BK, (uint32_t)a.N, (uint32_t)a.b_group};
         rc = sfvos_make_tmap(&tw, p->w, 3, dims, str, box, BK * 2);
         if (rc) return rc;
     }
     const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_group * b_bytes + 1024 + 8192;
     int grid = sfvos_num_sms();
-    if (grid > a.ntiles) grid = a.ntiles;
+    if (grid > a.ntiles * a.nchunks) grid = a.ntiles * a.nchunks;
     if (BK == 64) {
         SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         conv_umma_kernel<64><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);

@@ -88,6 +88,30 @@ __global__ void unpack_wgrad_kernel(const UnpackArgs a) {
     }
 }
 
+// 2-D transposes for the single-tap fully-connected layers of the box head (fc6: 1024 x 12544), where the generic
+// gather kernels above would touch one 32-byte sector per element: dst[r][c] (+)= src[c][r], 32 x 32 tiles through
+// shared memory, both sides coalesced.
+template <typename OutT, bool ACC>
+__global__ void __launch_bounds__(256) transpose2d_kernel(const float* __restrict__ src, OutT* dst, int R, int Ccols) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        tile[i][tx] = (c < Ccols && r < R) ? src[(long long)c * R + r] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        if (r < R && c < Ccols) {
+            OutT* d = dst + (long long)r * Ccols + c;
+            float v = tile[tx][i];
+            if (ACC) v += static_cast<float>(*d);
+            *d = static_cast<OutT>(v);
+        }
+    }
+}
+
 // ---- per-channel reductions -------------------------------------------------------------------------------------
 // Block of 256 threads: thread -> (pixel lane, 8-channel group).  G = C/8 groups, L = 256/G pixel lanes.
 constexpr int RED_THREADS = 256;
@@ -433,6 +457,13 @@ extern "C" int sfvos_pack_weights(const float* w, void* out, int32_t out_dtype, 
     a.taps = (mode <= 1) ? (int)(kt * kh * kw) : 1;
     SF_CHECK(Cp >= a.Kc, "pack_weights: Cp=%lld smaller than the channel count %d", (long long)Cp, a.Kc);
     const long long total = (long long)a.N * a.taps * a.Cp;
+    if (mode == 1 && a.taps == 1 && a.out_bf16 && Cp == Cout && Cout >= 256 && Cin >= 256) {
+        // fc dgrad operand: out[ci][co] = w[co][ci]
+        dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32));
+        transpose2d_kernel<__nv_bfloat16, false><<<grid, 256, 0, CS(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), (int)Cin, (int)Cout);
+        SF_LAUNCH_CHECK();
+        return SFVOS_OK;
+    }
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, CS(stream)>>>(a);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
@@ -443,6 +474,13 @@ extern "C" int sfvos_unpack_wgrad(const float* dw, float* grad, int32_t mode, in
     SF_CHECK(mode == 0 || mode == 2, "unpack_wgrad: bad mode %d", mode);
     UnpackArgs a{dw, grad, mode, (int)Cout, (int)Cin, (int)kt, (int)kh, (int)kw, (int)tap_i, (int)tap_j};
     const long long total = mode == 0 ? Cout * Cin * kt * kh * kw : Cout * Cin;
+    if (mode == 0 && kt * kh * kw == 1 && Cout >= 256 && Cin >= 256) {
+        // fc weight gradient: grad[co][ci] += dw[ci][co]
+        dim3 grid((unsigned)((Cin + 31) / 32), (unsigned)((Cout + 31) / 32));
+        transpose2d_kernel<float, true><<<grid, 256, 0, CS(stream)>>>(dw, grad, (int)Cout, (int)Cin);
+        SF_LAUNCH_CHECK();
+        return SFVOS_OK;
+    }
     unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, CS(stream)>>>(a);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;

@@ -323,9 +323,22 @@ __global__ void __launch_bounds__(256, 2) roi_align_fwd2_kernel(const RoiArgs a)
     if (NCHW) {
         __syncthreads();
         const long long o = k * a.C * pp;
-        for (int i = threadIdx.x; i < a.C * pp; i += blockDim.x) {
-            if (a.out_bf16) reinterpret_cast<__nv_bfloat16*>(a.out)[o + i] = __float2bfloat16(s_tile[i]);
-            else reinterpret_cast<float*>(a.out)[o + i] = s_tile[i];
+        const int n = a.C * pp;
+        if (a.out_bf16 && (n & 7) == 0) {
+            // bf16 rows for the native box head: 8 elements (16 bytes) per store
+            uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o);
+            for (int i = threadIdx.x; i < n / 8; i += blockDim.x) {
+                const float* s = s_tile + 8 * i;
+                uint4 u;
+                u.x = pack_bf16x2(s[0], s[1]); u.y = pack_bf16x2(s[2], s[3]);
+                u.z = pack_bf16x2(s[4], s[5]); u.w = pack_bf16x2(s[6], s[7]);
+                d[i] = u;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                if (a.out_bf16) reinterpret_cast<__nv_bfloat16*>(a.out)[o + i] = __float2bfloat16(s_tile[i]);
+                else reinterpret_cast<float*>(a.out)[o + i] = s_tile[i];
+            }
         }
     }
 }

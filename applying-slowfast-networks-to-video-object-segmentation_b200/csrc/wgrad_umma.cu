@@ -24,6 +24,7 @@ struct WgArgs {
     int B, To, H, W, C, N;
     int PW, PH, tiles_w, tiles_h, ntiles, tiles_per_split;
     int kt, kh, kw, pad_t, pad_h, pad_w, mblks, nb_atoms, stages;
+    int nblks, Ntot;                            // wide fc layers: N = 256-column blocks of Ntot output channels
     uint32_t idesc, tmem_cols;
     float* dw;
 };
@@ -47,7 +48,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // work item
     const int tap = blockIdx.x % (a.kt * a.kh * a.kw);
     const int mblk = (blockIdx.x / (a.kt * a.kh * a.kw)) % a.mblks;
-    const int split = blockIdx.x / (a.kt * a.kh * a.kw * a.mblks);
+    const int nblk = (blockIdx.x / (a.kt * a.kh * a.kw * a.mblks)) % a.nblks;
+    const int split = blockIdx.x / (a.kt * a.kh * a.kw * a.mblks * a.nblks);
+    const int n_base = nblk * a.N;
     const int tj = tap % a.kw, ti = (tap / a.kw) % a.kh, ta = tap / (a.kw * a.kh);
     const int tile_begin = split * a.tiles_per_split;
     int tile_end = tile_begin + a.tiles_per_split;
@@ -101,7 +104,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 tma_load_5d(sa, &tmap_x, &full_bar[stage], c_base, xw, xh, xt, b);
                 if (second_atom) tma_load_5d(sa + ATOM_BYTES, &tmap_x, &full_bar[stage], c_base + 64, xw, xh, xt, b);
                 for (int nb = 0; nb < a.nb_atoms; ++nb)
-                    tma_load_5d(sa + a_bytes + nb * ATOM_BYTES, &tmap_dy, &full_bar[stage], nb * 64, w0, h0, t, b);
+                    tma_load_5d(sa + a_bytes + nb * ATOM_BYTES, &tmap_dy, &full_bar[stage], n_base + nb * 64, w0, h0, t, b);
                 if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -136,7 +139,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (tile_end > tile_begin) {
             mbar_wait(done_bar, 0);
             tc_fence_after();
-            float* dst_row = a.dw + ((long long)tap * a.C + c) * a.N;
+            float* dst_row = a.dw + ((long long)tap * a.C + c) * a.Ntot + n_base;
             for (int n0 = 0; n0 < a.N; n0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + n0, v);
@@ -185,7 +188,8 @@ int sfvos_wgrad_c32_launch(const sfvos_wgrad_params* p, cudaStream_t stream);
 extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     SF_CHECK(p != nullptr, "wgrad_umma: null params");
-    SF_CHECK(p->N >= 32 && p->N <= 256 && p->N % 32 == 0, "wgrad_umma: N=%lld must be a multiple of 32 in [32,256]", (long long)p->N);
+    SF_CHECK(p->N >= 32 && p->N % 32 == 0 && (p->N <= 256 || p->N % 256 == 0),
+             "wgrad_umma: N=%lld must be a multiple of 32 in [32,256] or a multiple of 256", (long long)p->N);
     SF_CHECK(p->C % 8 == 0 && p->x_cstride % 8 == 0 && p->dy_cstride % 8 == 0, "wgrad_umma: C and strides must be multiples of 8");
     SF_CHECK((p->N % 4) == 0 && (reinterpret_cast<uintptr_t>(p->dw) & 15) == 0, "wgrad_umma: dw must be 16-byte aligned");
     SF_CHECK(p->B > 0 && p->To > 0 && p->H > 0 && p->W > 0, "wgrad_umma: empty tensor");
@@ -198,7 +202,10 @@ extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream
         return sfvos_wgrad_stack_launch(p, stream);     // narrow fast-pathway GEMMs: taps stacked along N
 
     WgArgs a;
-    a.B = (int)p->B; a.To = (int)p->To; a.H = (int)p->H; a.W = (int)p->W; a.C = (int)p->C; a.N = (int)p->N;
+    a.B = (int)p->B; a.To = (int)p->To; a.H = (int)p->H; a.W = (int)p->W; a.C = (int)p->C;
+    a.Ntot = (int)p->N;
+    a.nblks = p->N > 256 ? (int)(p->N / 256) : 1;
+    a.N = p->N > 256 ? 256 : (int)p->N;
     choose_ktile(a.H, a.W, &a.PW, &a.PH);
     a.tiles_w = (a.W + a.PW - 1) / a.PW;
     a.tiles_h = (a.H + a.PH - 1) / a.PH;
@@ -208,7 +215,7 @@ extern "C" int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream
     a.mblks = (a.C + 127) / 128;
     a.nb_atoms = (a.N + 63) / 64;
     const int taps = a.kt * a.kh * a.kw;
-    const int base_items = taps * a.mblks;
+    const int base_items = taps * a.mblks * a.nblks;
     int splits = (4 * sfvos_num_sms()) / base_items;          // 1 CTA per SM: keep the grid within whole waves
     int max_splits = (a.ntiles + 7) / 8;
     if (splits > max_splits) splits = max_splits;

@@ -8,11 +8,16 @@ into ``maskrcnn_model.roi_heads`` (see ``install`` and INTEGRATION.md):
   MaskRCNNHeads        <- torchvision...mask_rcnn.MaskRCNNHeads          (TV/models/detection/mask_rcnn.py:271-303)
   MaskRCNNPredictor    <- torchvision...mask_rcnn.MaskRCNNPredictor      (TV/models/detection/mask_rcnn.py:337-353)
   maskrcnn_loss / maskrcnn_inference <- TV/models/detection/roi_heads.py:56-129
+  TwoMLPHead           <- torchvision...faster_rcnn.TwoMLPHead           (TV/models/detection/faster_rcnn.py:286-307)
+  FastRCNNPredictor    <- torchvision...faster_rcnn.FastRCNNPredictor    (TV/models/detection/faster_rcnn.py:347-370)
+  fastrcnn_loss        <- TV/models/detection/roi_heads.py:12-53
   RoIHeads             <- torchvision...roi_heads.RoIHeads.forward       (TV/models/detection/roi_heads.py:739-887)
 
 Tensors exchanged between these modules keep torchvision's logical shapes ([K,C,P,P]) but are channels_last in
 memory and bf16 on the product path (fp32 when ``precision == "fp32"``), which is what the tensor-core kernels
-consume directly.  Box sampling, box head, box losses and NMS stay torchvision/torch (SURVEY 8(f) "next").
+consume directly.  The box head (fc6/fc7), the box predictor and fastrcnn_loss run on the same tensor-core GEMM
+kernels: a Linear layer is a 1x1x1 convolution over the M ROIs.  Box sampling, box decoding and NMS
+stay torchvision/torch.
 """
 import math
 import os
@@ -20,6 +25,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import nn, Tensor
+from torchvision.models.detection import faster_rcnn as tv_faster_rcnn
 from torchvision.models.detection import mask_rcnn as tv_mask_rcnn
 from torchvision.models.detection import roi_heads as tv_roi_heads
 from torchvision.ops import boxes as box_ops
@@ -108,7 +114,8 @@ class MultiScaleRoIAlign(nn.Module):
     ``out_layout="nhwc"`` returns the same logical shape with channels_last strides in the activation dtype."""
 
     def __init__(self, featmap_names: List[str], output_size, sampling_ratio: int, *, canonical_scale: int = 224,
-                 canonical_level: int = 4, out_layout: str = "nchw", precision: Optional[str] = None):
+                 canonical_level: int = 4, out_layout: str = "nchw", precision: Optional[str] = None,
+                 out_dtype: Optional[torch.dtype] = None):
         super().__init__()
         if isinstance(output_size, int):
             output_size = (output_size, output_size)
@@ -122,6 +129,7 @@ class MultiScaleRoIAlign(nn.Module):
         self.canonical_level = canonical_level
         self.out_layout = out_layout
         self.precision = precision or _default_precision()
+        self.out_dtype = out_dtype          # None: f32 for "nchw" (a torch consumer), the activation dtype for "nhwc"
 
     def _setup_scales(self, feats, image_shapes):
         max_h = max(s[0] for s in image_shapes)
@@ -142,6 +150,8 @@ class MultiScaleRoIAlign(nn.Module):
 
     def _out_spec(self):
         nchw = self.out_layout == "nchw"
+        if self.out_dtype is not None:
+            return nchw, self.out_dtype
         return nchw, (torch.float32 if nchw else _act_dtype(self.precision))
 
     def forward(self, x: Dict[str, Tensor], boxes: List[Tensor], image_shapes: List[Tuple[int, int]]) -> Tensor:
@@ -430,12 +440,217 @@ def maskrcnn_inference(x, labels):
     return prob.split(per_img, dim=0)
 
 
+
+# ----------------------------------------------------------------------------------------------------------------------
+# box head: fc6 (C*P*P -> 1024) + ReLU, fc7 (1024 -> 1024) + ReLU; predictor: cls_score / bbox_pred; fastrcnn_loss
+# A Linear layer over M ROIs is the 1x1x1 convolution of a [1,1,1,M] "image" with in_features channels: the same
+# tcgen05 kernels (N tiled in 256-column chunks), the same weight-gradient GEMM, the same ReLU-backward pass.
+# ----------------------------------------------------------------------------------------------------------------------
+def _rows_act(t2d):
+    """[M, C] contiguous tensor -> Act over M "pixels" (B=T=H=1, W=M)."""
+    M, C = t2d.shape
+    return Act(t2d.reshape(-1), 1, 1, 1, M, C)
+
+
+def _linear_fwd(x, w, b, umma, dt_act, relu, out_dtype=None):
+    """x: Act [M,K]; w [N,K] f32 parameter (N a multiple of 32 <= 256 or of 256); -> Act [M,N]."""
+    N, K = w.shape
+    wp, cp = _pack(w.view(N, K, 1, 1, 1), 0, umma, K)
+    y = Act.empty(1, 1, 1, x.W, N, out_dtype or dt_act, x.buf.device)
+    if x.W:
+        ops.conv(x, wp, cp, N, (1, 1, 1), (0, 0, 0), 1, y, umma=umma, relu=relu, shift=b)
+    return y
+
+
+def _linear_bwd(x, dy, w, umma, dx_dtype, need_dx=True):
+    """dy = gradient of the PRE-activation output [M,N] (Act); returns (gw [N,K] f32, dx Act [M,K] or None)."""
+    N, K = w.shape
+    dev = dy.buf.device
+    gw = torch.zeros(N, K, dtype=torch.float32, device=dev)
+    dx = None
+    if x.W:
+        dwp = torch.zeros(K * N, dtype=torch.float32, device=dev)
+        ops.wgrad(x, dy, (1, 1, 1), (0, 0, 0), dwp, umma=umma)
+        ops.unpack_wgrad(dwp, gw.view(N, K, 1, 1, 1), 0)
+    if need_dx:
+        dx = Act.empty(1, 1, 1, x.W, K, dx_dtype, dev)
+        if x.W:
+            wd, cpd = _pack(w.view(N, K, 1, 1, 1), 1, umma, N)
+            ops.conv(dy, wd, cpd, K, (1, 1, 1), (0, 0, 0), 1, dx, umma=umma)
+    return gw, dx
+
+
+def _as_rows(x, dt_act):
+    """Any [M, ...] tensor -> dense Act [M, features] in the activation dtype."""
+    x2 = x.flatten(start_dim=1)
+    if x2.dtype != dt_act or not x2.is_contiguous():
+        x2 = x2.to(dt_act).contiguous()
+    return _rows_act(x2)
+
+
+class _BoxHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, precision, w6, b6, w7, b7):
+        ops.device_check()
+        umma = precision != "fp32"
+        dt_act = _act_dtype(precision)
+        xin = _as_rows(x, dt_act)
+        y6 = _linear_fwd(xin, w6, b6.detach().float(), umma, dt_act, True)
+        y7 = _linear_fwd(y6, w7, b7.detach().float(), umma, dt_act, True)
+        ctx.acts = (xin, y6, y7)
+        ctx.meta = (umma, dt_act, x.dtype, tuple(x.shape))
+        ctx.save_for_backward(w6, b6, w7, b7)
+        return y7.buf.view(xin.W, w7.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        w6, b6, w7, b7 = ctx.saved_tensors
+        xin, y6, y7 = ctx.acts
+        umma, dt_act, x_dtype, x_shape = ctx.meta
+        M, dev = xin.W, g.device
+        gb6 = torch.zeros(w6.shape[0], dtype=torch.float32, device=dev)
+        gb7 = torch.zeros(w7.shape[0], dtype=torch.float32, device=dev)
+        dy7 = _as_rows(g, dt_act)
+        dc7 = Act.empty(1, 1, 1, M, y7.C, dt_act, dev)
+        if M:
+            ops.relu_bwd(dy7, y7, dc7, gb7)
+        gw7, dy6 = _linear_bwd(y6, dc7, w7, umma, dt_act)
+        dc6 = Act.empty(1, 1, 1, M, y6.C, dt_act, dev)
+        if M:
+            ops.relu_bwd(dy6, y6, dc6, gb6)
+        gw6, dx = _linear_bwd(xin, dc6, w6, umma, dt_act, need_dx=ctx.needs_input_grad[0])
+        gx = dx.buf.view(x_shape).to(x_dtype) if dx is not None else None
+        ctx.acts = None
+        return gx, None, gw6.to(w6.dtype), gb6.to(b6.dtype), gw7.to(w7.dtype), gb7.to(b7.dtype)
+
+
+class TwoMLPHead(tv_faster_rcnn.TwoMLPHead):
+    """Same ctor / state_dict keys (fc6.*, fc7.*) as torchvision; flatten -> fc6 -> ReLU -> fc7 -> ReLU on libsfvos."""
+
+    precision = None
+
+    def forward(self, x):
+        return _BoxHeadFn.apply(x, self.precision or _default_precision(), self.fc6.weight, self.fc6.bias,
+                                self.fc7.weight, self.fc7.bias)
+
+
+def _pred_pad(n):
+    return 64 if n <= 64 else (n + 255) // 256 * 256 if n > 256 else (n + 31) // 32 * 32
+
+
+class _BoxPredictorFn(torch.autograd.Function):
+    """cls_score and bbox_pred as ONE GEMM: rows [0,n_cls) of the stacked weight are the class logits, rows
+    [n_cls, 5 n_cls) the box deltas; zero rows pad the output to a tensor-core tile.  Returns f32 [M, Npad]."""
+
+    @staticmethod
+    def forward(ctx, x, precision, wc, bc, wb, bb):
+        ops.device_check()
+        umma = precision != "fp32"
+        dt_act = _act_dtype(precision)
+        n_out = wc.shape[0] + wb.shape[0]
+        n_pad = _pred_pad(n_out)
+        K = wc.shape[1]
+        w = torch.zeros(n_pad, K, dtype=torch.float32, device=x.device)
+        w[:wc.shape[0]] = wc.detach()
+        w[wc.shape[0]:n_out] = wb.detach()
+        b = torch.zeros(n_pad, dtype=torch.float32, device=x.device)
+        b[:wc.shape[0]] = bc.detach()
+        b[wc.shape[0]:n_out] = bb.detach()
+        xin = _as_rows(x, dt_act)
+        y = _linear_fwd(xin, w, b, umma, dt_act, False, out_dtype=torch.float32)
+        ctx.acts = (xin, w)
+        ctx.meta = (umma, dt_act, x.dtype, tuple(x.shape), n_pad)
+        ctx.save_for_backward(wc, bc, wb, bb)
+        return y.buf.view(xin.W, n_pad)
+
+    @staticmethod
+    def backward(ctx, g):
+        wc, bc, wb, bb = ctx.saved_tensors
+        xin, w = ctx.acts
+        umma, dt_act, x_dtype, x_shape, n_pad = ctx.meta
+        M, dev = xin.W, g.device
+        nc, nb = wc.shape[0], wb.shape[0]
+        g32 = _rows_act(g.float().contiguous())
+        stats = torch.zeros(2, n_pad, dtype=torch.float32, device=dev)     # row 0 = column sums = the bias gradients
+        if M:
+            ops.channel_stats(g32, stats)
+        if umma:
+            dy = Act.empty(1, 1, 1, M, n_pad, dt_act, dev)
+            if M:
+                ops.affine_act(g32, dy, torch.ones(n_pad, device=dev), torch.zeros(n_pad, device=dev), False)
+        else:
+            dy = g32
+        gw, dx = _linear_bwd(xin, dy, w, umma, dt_act, need_dx=ctx.needs_input_grad[0])
+        gx = dx.buf.view(x_shape).to(x_dtype) if dx is not None else None
+        ctx.acts = None
+        return (gx, None, gw[:nc].to(wc.dtype), stats[0, :nc].to(bc.dtype), gw[nc:nc + nb].to(wb.dtype),
+                stats[0, nc:nc + nb].to(bb.dtype))
+
+
+class FastRCNNPredictor(tv_faster_rcnn.FastRCNNPredictor):
+    """Same ctor / state_dict keys (cls_score.*, bbox_pred.*) as torchvision; returns (scores [M,n_cls], bbox_deltas
+    [M,4 n_cls]) as column slices of one fused f32 GEMM output."""
+
+    precision = None
+
+    def forward(self, x):
+        if x.dim() == 4:
+            assert list(x.shape[2:]) == [1, 1], f"x has the wrong shape, expecting the last two dimensions to be [1,1] instead of {list(x.shape[2:])}"
+        fused = _BoxPredictorFn.apply(x, self.precision or _default_precision(), self.cls_score.weight, self.cls_score.bias,
+                                      self.bbox_pred.weight, self.bbox_pred.bias)
+        nc, nb = self.cls_score.out_features, self.bbox_pred.out_features
+        return fused[:, :nc], fused[:, nc:nc + nb]
+
+
+class _FastRCNNLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, class_logits, box_regression, labels, regression_targets, beta):
+        ops.device_check()
+        M, n_cls = class_logits.shape
+
+        def rows(t):   # f32 rows with unit column stride (column slices of the fused predictor output pass as they are)
+            return t if (t.dtype == torch.float32 and t.stride(1) == 1) else t.float().contiguous()
+        cls, box = rows(class_logits), rows(box_regression)
+        losses = torch.empty(2, dtype=torch.float32, device=cls.device)
+        call("sfvos_fastrcnn_loss_fwd", _p(cls), cls.stride(0), _p(box), box.stride(0), _p(labels), _p(regression_targets), M,
+             n_cls, float(beta), _p(losses), stream())
+        ctx.save_for_backward(cls, box, labels, regression_targets)
+        ctx.beta = float(beta)
+        ctx.dtypes = (class_logits.dtype, box_regression.dtype)
+        return losses[0].clone(), losses[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_cls, g_box):
+        cls, box, labels, tgt = ctx.saved_tensors
+        M, n_cls = cls.shape
+        gl = torch.zeros(2, dtype=torch.float32, device=cls.device)
+        if g_cls is not None:
+            gl[0] = g_cls
+        if g_box is not None:
+            gl[1] = g_box
+        dcls = torch.empty(M, n_cls, dtype=torch.float32, device=cls.device)
+        dbox = torch.empty(M, 4 * n_cls, dtype=torch.float32, device=cls.device)
+        call("sfvos_fastrcnn_loss_bwd", _p(cls), cls.stride(0), _p(box), box.stride(0), _p(labels), _p(tgt), _p(gl), M, n_cls,
+             ctx.beta, _p(dcls), dcls.stride(0), _p(dbox), dbox.stride(0), stream())
+        return dcls.to(ctx.dtypes[0]), dbox.to(ctx.dtypes[1]), None, None, None
+
+
+def fastrcnn_loss(class_logits, box_regression, labels, regression_targets):
+    """Same signature and values as torchvision's fastrcnn_loss (TV roi_heads.py:12-53): (cross-entropy over the class
+    logits, smooth-L1(beta=1/9, sum) / M over the matched class's deltas of the positive ROIs)."""
+    labels = torch.cat(labels, dim=0).to(torch.int64).contiguous()
+    regression_targets = torch.cat(regression_targets, dim=0).float().contiguous()
+    if labels.numel() == 0:
+        return tv_roi_heads.fastrcnn_loss(class_logits, box_regression, [labels], [regression_targets])
+    return _FastRCNNLossFn.apply(class_logits, box_regression, labels, regression_targets, 1.0 / 9)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # RoIHeads
 # ----------------------------------------------------------------------------------------------------------------------
 class RoIHeads(tv_roi_heads.RoIHeads):
-    """torchvision RoIHeads with the mask branch (pool -> head -> predictor -> loss/inference) on libsfvos kernels.
-    Box sampling / box head / box losses / NMS are inherited unchanged."""
+    """torchvision RoIHeads with both branches on libsfvos kernels: box pool -> fc6/fc7 -> predictor -> fastrcnn_loss and
+    mask pool -> head -> predictor -> loss/inference.  Box sampling, box decoding and NMS are inherited unchanged."""
 
     def forward(self, features, proposals, image_shapes, targets=None):
         if self.training:
@@ -462,7 +677,7 @@ class RoIHeads(tv_roi_heads.RoIHeads):
         result: List[Dict[str, Tensor]] = []
         losses = {}
         if self.training:
-            loss_classifier, loss_box_reg = tv_roi_heads.fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
+            loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
             losses = {"loss_classifier": loss_classifier, "loss_box_reg": loss_box_reg}
         else:
             boxes, scores, labels = self.postprocess_detections(class_logits, box_regression, proposals, image_shapes)
@@ -496,14 +711,23 @@ def install(roi_heads: tv_roi_heads.RoIHeads, precision: Optional[str] = None):
     """Swap the libsfvos modules into an existing torchvision ``roi_heads`` IN PLACE, keeping every parameter
     (same tensors, same state_dict keys, same registration order).  Returns the same object, now a ``RoIHeads``."""
     precision = precision or _default_precision()
+    native_box = type(roi_heads.box_head) in (tv_faster_rcnn.TwoMLPHead, TwoMLPHead)
     for name, layout in (("box_roi_pool", "nchw"), ("mask_roi_pool", "nhwc")):
         old = getattr(roi_heads, name)
         if old is None:
             continue
+        # the native box head consumes the [K, C*P*P] rows (torchvision's flatten order) in the activation dtype
+        od = _act_dtype(precision) if (name == "box_roi_pool" and native_box) else None
         new = MultiScaleRoIAlign(list(old.featmap_names), old.output_size, old.sampling_ratio,
                                  canonical_scale=old.canonical_scale, canonical_level=old.canonical_level,
-                                 out_layout=layout, precision=precision)
+                                 out_layout=layout, precision=precision, out_dtype=od)
         setattr(roi_heads, name, new)
+    if native_box:
+        roi_heads.box_head.__class__ = TwoMLPHead
+        roi_heads.box_head.precision = precision
+    if type(roi_heads.box_predictor) in (tv_faster_rcnn.FastRCNNPredictor, FastRCNNPredictor):
+        roi_heads.box_predictor.__class__ = FastRCNNPredictor
+        roi_heads.box_predictor.precision = precision
     if roi_heads.mask_head is not None:
         roi_heads.mask_head.__class__ = MaskRCNNHeads
         roi_heads.mask_head.precision = precision

@@ -1,15 +1,16 @@
 """Synthetic DAVIS-shaped hot-path step: SlowFast temporal module on B clips (all 5 FPN levels) ->
-multi-level ROIAlign for the box (7x7) and mask (14x14) branches -> mask head -> mask predictor -> mask loss,
-forward + backward.  Used by bench.py (the measured step) and the data-parallel trainer; everything numeric runs
-in libsfvos.so except the stand-in box loss (mean of squares of the pooled box features: the torch box head is
-outside the hot path)."""
+multi-level ROIAlign for the box (7x7) and mask (14x14) branches -> box head (fc6/fc7) -> box predictor ->
+fastrcnn_loss, and mask head -> mask predictor -> mask loss, forward + backward: what ``roi_heads`` computes in a
+training step of the reference (code/helpers/model.py:340-346) once the proposals are sampled.  Used by bench.py (the
+measured step) and the data-parallel trainer; everything numeric runs in libsfvos.so."""
 import math
 from collections import OrderedDict
 
 import torch
 
 from . import ops
-from .roi_heads import MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, maskrcnn_loss, pool_pair
+from .roi_heads import (FastRCNNPredictor, MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, TwoMLPHead, _act_dtype,
+                        fastrcnn_loss, maskrcnn_loss, pool_pair)
 from .slowfast import SlowFastLayers
 
 # 480x854 DAVIS frame -> GeneralizedRCNNTransform -> 749x1333 -> padded 768x1344 -> FPN strides 4..64
@@ -103,6 +104,20 @@ def roi_align_bytes(boxes, P, e_in, e_out, backward=False, C=256, image_hw=IMAGE
 
 
 MASK_HEAD_FLOPS_PER_ROI = 2.0 * 196 * 256 * 2304 * 4 + 2.0 * 196 * 256 * 1024 + 2.0 * 784 * 2 * 256   # fwd
+BOX_HEAD_FLOPS_PER_ROI = 2.0 * (256 * 49 * 1024 + 1024 * 1024 + 1024 * 10)                            # fwd: fc6, fc7, cls+bbox
+
+
+def synthetic_box_targets(n_clips, k_box, k_pos, seed=977):
+    """Per clip: labels int64 [k_box] (the first k_pos ROIs are foreground = the mask branch's ROIs, the rest background,
+    1:3 like torchvision's sampler) and regression targets f32 [k_box,4] ~ 0.5 * N(0,1) (both sides of beta = 1/9)."""
+    g = torch.Generator().manual_seed(seed)
+    labels, targets = [], []
+    for _ in range(n_clips):
+        lab = torch.zeros(k_box, dtype=torch.int64)
+        lab[:k_pos] = 1
+        labels.append(lab)
+        targets.append(0.5 * torch.randn(k_box, 4, generator=g))
+    return labels, targets
 
 
 class HotPathStep:
@@ -119,7 +134,10 @@ class HotPathStep:
         self.mask_predictor = MaskRCNNPredictor(256, 256, 2).to(self.device)
         self.mask_head.precision = self.mask_predictor.precision = precision
         names = [k for k in levels if k in POOL_LEVELS]
-        self.box_roi_pool = MultiScaleRoIAlign(names, 7, 2, out_layout="nchw", precision=precision)
+        self.box_head = TwoMLPHead(256 * 7 * 7, 1024).to(self.device)
+        self.box_predictor = FastRCNNPredictor(1024, 2).to(self.device)
+        self.box_head.precision = self.box_predictor.precision = precision
+        self.box_roi_pool = MultiScaleRoIAlign(names, 7, 2, out_layout="nchw", precision=precision, out_dtype=_act_dtype(precision))
         self.mask_roi_pool = MultiScaleRoIAlign(names, 14, 2, out_layout="nhwc", precision=precision)
         self.image_shapes = [IMAGE_HW] * n_clips
         box = synthetic_rois(n_clips, k_box, seed=4321)
@@ -130,13 +148,23 @@ class HotPathStep:
         self.gt_masks = [gt.to(self.device) for _ in range(n_clips)]
         self.gt_labels = [torch.ones(1, dtype=torch.int64, device=self.device) for _ in range(n_clips)]
         self.matched = [torch.zeros(k_mask, dtype=torch.int64, device=self.device) for _ in range(n_clips)]
+        lab, tgt = synthetic_box_targets(n_clips, k_box, k_mask)
+        self.box_labels = [t.to(self.device) for t in lab]
+        self.box_targets = [t.to(self.device) for t in tgt]
         self.k_box, self.k_mask = k_box, k_mask
 
+    def modules(self):
+        """(name, module) in the registration order of the reference's roi_heads, after slow_fast."""
+        return [("slow_fast", self.slow_fast), ("box_head", self.box_head), ("box_predictor", self.box_predictor),
+                ("mask_head", self.mask_head), ("mask_predictor", self.mask_predictor)]
+
     def parameters(self):
-        return list(self.slow_fast.parameters()) + list(self.mask_head.parameters()) + list(self.mask_predictor.parameters())
+        return [p for _, m in self.modules() for p in m.parameters()]
 
     def state_dict(self):
         sd = OrderedDict(("slow_fast." + k, v) for k, v in self.slow_fast.state_dict().items())
+        sd.update(("box_head." + k, v) for k, v in self.box_head.state_dict().items())
+        sd.update(("box_predictor." + k, v) for k, v in self.box_predictor.state_dict().items())
         sd.update(("mask_head." + k, v) for k, v in self.mask_head.state_dict().items())
         sd.update(("mask_predictor." + k, v) for k, v in self.mask_predictor.state_dict().items())
         return sd
@@ -148,10 +176,11 @@ class HotPathStep:
         # both poolings in one autograd node, as RoIHeads.forward does in training (one set of gradient maps)
         box_feats, mask_feats = pool_pair(self.box_roi_pool, self.mask_roi_pool, merged, self.box_props, self.mask_props,
                                           self.image_shapes)
-        loss_box = box_feats.square().mean()                          # stand-in for the torch box head + losses
+        class_logits, box_regression = self.box_predictor(self.box_head(box_feats))
+        loss_cls, loss_reg = fastrcnn_loss(class_logits, box_regression, self.box_labels, self.box_targets)
         logits = self.mask_predictor(self.mask_head(mask_feats))
         loss_mask = maskrcnn_loss(logits, self.mask_props, self.gt_masks, self.gt_labels, self.matched)
-        return loss_mask + loss_box, merged
+        return loss_cls + loss_reg + loss_mask, merged
 
     def step(self, features, zero_grad=True):
         loss, _ = self.forward(features)
@@ -188,7 +217,8 @@ class HotPathStep:
     def flops_per_step(self):
         conv = conv_flops(self.sp, self.fp, self.levels) * self.B
         mask = 3.0 * MASK_HEAD_FLOPS_PER_ROI * self.k_mask * self.B
-        return conv, mask
+        box = 3.0 * BOX_HEAD_FLOPS_PER_ROI * self.k_box * self.B
+        return conv, mask + box
 
 
 def flat_grads(params):

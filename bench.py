@@ -6,8 +6,8 @@
         bench.py --gpus N --steps K --warmup W
 
 Workload = BASELINE.json configs[1]: SlowFast temporal module (sp=1, fp=8) on B=8 clips x 5 FPN levels of a
-480x854 DAVIS frame + multi-level ROIAlign (512 box / 128 mask ROIs per clip) + mask head + mask loss,
-forward AND backward, bf16 tensor-core path.  One rank per GPU; every rank runs its own B clips (weak scaling)
+480x854 DAVIS frame + multi-level ROIAlign (512 box / 128 mask ROIs per clip) + box head (fc6/fc7/predictor) +
+fastrcnn_loss + mask head + mask loss, forward AND backward, bf16 tensor-core path.  One rank per GPU; every rank runs its own B clips (weak scaling)
 and the trainable gradients are summed with one NCCL all-reduce per step when N > 1.
 
 Prints ONE JSON line (rank 0): value = device-timed clip-frames/s with inputs resident in HBM; e2e = the same step
@@ -87,25 +87,29 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_reference_step(state):
     """One fwd+bwd of the hot path for ONE clip on the host CPU: oracle restatement of SlowFastLayers (torch CPU fp32,
-    what the reference's nn modules dispatch to) + torchvision's own CPU ROIAlign / mask head / mask loss."""
+    what the reference's nn modules dispatch to) + torchvision's own CPU ROIAlign / box head / fastrcnn_loss / mask head /
+    mask loss."""
     import torch
     from oracle import slowfast_oracle as so
-    sd, feats, slow, pools, head, pred, props_box, props_mask, gt, lab, matched, shapes = state
-    from torchvision.models.detection.roi_heads import maskrcnn_loss
+    sd, feats, slow, pools, head, pred, props_box, props_mask, gt, lab, matched, shapes, box_head, box_pred, box_lab, box_tgt = state
+    from torchvision.models.detection.roi_heads import fastrcnn_loss, maskrcnn_loss
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
     work = {k: (leaves[k] if k in leaves else v.clone()) for k, v in sd.items()}
     merged = so.temporally_enhance_features(work, slow, feats, True)
     box = pools[0](merged, props_box, shapes)
     mask = pools[1](merged, props_mask, shapes)
     logits = pred(head(mask))
-    loss = maskrcnn_loss(logits, props_mask, gt, lab, matched) + box.square().mean()
+    loss_cls, loss_reg = fastrcnn_loss(*box_pred(box_head(box)), box_lab, box_tgt)
+    loss = maskrcnn_loss(logits, props_mask, gt, lab, matched) + loss_cls + loss_reg
     loss.backward()
-    head.zero_grad(); pred.zero_grad()
+    for m in (head, pred, box_head, box_pred):
+        m.zero_grad()
     return float(loss.detach())
 
 
 def build_cpu_state():
     import torch
+    from torchvision.models.detection.faster_rcnn import FastRCNNPredictor, TwoMLPHead
     from torchvision.models.detection.mask_rcnn import MaskRCNNHeads, MaskRCNNPredictor
     from torchvision.ops import MultiScaleRoIAlign
     from oracle import slowfast_oracle as so
@@ -118,11 +122,13 @@ def build_cpu_state():
     torch.manual_seed(63)
     pools = (MultiScaleRoIAlign(wl.POOL_LEVELS, 7, 2), MultiScaleRoIAlign(wl.POOL_LEVELS, 14, 2))
     head, pred = MaskRCNNHeads(256, (256, 256, 256, 256), 1), MaskRCNNPredictor(256, 256, 2)
+    box_head, box_pred = TwoMLPHead(256 * 7 * 7, 1024), FastRCNNPredictor(1024, 2)
+    box_lab, box_tgt = wl.synthetic_box_targets(1, K_BOX, K_MASK)
     box = wl.synthetic_rois(1, K_BOX)
     gt = torch.zeros(1, wl.IMAGE_HW[0], wl.IMAGE_HW[1], dtype=torch.uint8)
     gt[0, 200:500, 400:600] = 1
     return (sd, feats, slow, pools, head, pred, box, [box[0][:K_MASK]], [gt], [torch.ones(1, dtype=torch.int64)],
-            [torch.zeros(K_MASK, dtype=torch.int64)], [wl.IMAGE_HW])
+            [torch.zeros(K_MASK, dtype=torch.int64)], [wl.IMAGE_HW], box_head, box_pred, box_lab, box_tgt)
 
 
 def time_cpu_reference(steps, warmup):
@@ -149,7 +155,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: SlowFast(sp=1,fp=8) + ROIAlign + mask head fwd+bwd (CPU sample: 1 clip/step)"},
+            "config": {"workload": "C2: SlowFast(sp=1,fp=8) + ROIAlign + box head/losses + mask head/loss fwd+bwd (CPU sample: 1 clip/step)"},
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -248,9 +254,9 @@ def run_ours(args, rank, local_rank, world):
     # ---- rooflines from the per-launch CUDA events of the timed region ----
     # tensor-core GEMM kernels: work = algorithmic FLOPs of the launch (no padding / halo / zero-tap FLOPs);
     # ROIAlign: work = algorithmic bytes of the launch (workload.roi_align_bytes).
-    roi_bytes = {"roi_align_fwd_p7": wl.roi_align_bytes(step.box_props, 7, 4, 4),
+    roi_bytes = {"roi_align_fwd_p7": wl.roi_align_bytes(step.box_props, 7, 4, 2),
                  "roi_align_fwd_p14": wl.roi_align_bytes(step.mask_props, 14, 4, 2),
-                 "roi_align_bwd_p7": wl.roi_align_bytes(step.box_props, 7, 4, 4, backward=True),
+                 "roi_align_bwd_p7": wl.roi_align_bytes(step.box_props, 7, 4, 2, backward=True),
                  "roi_align_bwd_p14": wl.roi_align_bytes(step.mask_props, 14, 4, 2, backward=True)}
     fam = {}
     for name, flops, a, b in timing:
@@ -353,7 +359,7 @@ def run_ours(args, rank, local_rank, world):
         line = {"metric": METRIC, "value": round(world * B_PER_GPU * FP / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "C2: SlowFast temporal module (sp=1, fp=8) + multi-level ROIAlign + mask head/predictor/loss, fwd+bwd",
+                "config": {"workload": "C2: SlowFast temporal module (sp=1, fp=8) + multi-level ROIAlign + box head (fc6/fc7/predictor/fastrcnn_loss) + mask head/predictor/loss, fwd+bwd",
                            "clips_per_gpu": B_PER_GPU, "frames_per_clip": FP, "levels": "192x336,96x168,48x84,24x42,12x21 x256ch",
                            "rois_per_clip": {"box": K_BOX, "mask": K_MASK}, "parallelism": f"dp{world} by clip, 1 NCCL grad all-reduce/step",
                            "l2": "inputs (5.6 GB of features per step) far exceed the 126 MB L2; no explicit flush",

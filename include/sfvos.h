@@ -65,7 +65,10 @@ typedef struct sfvos_conv_params {
                                                   the ConvTranspose2d backward read every 2nd row/column of dy */
     const void* w;            /* packed weights */
     int64_t Cp;               /* per-tap K extent of the packed weights (C rounded up to 64 for umma) */
-    int64_t N;                /* output channels (multiple of 32, <= 256) */
+    int64_t N;                /* output channels: a multiple of 32 up to 256 (one N tile, activations fetched once),
+                                 or a multiple of 256 (256-column N tiles; the fully-connected layers of the box
+                                 head, TV/models/detection/faster_rcnn.py:286-307, run as 1x1x1 convolutions over
+                                 [1,1,1,M rois] "pixels" with C = in_features) */
     int64_t kt, kh, kw;
     int64_t pad_t, pad_h, pad_w;
     int64_t To;
@@ -89,7 +92,8 @@ int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream);
 int sfvos_conv_simt(const sfvos_conv_params* p, sfvos_stream stream);
 
 /* Weight-gradient GEMM: dw[(a,i,j)][c][n] += sum_{b,t,h,w} x[b,t+a-pad_t,h+i-pad_h,w+j-pad_w,c] * dy[b,t,h,w,n].
- * Replaces cudnn_convolution_backward_weight for the same modules.  dw is f32 [taps][C][N], accumulated. */
+ * Replaces cudnn_convolution_backward_weight for the same modules (and addmm's weight gradient for the box head's
+ * nn.Linear layers).  dw is f32 [taps][C][N], accumulated.  N: a multiple of 32 up to 256, or a multiple of 256. */
 typedef struct sfvos_wgrad_params {
     const void* x;  int64_t B, T, H, W, C, x_cstride;
     int64_t x_hstride, x_tstride, x_bstride;      /* 0 = dense */
@@ -218,6 +222,24 @@ int sfvos_mask_bce_bwd(const float* logits, const int64_t* labels, const float* 
 /* maskrcnn_inference: prob[k,0,s,s] = sigmoid(logits[k,labels[k]]). */
 int sfvos_mask_probs(const float* logits, const int64_t* labels, float* prob, int64_t K, int64_t S, int32_t n_cls,
                      sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Box-branch losses.  Replaces fastrcnn_loss (TV/models/detection/roi_heads.py:12-53: F.cross_entropy over the
+ * class logits + F.smooth_l1_loss(beta, reduction="sum") / M over the matched class's 4 box deltas of the
+ * positive ROIs), reached from code/helpers/model.py:346 via RoIHeads.forward (TV roi_heads.py:783).
+ * cls_logits [M,n_cls] and box_reg [M,4*n_cls] are f32 with a row stride (elements) each -- they may be column
+ * slices of one fused predictor output; labels int64 [M]; reg_targets f32 [M,4] dense.
+ * ------------------------------------------------------------------------------------------------------- */
+/* losses[0] = loss_classifier, losses[1] = loss_box_reg (written, not accumulated; deterministic). */
+int sfvos_fastrcnn_loss_fwd(const float* cls_logits, int64_t cls_stride, const float* box_reg, int64_t box_stride,
+                            const int64_t* labels, const float* reg_targets, int64_t M, int32_t n_cls, float beta,
+                            float* losses, sfvos_stream stream);
+/* gloss [2] = upstream gradients of the two losses.  Writes every element of dcls [M,n_cls] and dbox [M,4*n_cls]
+ * (row strides in elements; zeros outside the matched class / for background ROIs). */
+int sfvos_fastrcnn_loss_bwd(const float* cls_logits, int64_t cls_stride, const float* box_reg, int64_t box_stride,
+                            const int64_t* labels, const float* reg_targets, const float* gloss, int64_t M,
+                            int32_t n_cls, float beta, float* dcls, int64_t dcls_stride, float* dbox,
+                            int64_t dbox_stride, sfvos_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Optimiser-side helpers for the data-parallel step (the one collective is NCCL all-reduce, called from Python).

@@ -163,3 +163,45 @@ def test_multiscale_and_mask_head_match_golden():
     props = [torch.tensor([[50.0, 30.0, 210.0, 130.0], [140.0, 90.0, 310.0, 186.0], [0.0, 0.0, 20.5, 17.25]])]
     loss = ro.maskrcnn_loss(logits, props, [gt], [torch.tensor([1, 1])], [torch.tensor([0, 1, 0])])
     assert abs(loss.item() - float(gold["mh_loss"])) <= 1e-4 * abs(float(gold["mh_loss"]))
+
+
+def _box_golden_modules():
+    """The torchvision modules of tests/golden/make_box_golden.py, rebuilt from the seed (the 13 M weights are not stored)."""
+    from torchvision.models.detection.faster_rcnn import FastRCNNPredictor, TwoMLPHead
+    torch.manual_seed(21)
+    return TwoMLPHead(256 * 7 * 7, 1024), FastRCNNPredictor(1024, 2)
+
+
+def test_box_head_and_fastrcnn_loss_match_golden_and_torchvision():
+    gold = np.load(os.path.join(GOLDEN, "box_head.npz"))
+    head, pred = _box_golden_modules()
+    sd = {"box_head." + k: v for k, v in head.state_dict().items()}
+    sd.update({"box_predictor." + k: v for k, v in pred.state_dict().items()})
+    x = torch.from_numpy(gold["x"]).requires_grad_(True)
+    labels = [torch.from_numpy(gold["labels0"]), torch.from_numpy(gold["labels1"])]
+    targets = [torch.from_numpy(gold["targets0"]), torch.from_numpy(gold["targets1"])]
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    feat = ro.box_head_forward(leaves, x)
+    scores, deltas = ro.box_predictor_forward(leaves, feat)
+    l_cls, l_box = ro.fastrcnn_loss(scores, deltas, labels, targets)
+    for got, key in ((feat, "feat"), (scores, "scores"), (deltas, "deltas")):
+        ref = torch.from_numpy(gold[key])
+        assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), key
+    assert abs(l_cls.item() - float(gold["loss_cls"])) <= 1e-5 and abs(l_box.item() - float(gold["loss_box"])) <= 1e-5
+    (l_cls + l_box).backward()
+    gx = torch.from_numpy(gold["gx"])
+    assert (x.grad - gx).abs().max().item() <= 1e-4 * gx.abs().max().item()
+    for k, v in leaves.items():
+        assert abs(v.grad.double().sum().item() - float(gold["gsum_" + k])) <= 1e-4 * float(gold["gabs_" + k]) + 1e-9, k
+        got64 = v.grad.reshape(-1)[:: max(1, v.numel() // 64)][:64]
+        ref64 = torch.from_numpy(gold["g64_" + k])
+        assert (got64 - ref64).abs().max().item() <= 1e-4 * max(ref64.abs().max().item(), 1e-6), k
+    # the written-out loss against the live torchvision function on a larger random case (incl. |d| on both sides of beta)
+    from torchvision.models.detection.roi_heads import fastrcnn_loss as tv_loss
+    g = torch.Generator().manual_seed(5)
+    z, r = torch.randn(300, 3, generator=g) * 2, torch.randn(300, 12, generator=g) * 0.2
+    lab = [torch.randint(0, 3, (300,), generator=g)]
+    tgt = [torch.randn(300, 4, generator=g) * 0.2]
+    a, b = ro.fastrcnn_loss(z, r, lab, tgt)
+    ra, rb = tv_loss(z, r, lab, tgt)
+    assert abs(a.item() - ra.item()) <= 1e-6 and abs(b.item() - rb.item()) <= 1e-6
