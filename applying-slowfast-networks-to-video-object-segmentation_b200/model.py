@@ -66,6 +66,10 @@ class SegmentationModel(nn.Module):
         sf_roi_heads.install(self.maskrcnn_model.roi_heads)      # same parameters, libsfvos kernels
         self.features_cache = {}
         self.use_caching = True
+        # eval only: one temporal sweep per sequence chunk instead of one window per frame (same outputs, see
+        # SlowFastLayers.temporally_enhance_sequence); False restores the reference's per-frame loop
+        self.sequence_mode = True
+        self.sequence_chunk = 32
 
     # ---- feature cache / windowing (model.py:191-273) ----------------------------------------------------------------
     def compute_maskrcnn_features(self, images_tensors, indices):
@@ -116,6 +120,55 @@ class SegmentationModel(nn.Module):
     def _detach_features(self, features):
         return OrderedDict((k, v.detach()) for k, v in features.items())
 
+    # ---- eval-mode sequence sweep ------------------------------------------------------------------
+    @torch.no_grad()
+    def _forward_eval_sequence(self, transformed_images, targets, valid, original_image_sizes):
+        """Same detections as the per-frame loop of forward() in eval mode (model.py:318-348), computed per chunk of
+        ``sequence_chunk`` frames: the frozen backbone once per frame (what features_cache achieves in the reference),
+        SlowFast as one temporal sweep over the chunk plus its fp-1 halo frames, and ONE roi_heads call for all valid
+        frames of the chunk (roi_heads has no cross-image interaction in eval mode)."""
+        n = len(valid)
+        fp = self.fast_pathway_size
+        lo, hi = fp // 2, fp - fp // 2 - 1
+        tensors, sizes = transformed_images.tensors, transformed_images.image_sizes
+        cache = {}
+
+        def backbone(i):
+            if i not in cache:
+                cache[i] = self.maskrcnn_model.backbone(tensors[i:i + 1].to(self.device))
+            return cache[i]
+
+        detections = [{} for _ in range(n)]
+        step = max(1, int(self.sequence_chunk))
+        for c0 in range(0, n, step):
+            c1 = min(n, c0 + step)
+            idxs = [i for i in range(c0, c1) if valid[i]]
+            if not idxs:
+                continue
+            f0, f1 = max(0, c0 - lo), min(n, c1 + hi)
+            for key in [k for k in cache if k < f0]:
+                cache.pop(key)
+            frames = [backbone(i) for i in range(f0, f1)]
+            feats = OrderedDict((k, torch.cat([f[k] for f in frames])) for k in frames[0].keys())
+            merged = self.slow_fast.temporally_enhance_sequence(feats, halo=(c0 - f0, f1 - c1))
+            proposals = []
+            for i in idxs:
+                centre = self._index_features(feats, i - f0, i - f0 + 1)
+                target = self._targets_to_device(targets[i:i + 1], self.device)
+                props, _ = self.compute_rpn_proposals(tensors[i:i + 1], sizes[i:i + 1], centre, target)
+                proposals.append(props[0])
+            if len(idxs) == c1 - c0:
+                sel = merged
+            else:
+                pick = torch.tensor([i - c0 for i in idxs], device=self.device)
+                sel = OrderedDict((k, v[pick]) for k, v in merged.items())
+            image_sizes = sizes[0:1] * len(idxs)        # all images of one sequence have the same size (model.py:342)
+            dets, _ = self.maskrcnn_model.roi_heads(sel, proposals, image_sizes)
+            dets = self.maskrcnn_model.transform.postprocess(dets, image_sizes, [original_image_sizes[i] for i in idxs])
+            for i, d in zip(idxs, self._targets_to_device(dets, torch.device('cpu'))):
+                detections[i] = d
+        return detections
+
     # ---- forward (model.py:275-389) --------------------------------------------------------------------------------------
     def forward(self, images, targets=None, optimizer=None):
         self.features_cache = {}
@@ -129,6 +182,9 @@ class SegmentationModel(nn.Module):
         it = iter(t_targets)
         targets = [next(it) if v else {} for v in valid]
         images = transformed_images
+
+        if not self.training and self.sequence_mode:
+            return (0., self._forward_eval_sequence(transformed_images, targets, valid, original_image_sizes))
 
         total_loss = 0.
         all_detections = []

@@ -177,6 +177,62 @@ class SlowFastLayers(nn.Module):
         return merged
 
 
+    @torch.no_grad()
+    def temporally_enhance_sequence(self, frame_features, max_frames=None, halo=(0, 0)):
+        """Eval-mode features of EVERY frame of one sequence in a single temporal sweep.
+
+        ``frame_features``: OrderedDict{level: [F,256,H,W]} -- the backbone features of the F frames of a sequence, in
+        order.  Returns OrderedDict{level: [F,256,H,W]} whose row t equals what ``temporally_enhance_features`` returns for
+        the window centred on frame t (fast = frames [t - fp//2, t + ceil(fp/2)), slow = its centre sp frames, frames
+        outside the sequence all-zero: code/helpers/model.py:215-248,322-340).
+
+        Why it is the same arithmetic: every Conv3d has "valid" temporal padding and eval-mode BatchNorm is a fixed
+        per-channel affine map, so the whole stack is a shift-invariant temporal filter; consecutive windows share
+        fp - 1 frames and every intermediate activation at an absolute time is identical in all of them.  Feeding the
+        zero-padded sequence ([F + fp - 1] frames, the slow pathway a frame range of the same buffer) as ONE clip makes each
+        layer compute every such activation once: per frame fp/k-fold less convolution work (497.7 -> ~293 GFLOP at
+        (1,8), 4261 -> ~668 GFLOP at (4,32)) and one layout conversion per frame instead of fp.  Not valid in train mode
+        (batch statistics are per window), where it raises.  ``max_frames`` bounds the frames per sweep (memory).
+        ``halo=(hl, hr)``: the first hl / last hr given frames are context only (a caller streaming a long sequence in
+        pieces passes up to fp//2 / ceil(fp/2)-1 neighbouring frames); outputs are returned for the frames in between and
+        only the part of a window that the given frames do not cover is zero-filled."""
+        if self.training:
+            raise RuntimeError("temporally_enhance_sequence needs eval mode: train-mode BatchNorm statistics are per window")
+        ops.device_check()
+        dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
+        sp, fp = self.slow_pathway_size, self.fast_pathway_size
+        lo, hi = fp // 2, fp - fp // 2 - 1                  # zero frames before / after the sequence
+        s_off = fp // 2 - sp // 2                           # first slow frame inside a fast window (_slice_features)
+        keys = list(frame_features.keys())
+        hl, hr = halo
+        n_in = frame_features[keys[0]].shape[0]
+        n = n_in - hl - hr                                  # frames that get an output
+        assert n >= 1 and 0 <= hl <= lo and 0 <= hr <= hi, "halo must leave >= 1 frame and fit inside one window"
+        chunk = n if not max_frames else max(1, int(max_frames))
+        outs = OrderedDict((k, []) for k in keys)
+        for c0 in range(0, n, chunk):
+            c1 = min(n, c0 + chunk)
+            for key in keys:
+                x = frame_features[key]
+                _, c, h, w = x.shape
+                t_in = (c1 - c0) + fp - 1                    # padded frames [c0 - lo, c1 + hi) of the output numbering
+                fast_in = Act.empty(1, t_in, h, w, c, self._act_dtype, dev)
+                f0, f1 = max(-hl, c0 - lo), min(n + hr, c1 + hi)   # given frames inside the padded range
+                per = h * w * c
+                left, right = f0 - (c0 - lo), (c1 + hi) - f1
+                if left:
+                    fast_in.buf[:left * per].zero_()
+                if right:
+                    fast_in.buf[(t_in - right) * per:].zero_()
+                src = x[f0 + hl:f1 + hl].to(dev)
+                if src.dtype != torch.float32 or not src.is_contiguous():
+                    src = src.float().contiguous()
+                ops.nchw_to_nhwc(src, fast_in, frame_off=left)
+                slow_in = fast_in.frames(s_off, s_off + (c1 - c0) + sp - 1)
+                outs[key].append(_level_forward(self, slow_in, fast_in, False, None).as_nchw())
+        return OrderedDict((k, v[0] if len(v) == 1 else torch.cat(v)) for k, v in outs.items())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # engine
 # ----------------------------------------------------------------------------------------------------------------------
@@ -284,7 +340,9 @@ def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
 
 
 def _level_forward(mod, slow_in, fast_in, training, saved, scratch=None):
-    """One pyramid level (model.py:118-149 + the concat of :162).  Returns the merged f32 Act [B,1,H,W,256]."""
+    """One pyramid level (model.py:118-149 + the concat of :162).  Returns the merged f32 Act [B,T3,H,W,256]: T3 = 1 for
+    the reference's windows (sp / fp frames in); in sequence mode (temporally_enhance_sequence) the inputs are whole
+    zero-padded sequences and T3 = the number of frames."""
     sp = mod._specs
     dt_act = mod._act_dtype
     dev = fast_in.buf.device
@@ -303,8 +361,10 @@ def _level_forward(mod, slow_in, fast_in, training, saved, scratch=None):
     _conv_bn_forward(mod, sp["slow_conv2"], s1, s2.slice(0, 192), training, saved, scratch)
     _conv_bn_forward(mod, sp["fast_conv2"], f1, f2, training, saved, scratch)
     _conv_bn_forward(mod, sp["conv_f2s2"], f2, s2.slice(192, 64), training, saved, scratch)
-    # layer 3: both pathways land in one f32 [B,H,W,256] buffer = cat([slow, fast], 1).squeeze(2)
-    out = Act.empty(B, 1, H, W, 256, torch.float32, dev)
+    # layer 3: both pathways land in one f32 [B,T3,H,W,256] buffer = cat([slow, fast], 1).squeeze(2) when T3 = 1
+    t3 = t2s - sp["slow_conv3"].kt + 1
+    assert t3 >= 1 and t3 == t2f - sp["fast_conv3"].kt + 1, "slow / fast temporal extents do not meet after layer 3"
+    out = Act.empty(B, t3, H, W, 256, torch.float32, dev)
     _conv_bn_forward(mod, sp["slow_conv3"], s2, out.slice(0, 224), training, saved, scratch)
     _conv_bn_forward(mod, sp["fast_conv3"], f2, out.slice(224, 32), training, saved, scratch)
     if saved is not None:

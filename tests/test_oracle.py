@@ -205,3 +205,34 @@ def test_box_head_and_fastrcnn_loss_match_golden_and_torchvision():
     a, b = ro.fastrcnn_loss(z, r, lab, tgt)
     ra, rb = tv_loss(z, r, lab, tgt)
     assert abs(a.item() - ra.item()) <= 1e-6 and abs(b.item() - rb.item()) <= 1e-6
+
+
+@pytest.mark.parametrize("sp,fp", [(1, 8), (3, 7), (2, 16), (1, 1)])
+def test_eval_mode_is_a_shift_invariant_temporal_filter(sp, fp):
+    """The identity behind SlowFastLayers.temporally_enhance_sequence, on the reference restatement itself: in eval mode
+    the zero-padded sequence fed as ONE clip yields at temporal index t the output of the reference's window around t."""
+    from math import ceil, floor
+    levels = OrderedDict([("0", (6, 8))])
+    sd = so.init_state_dict(sp, fp, seed=63)
+    g = torch.Generator().manual_seed(2)
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+    n = 6
+    frames = torch.randn(n, 256, 6, 8, generator=g)
+    lo, hi = fp // 2, fp - fp // 2 - 1
+    padded = torch.cat([torch.zeros(lo, 256, 6, 8), frames, torch.zeros(hi, 256, 6, 8)])
+    s_off = fp // 2 - sp // 2
+    fast = padded.unsqueeze(0).transpose(1, 2)                                   # [1,256,n+fp-1,H,W]
+    slow = padded[s_off:s_off + n + sp - 1].unsqueeze(0).transpose(1, 2)
+    s, f = so.forward(sd, slow, fast, False)
+    assert s.shape[2] == n and f.shape[2] == n
+    sweep = torch.cat([s, f], dim=1)[0].transpose(0, 1)                          # [n,256,H,W]
+    for t in range(n):
+        win = torch.stack([frames[i] if 0 <= i < n else torch.zeros(256, 6, 8) for i in range(t - floor(fp / 2), t + ceil(fp / 2))])
+        p = fp // 2
+        ref = so.temporally_enhance_features(sd, [OrderedDict([("0", win[p - floor(sp / 2):p + ceil(sp / 2)])])],
+                                             [OrderedDict([("0", win)])], False)["0"][0]
+        assert (sweep[t] - ref).abs().max().item() <= 2e-5 * ref.abs().max().item(), t
