@@ -2,8 +2,8 @@
 from . import _lib, ops  # noqa: F401
 from .slowfast import SlowFastLayers  # noqa: F401
 from .roi_heads import (FastRCNNPredictor, MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, RoIHeads,  # noqa: F401
-                        TwoMLPHead, fastrcnn_loss, install, maskrcnn_inference, maskrcnn_loss, pool_pair,
-                        project_masks_on_boxes)
+                        TwoMLPHead, fastrcnn_loss, install, maskrcnn_inference, maskrcnn_loss, paste_masks_in_image,
+                        pool_pair, postprocess, project_masks_on_boxes)
 
-__all__ = ["SlowFastLayers", "MultiScaleRoIAlign", "MaskRCNNHeads", "MaskRCNNPredictor", "RoIHeads", "TwoMLPHead", "FastRCNNPredictor", "fastrcnn_loss", "install",
+__all__ = ["SlowFastLayers", "MultiScaleRoIAlign", "MaskRCNNHeads", "MaskRCNNPredictor", "RoIHeads", "TwoMLPHead", "FastRCNNPredictor", "fastrcnn_loss", "paste_masks_in_image", "postprocess", "install",
            "maskrcnn_loss", "maskrcnn_inference", "project_masks_on_boxes", "pool_pair", "ops", "_lib"]

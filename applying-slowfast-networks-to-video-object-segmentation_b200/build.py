@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libsfvos.so")
-SOURCES = ["runtime.cu", "conv_umma.cu", "conv_tstack_umma.cu", "conv_pair_umma.cu", "wgrad_umma.cu", "wgrad_stack_umma.cu", "wgrad_halo_umma.cu", "wgrad_c32_umma.cu", "wgrad_pair_umma.cu", "conv_simt.cu", "elementwise.cu", "roi_align.cu", "mask_tail.cu", "box_tail.cu"]
+SOURCES = ["runtime.cu", "conv_umma.cu", "conv_tstack_umma.cu", "conv_pair_umma.cu", "wgrad_umma.cu", "wgrad_stack_umma.cu", "wgrad_halo_umma.cu", "wgrad_c32_umma.cu", "wgrad_pair_umma.cu", "conv_simt.cu", "elementwise.cu", "roi_align.cu", "mask_tail.cu", "box_tail.cu", "paste_masks.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "sfvos.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

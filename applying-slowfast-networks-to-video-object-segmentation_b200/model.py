@@ -164,7 +164,7 @@ class SegmentationModel(nn.Module):
                 sel = OrderedDict((k, v[pick]) for k, v in merged.items())
             image_sizes = sizes[0:1] * len(idxs)        # all images of one sequence have the same size (model.py:342)
             dets, _ = self.maskrcnn_model.roi_heads(sel, proposals, image_sizes)
-            dets = self.maskrcnn_model.transform.postprocess(dets, image_sizes, [original_image_sizes[i] for i in idxs])
+            dets = sf_roi_heads.postprocess(dets, image_sizes, [original_image_sizes[i] for i in idxs])   # one paste launch per chunk
             for i, d in zip(idxs, self._targets_to_device(dets, torch.device('cpu'))):
                 detections[i] = d
         return detections

@@ -12,6 +12,7 @@ into ``maskrcnn_model.roi_heads`` (see ``install`` and INTEGRATION.md):
   FastRCNNPredictor    <- torchvision...faster_rcnn.FastRCNNPredictor    (TV/models/detection/faster_rcnn.py:347-370)
   fastrcnn_loss        <- TV/models/detection/roi_heads.py:12-53
   RoIHeads             <- torchvision...roi_heads.RoIHeads.forward       (TV/models/detection/roi_heads.py:739-887)
+  paste_masks_in_image / postprocess <- TV/models/detection/roi_heads.py:415-501, transform.py:257-279 (8(f) rank 4)
 
 Tensors exchanged between these modules keep torchvision's logical shapes ([K,C,P,P]) but are channels_last in
 memory and bf16 on the product path (fp32 when ``precision == "fp32"``), which is what the tensor-core kernels
@@ -705,6 +706,40 @@ class RoIHeads(tv_roi_heads.RoIHeads):
                 for mask_prob, r in zip(maskrcnn_inference(mask_logits, labels), result):
                     r["masks"] = mask_prob
         return result, losses
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# mask paste-back (the step after the path: code/helpers/model.py:347 -> transform.postprocess)
+# ----------------------------------------------------------------------------------------------------------------------
+def paste_masks_in_image(masks, boxes, img_shape, padding=1):
+    """Same signature and values as torchvision's paste_masks_in_image (TV roi_heads.py:474-501): masks [K,1,M,M], boxes
+    [K,4] in output-image pixels -> [K,1,im_h,im_w].  One kernel for all K masks instead of a Python loop per mask."""
+    ops.device_check()
+    im_h, im_w = int(img_shape[0]), int(img_shape[1])
+    K, M = masks.shape[0], masks.shape[-1]
+    out = torch.empty(K, 1, im_h, im_w, dtype=torch.float32, device=masks.device)
+    if K:
+        call("sfvos_paste_masks", _p(masks.float().contiguous()), _p(boxes.float().contiguous()), K, M, int(padding), im_h, im_w,
+             _p(out), stream())
+    return out.to(masks.dtype)
+
+
+def postprocess(result, image_shapes, original_image_sizes):
+    """GeneralizedRCNNTransform.postprocess in eval mode (TV transform.py:257-279): boxes rescaled to the original image,
+    masks pasted back.  Images that share one original size (all frames of a sequence, model.py:342) are pasted in ONE launch."""
+    from torchvision.models.detection.transform import resize_boxes
+    for pred, im_s, o_im_s in zip(result, image_shapes, original_image_sizes):
+        pred["boxes"] = resize_boxes(pred["boxes"], im_s, o_im_s)
+    groups = {}
+    for i, (pred, o_im_s) in enumerate(zip(result, original_image_sizes)):
+        if "masks" in pred:
+            groups.setdefault((int(o_im_s[0]), int(o_im_s[1])), []).append(i)
+    for size, idxs in groups.items():
+        counts = [result[i]["masks"].shape[0] for i in idxs]
+        pasted = paste_masks_in_image(torch.cat([result[i]["masks"] for i in idxs]), torch.cat([result[i]["boxes"] for i in idxs]), size)
+        for i, part in zip(idxs, pasted.split(counts)):
+            result[i]["masks"] = part
+    return result
 
 
 def install(roi_heads: tv_roi_heads.RoIHeads, precision: Optional[str] = None):

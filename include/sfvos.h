@@ -242,6 +242,16 @@ int sfvos_fastrcnn_loss_bwd(const float* cls_logits, int64_t cls_stride, const f
                             int64_t dbox_stride, sfvos_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Mask paste-back.  Replaces paste_masks_in_image (TV/models/detection/roi_heads.py:415-501: expand_masks, expand_boxes,
+ * per-mask F.interpolate(bilinear, align_corners=False) + slice assignment in a Python loop), reached from
+ * code/helpers/model.py:347 via GeneralizedRCNNTransform.postprocess (TV/models/detection/transform.py:257-279).
+ * masks f32 [K,1,M,M] (probabilities), boxes f32 [K,4] in the OUTPUT image's pixels, out f32 [K,1,im_h,im_w] (every
+ * element written; zeros outside the grown box).  One launch for all K masks (K <= 65535).
+ * ------------------------------------------------------------------------------------------------------- */
+int sfvos_paste_masks(const float* masks, const float* boxes, int64_t K, int32_t M, int32_t padding, int64_t im_h,
+                      int64_t im_w, float* out, sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Optimiser-side helpers for the data-parallel step (the one collective is NCCL all-reduce, called from Python).
  * ------------------------------------------------------------------------------------------------------- */
 /* y[i] = a*x[i] + b*y[i]  (flat f32), used to fold 1/world_size into the reduced gradient bucket. */

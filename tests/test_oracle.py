@@ -236,3 +236,25 @@ def test_eval_mode_is_a_shift_invariant_temporal_filter(sp, fp):
         ref = so.temporally_enhance_features(sd, [OrderedDict([("0", win[p - floor(sp / 2):p + ceil(sp / 2)])])],
                                              [OrderedDict([("0", win)])], False)["0"][0]
         assert (sweep[t] - ref).abs().max().item() <= 2e-5 * ref.abs().max().item(), t
+
+
+def _paste_cases():
+    g = torch.Generator().manual_seed(9)
+    masks = torch.rand(9, 1, 28, 28, generator=g)
+    boxes = torch.tensor([[10.3, 12.7, 90.2, 70.9], [-15.0, -8.0, 30.5, 25.0], [100.0, 60.0, 170.0, 125.0],
+                          [40.0, 30.0, 40.5, 30.2], [0.0, 0.0, 160.0, 120.0], [150.2, 100.1, 200.0, 140.0],
+                          [155.0, 110.0, 190.0, 150.0], [20.0, 20.0, 48.0, 48.0], [33.3, 44.4, 77.7, 99.9]])
+    # (a box entirely outside the image makes torchvision's slice assignment raise; detections are clipped to the image,
+    # so the reference never meets one -- the kernel writes zeros there)
+    return masks, boxes, (120, 160)
+
+
+def test_paste_masks_restatement_matches_torchvision():
+    from torchvision.models.detection.roi_heads import paste_masks_in_image as tv_paste
+    masks, boxes, shape = _paste_cases()
+    ref = tv_paste(masks, boxes, shape)
+    got = ro.paste_masks_in_image(masks, boxes, shape)
+    assert got.shape == ref.shape == (9, 1, 120, 160)
+    assert (got - ref).abs().max().item() <= 2e-6
+    assert ((got != 0) == (ref != 0)).all()                   # identical footprint: same integer boxes, same clipping
+    assert ro.paste_masks_in_image(masks[:0], boxes[:0], shape).shape == (0, 1, 120, 160)
