@@ -112,6 +112,18 @@ __global__ void __launch_bounds__(256) transpose2d_kernel(const float* __restric
     }
 }
 
+// fc fprop operand: [N][K] f32 -> [N][K] bf16, 8 elements per thread (the generic pack kernel spends its time on index arithmetic)
+__global__ void __launch_bounds__(256) convert_bf16x8_kernel(const float* __restrict__ src, __nv_bfloat16* dst, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+        uint4 u;
+        u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+        u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+        reinterpret_cast<uint4*>(dst)[i] = u;
+    }
+}
+
 // ---- per-channel reductions -------------------------------------------------------------------------------------
 // Block of 256 threads: thread -> (pixel lane, 8-channel group).  G = C/8 groups, L = 256/G pixel lanes.
 constexpr int RED_THREADS = 256;
@@ -457,6 +469,13 @@ extern "C" int sfvos_pack_weights(const float* w, void* out, int32_t out_dtype, 
     a.taps = (mode <= 1) ? (int)(kt * kh * kw) : 1;
     SF_CHECK(Cp >= a.Kc, "pack_weights: Cp=%lld smaller than the channel count %d", (long long)Cp, a.Kc);
     const long long total = (long long)a.N * a.taps * a.Cp;
+    if (mode == 0 && a.taps == 1 && a.out_bf16 && Cp == Cin && total % 8 == 0 && total >= (1 << 20) &&
+        (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        // fc fprop operand: the state_dict layout [Cout][Cin] already is the K-major operand -> a pure conversion
+        convert_bf16x8_kernel<<<grid_for(total / 8, 256), 256, 0, CS(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(out), total / 8);
+        SF_LAUNCH_CHECK();
+        return SFVOS_OK;
+    }
     if (mode == 1 && a.taps == 1 && a.out_bf16 && Cp == Cout && Cout >= 256 && Cin >= 256) {
         // fc dgrad operand: out[ci][co] = w[co][ci]
         dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32));

@@ -32,6 +32,9 @@ if ROOT not in sys.path:
 METRIC = "clip_frames_per_sec_fwd_bwd"
 UNIT = "clip-frames/s"
 SP, FP, B_PER_GPU, K_BOX, K_MASK = 1, 8, 8, 512, 128
+# BASELINE.json configs by (sp, fp, clips per GPU): "alpha = 8" reads as sp = fp / 8 (notation)
+CONFIGS = {"c2": (1, 8, 8, "C2"), "c3": (4, 32, 1, "C3 (long context, alpha=8)"), "c5": (2, 16, 8, "C5 (DP training, 16-frame clips, global batch 64)")}
+CONFIG_NAME = "C2"
 
 
 def _peaks():
@@ -155,7 +158,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: SlowFast(sp=1,fp=8) + ROIAlign + box head/losses + mask head/loss fwd+bwd (CPU sample: 1 clip/step)"},
+            "config": {"workload": f"{CONFIG_NAME}: SlowFast(sp={SP},fp={FP}) + ROIAlign + box head/losses + mask head/loss fwd+bwd (CPU sample: 1 clip/step)"},
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -359,10 +362,10 @@ def run_ours(args, rank, local_rank, world):
         line = {"metric": METRIC, "value": round(world * B_PER_GPU * FP / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "C2: SlowFast temporal module (sp=1, fp=8) + multi-level ROIAlign + box head (fc6/fc7/predictor/fastrcnn_loss) + mask head/predictor/loss, fwd+bwd",
+                "config": {"workload": f"{CONFIG_NAME}: SlowFast temporal module (sp={SP}, fp={FP}) + multi-level ROIAlign + box head (fc6/fc7/predictor/fastrcnn_loss) + mask head/predictor/loss, fwd+bwd",
                            "clips_per_gpu": B_PER_GPU, "frames_per_clip": FP, "levels": "192x336,96x168,48x84,24x42,12x21 x256ch",
                            "rois_per_clip": {"box": K_BOX, "mask": K_MASK}, "parallelism": f"dp{world} by clip, 1 NCCL grad all-reduce/step",
-                           "l2": "inputs (5.6 GB of features per step) far exceed the 126 MB L2; no explicit flush",
+                           "l2": f"inputs ({h2d / 1e9:.1f} GB of features per step) far exceed the 126 MB L2; no explicit flush",
                            "launch": mode, "eager_ms_per_step": round(ms_eager, 3)},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "model_tflops": round((conv_f + mask_f) * world / (ms * 1e-3) / 1e12, 1)}
@@ -378,7 +381,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="BASELINE.json workload: c2 (default, the configuration the metric is quoted on), c3 long context, c5 DP training")
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: the config's)")
     args = ap.parse_args()
+    global SP, FP, B_PER_GPU, CONFIG_NAME
+    SP, FP, B_PER_GPU, CONFIG_NAME = CONFIGS[args.config]
+    if args.config == "c5":
+        B_PER_GPU = max(1, 64 // max(1, args.gpus)) if args.gpus > 1 else 8      # global batch 64; one GPU cannot hold 64 clips
+    if args.clips:
+        B_PER_GPU = args.clips
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -390,7 +402,8 @@ def main():
         port = 29500 + (os.getpid() % 2000)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup)] + (["--no-cpu"] if args.no_cpu else [])
+               "--warmup", str(args.warmup), "--config", args.config] + (["--no-cpu"] if args.no_cpu else []) + (
+                   ["--clips", str(args.clips)] if args.clips else [])
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, local_rank, world)
 
