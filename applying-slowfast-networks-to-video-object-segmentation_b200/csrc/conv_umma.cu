@@ -38,6 +38,7 @@ struct ConvArgs {
     int TW, TH, tiles_w, tiles_h, ntiles;
     int N, kt, kh, kw, pad_t, pad_h, pad_w, cchunks;
     int nchunks;                                // N tiles of one pixel tile (wide fc layers: Cout = nchunks * 256)
+    int b_resident;                             // per-tap mode: ALL weight tiles stay in shared memory for the CTA's lifetime
     int halo, use_bo, a_stages, b_stages, a_stage_bytes, b_group;     // b_group = taps per B stage
     uint32_t idesc, tmem_cols, a_tx_bytes;
     void* y;
@@ -108,6 +109,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             int as = 0, bs = 0;
             uint32_t aphase = 0, bphase = 0;
             const int taps_hw = a.kh * a.kw;
+            if (a.b_resident) {
+                // small weight sets (1x1 lateral convs, the 2x2 ConvTranspose taps, the box predictor): every (tap, chunk)
+                // tile is loaded ONCE per CTA and reused by all its pixel tiles -- the per-tile L2 -> SM traffic drops to A
+                const int nb = a.kt * taps_hw * a.cchunks;
+                mbar_arrive_expect_tx(&b_full[0], (uint32_t)(nb * b_bytes));
+                for (int tp = 0; tp < a.kt * taps_hw; ++tp)
+                    for (int cc = 0; cc < a.cchunks; ++cc)
+                        tma_load_3d(smem_b + (tp * a.cchunks + cc) * b_bytes, &tmap_w, &b_full[0], cc * BK, 0, tp);
+            }
             for (int item = blockIdx.x; item < a.ntiles * a.nchunks; item += gridDim.x) {
                 // consecutive items = the N chunks of one pixel tile: concurrent CTAs share the activation tile in L2
                 const int tile = item / a.nchunks;
@@ -126,11 +136,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             for (int tj = 0; tj < a.kw; ++tj)
                                 for (int cc = 0; cc < a.cchunks; ++cc) {
                                     mbar_wait(&a_empty[as], aphase ^ 1);
-                                    mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes + b_bytes);
+                                    mbar_arrive_expect_tx(&a_full[as], a.a_tx_bytes + (a.b_resident ? 0 : b_bytes));
                                     tma_load_5d(smem_a + as * a.a_stage_bytes, &tmap_x, &a_full[as], cc * BK,
                                                 w0 + tj - a.pad_w, h0 + ti - a.pad_h, t + ta - a.pad_t, b);
-                                    tma_load_3d(smem_b + as * b_bytes, &tmap_w, &a_full[as], cc * BK, n0,
-                                                (ta * a.kh + ti) * a.kw + tj);
+                                    if (!a.b_resident)
+                                        tma_load_3d(smem_b + as * b_bytes, &tmap_w, &a_full[as], cc * BK, n0,
+                                                    (ta * a.kh + ti) * a.kw + tj);
                                     if (++as == a.a_stages) { as = 0; aphase ^= 1; }
                                 }
                 } else {
@@ -161,6 +172,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint32_t acc_phase = 0;
             const int taps_hw = a.kh * a.kw;
             const int outer = a.halo ? a.kt * a.cchunks : a.kt * taps_hw * a.cchunks;
+            if (a.b_resident) mbar_wait(&b_full[0], 0);
             for (int item = blockIdx.x; item < a.ntiles * a.nchunks; item += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -171,7 +183,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const uint32_t a_addr = smem_u32(smem_a + as * a.a_stage_bytes);
                     if (!a.halo) {
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(smem_b + as * b_bytes);
+                        const uint32_t b_addr = smem_u32(smem_b + (a.b_resident ? o : as) * b_bytes);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, 8 * ROW, LAYOUT);
@@ -384,6 +396,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         const double eff_halo = (double)a.H * a.W / (double)(tiles * BM);
         if (eff_halo >= eff_tap - 0.15) { a.halo = 1; a.TW = 8; a.TH = 16; }
     }
+    a.b_resident = 0;
     a.use_bo = env_int("SFVOS_HALO_BO", 0);   // measured on B200: the swizzle XOR uses absolute smem address bits, so a shifted start needs NO base offset
     a.tiles_w = (a.W + a.TW - 1) / a.TW;
     a.tiles_h = (a.H + a.TH - 1) / a.TH;
@@ -411,10 +424,19 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         abox_w = (uint32_t)a.TW; abox_h = (uint32_t)a.TH;
         a.a_stage_bytes = BM * BK * 2;
         a.b_group = 1;
-        int st = smem_budget / (a.a_stage_bytes + b_bytes);
-        if (st > 8) st = 8;
-        SF_CHECK(st >= 2, "conv_umma: not enough shared memory for 2 stages");
-        a.a_stages = a.b_stages = st;
+        const long long all_b = (long long)p->kt * p->kh * p->kw * a.cchunks * b_bytes;
+        if (a.nchunks == 1 && all_b <= 144 * 1024 && env_int("SFVOS_B_RESIDENT", 1)) {
+            a.b_resident = 1;
+            a.b_stages = (int)(all_b / b_bytes);
+            int st = (int)((smem_budget - all_b) / a.a_stage_bytes);
+            a.a_stages = st > 8 ? 8 : st;
+            SF_CHECK(a.a_stages >= 3, "conv_umma: not enough shared memory next to the resident weights");
+        } else {
+            int st = smem_budget / (a.a_stage_bytes + b_bytes);
+            if (st > 8) st = 8;
+            SF_CHECK(st >= 2, "conv_umma: not enough shared memory for 2 stages");
+            a.a_stages = a.b_stages = st;
+        }
     }
     a.a_tx_bytes = abox_w * abox_h * BK * 2;
     a.idesc = umma_idesc_bf16(BM, a.N, 0, 0);
