@@ -46,9 +46,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int lane = threadIdx.x & 31;
 
     // work item
-    const int tap = blockIdx.x % (a.kt * a.kh * a.kw);
-    const int mblk = (blockIdx.x / (a.kt * a.kh * a.kw)) % a.mblks;
-    const int nblk = (blockIdx.x / (a.kt * a.kh * a.kw * a.mblks)) % a.nblks;
+    // N block fastest: the nblks CTAs that read the same x block run side by side and share it in L2
+    const int nblk = blockIdx.x % a.nblks;
+    const int tap = (blockIdx.x / a.nblks) % (a.kt * a.kh * a.kw);
+    const int mblk = (blockIdx.x / (a.nblks * a.kt * a.kh * a.kw)) % a.mblks;
     const int split = blockIdx.x / (a.kt * a.kh * a.kw * a.mblks * a.nblks);
     const int n_base = nblk * a.N;
     const int tj = tap % a.kw, ti = (tap / a.kw) % a.kh, ta = tap / (a.kw * a.kh);

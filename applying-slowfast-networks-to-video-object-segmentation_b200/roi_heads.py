@@ -130,7 +130,9 @@ class MultiScaleRoIAlign(nn.Module):
         self.canonical_level = canonical_level
         self.out_layout = out_layout
         self.precision = precision or _default_precision()
-        self.out_dtype = out_dtype          # None: f32 for "nchw" (a torch consumer), the activation dtype for "nhwc"
+        # None: f32 for "nchw" (a torch consumer), the activation dtype for "nhwc"; "act": always the activation dtype of
+        # ``self.precision`` (the native box head's [K, C*P*P] rows); or an explicit torch dtype
+        self.out_dtype = out_dtype
 
     def _setup_scales(self, feats, image_shapes):
         max_h = max(s[0] for s in image_shapes)
@@ -151,6 +153,8 @@ class MultiScaleRoIAlign(nn.Module):
 
     def _out_spec(self):
         nchw = self.out_layout == "nchw"
+        if self.out_dtype == "act":
+            return nchw, _act_dtype(self.precision)
         if self.out_dtype is not None:
             return nchw, self.out_dtype
         return nchw, (torch.float32 if nchw else _act_dtype(self.precision))
@@ -752,7 +756,7 @@ def install(roi_heads: tv_roi_heads.RoIHeads, precision: Optional[str] = None):
         if old is None:
             continue
         # the native box head consumes the [K, C*P*P] rows (torchvision's flatten order) in the activation dtype
-        od = _act_dtype(precision) if (name == "box_roi_pool" and native_box) else None
+        od = "act" if (name == "box_roi_pool" and native_box) else None
         new = MultiScaleRoIAlign(list(old.featmap_names), old.output_size, old.sampling_ratio,
                                  canonical_scale=old.canonical_scale, canonical_level=old.canonical_level,
                                  out_layout=layout, precision=precision, out_dtype=od)

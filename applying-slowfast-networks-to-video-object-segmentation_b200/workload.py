@@ -9,7 +9,7 @@ from collections import OrderedDict
 import torch
 
 from . import ops
-from .roi_heads import (FastRCNNPredictor, MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, TwoMLPHead, _act_dtype,
+from .roi_heads import (FastRCNNPredictor, MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, TwoMLPHead,
                         fastrcnn_loss, maskrcnn_loss, pool_pair)
 from .slowfast import SlowFastLayers
 
@@ -137,7 +137,7 @@ class HotPathStep:
         self.box_head = TwoMLPHead(256 * 7 * 7, 1024).to(self.device)
         self.box_predictor = FastRCNNPredictor(1024, 2).to(self.device)
         self.box_head.precision = self.box_predictor.precision = precision
-        self.box_roi_pool = MultiScaleRoIAlign(names, 7, 2, out_layout="nchw", precision=precision, out_dtype=_act_dtype(precision))
+        self.box_roi_pool = MultiScaleRoIAlign(names, 7, 2, out_layout="nchw", precision=precision, out_dtype="act")
         self.mask_roi_pool = MultiScaleRoIAlign(names, 14, 2, out_layout="nhwc", precision=precision)
         self.image_shapes = [IMAGE_HW] * n_clips
         box = synthetic_rois(n_clips, k_box, seed=4321)

@@ -127,3 +127,61 @@ def test_roi_align_bench_rois_match_torchvision_cuda_op(P, k_per_clip):
     (ref * wgt).sum().backward()
     for k in names:
         assert _nerr(f_a[k].grad, f_b[k].grad) < 1e-5, k
+
+
+def test_box_branch_bench_size_properties_and_cublas_crosscheck():
+    """The box branch at the bench size (M = 4096 ROIs, fc6 12544 -> 1024): exact power-of-two scaling of the N-tiled GEMM
+    (every pixel tile x N chunk), linear + accumulating weight gradient, and the whole fc6 output against a cuBLAS bf16 GEMM
+    with fp32 accumulation of the same bf16 operands (an independent implementation of the same arithmetic)."""
+    from sfvos_b200 import ops
+    M, K, N = 4096, 12544, 1024
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    b = torch.randn(N, device=DEV, generator=g)
+    wp = ops.pack_weights(w.view(N, K, 1, 1, 1), 0, ops.BF16, K)
+    assert torch.equal(wp.view(N, K), w.bfloat16())                       # the vectorised conversion is RNE like torch
+    outs = []
+    for scale in (1.0, 2.0):
+        xa = ops.Act((x.float() * scale).bfloat16().reshape(-1), 1, 1, 1, M, K)
+        y = ops.Act.empty(1, 1, 1, M, N, torch.float32, DEV)
+        ops.conv(xa, wp, K, N, (1, 1, 1), (0, 0, 0), 1, y, umma=True)
+        outs.append(y.buf.view(M, N).clone())
+    assert torch.equal(outs[1], 2 * outs[0])
+    ref = torch.matmul(x, w.bfloat16().t()).float()                        # cuBLAS, bf16 output of fp32 accumulators
+    assert _nerr(outs[0], ref) < 4e-3                                      # bf16 output rounding of the cuBLAS side
+    ref32 = x.float() @ w.bfloat16().float().t()
+    assert _nerr(outs[0], ref32) < 2e-5
+    # bias + ReLU epilogue on all N chunks
+    y = ops.Act.empty(1, 1, 1, M, N, torch.float32, DEV)
+    ops.conv(ops.Act(x.reshape(-1), 1, 1, 1, M, K), wp, K, N, (1, 1, 1), (0, 0, 0), 1, y, umma=True, relu=True, shift=b)
+    assert _nerr(y.buf.view(M, N), torch.relu(ref32 + b)) < 2e-5
+    # weight gradient: linear in dy, accumulating
+    dy = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    dwp = torch.zeros(K * N, device=DEV)
+    xa = ops.Act(x.reshape(-1), 1, 1, 1, M, K)
+    ops.wgrad(xa, ops.Act(dy.reshape(-1), 1, 1, 1, M, N), (1, 1, 1), (0, 0, 0), dwp, umma=True)
+    one = dwp.clone()
+    ops.wgrad(xa, ops.Act((dy.float() * 2).bfloat16().reshape(-1), 1, 1, 1, M, N), (1, 1, 1), (0, 0, 0), dwp, umma=True)
+    assert _nerr(dwp, 3 * one) < 1e-6
+    refw = (x.float().t() @ dy.float())                                    # [K, N] = the packed gradient layout
+    assert _nerr(one.view(K, N), refw) < 2e-5
+
+
+def test_sequence_sweep_full_size_level_is_bit_identical_to_windows():
+    """Eval-mode sequence sweep at a full-size pyramid level (96x168): identical bits to the per-window path."""
+    from sfvos_b200 import SlowFastLayers
+    torch.manual_seed(63)
+    sp, fp, n = 1, 8, 10
+    mod = SlowFastLayers(256, torch.device(DEV), sp, fp).cuda().eval()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    frames = OrderedDict([("1", torch.randn(n, 256, 96, 168, device=DEV, generator=g))])
+    seq = mod.temporally_enhance_sequence(frames)["1"]
+    zero = torch.zeros_like(frames["1"][0])
+    for t in (0, 4, n - 1):
+        idx = range(t - fp // 2, t + (fp + 1) // 2)
+        fast = OrderedDict([("1", torch.stack([frames["1"][i] if 0 <= i < n else zero for i in idx]))])
+        slow = OrderedDict([("1", fast["1"][fp // 2 - sp // 2:fp // 2 - sp // 2 + sp])])
+        with torch.no_grad():
+            win = mod.temporally_enhance_features([slow], [fast])["1"]
+        assert torch.equal(seq[t:t + 1], win), t

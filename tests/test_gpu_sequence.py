@@ -108,7 +108,6 @@ def test_segmentation_model_sequence_mode_equals_per_frame_loop():
               model.maskrcnn_model.roi_heads.mask_head, model.maskrcnn_model.roi_heads.mask_predictor,
               model.maskrcnn_model.roi_heads.box_head, model.maskrcnn_model.roi_heads.box_predictor):
         m.precision = "fp32"
-    model.maskrcnn_model.roi_heads.box_roi_pool.out_dtype = torch.float32
     model.maskrcnn_model.roi_heads.score_thresh = 0.0
     imgs, targets = _sequence(n=5)
     targets[2] = {}                                  # a frame without objects is skipped (model.py:289-296) but still feeds its neighbours' windows
