@@ -26,7 +26,10 @@ constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
 constexpr int TW = 8, TH = 16;              // spatial tile (8 wide x 16 tall = 128 accumulator rows)
-constexpr int MAX_NSP = 9;                  // 3x3 spatial taps (or 1: k_t x 1 x 1 lateral convolutions)
+constexpr int SMALL_BYTES = 2048;           // barriers, scale / shift, statistics
+constexpr int STAGE_PITCH = 33;             // floats per staged accumulator row (32 + 1: conflict-free both ways)
+constexpr int STAGE_BYTES = 4 * 32 * STAGE_PITCH * 4;   // one 32 x 32 f32 block per epilogue warp
+constexpr int STAGE_RESERVE = (STAGE_BYTES + 1023) / 1024 * 1024;
 
 struct TsArgs {
     int B, To, Ti, H, W;
@@ -34,7 +37,7 @@ struct TsArgs {
     int kt, pad_t, G, ngroups, Fg, nfg, cchunks;
     int LP, a_stages, a_stage_bytes, piece_bytes;
     uint32_t a_tx_bytes, tmem_cols;
-    int nbuf, b_resident;
+    int nbuf, b_resident, stage_mode;            // stage_mode: f32 epilogue through the shared-memory transpose
     void* y;
     int y_bf16, relu, accumulate;
     long long y_cstride;
@@ -91,6 +94,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     float* s_shift = s_scale + NC;
     float* s_sum = s_shift + NC;
     float* s_sq = s_sum + NC;
+    float* s_stage = reinterpret_cast<float*>(smem_b + NSP * a.piece_bytes + SMALL_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -272,39 +276,28 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     s = warp_transpose_reduce32(f, lane);
                     atomicAdd(&s_sq[lane], s);
                 }
-                if (valid) {
-                    float o[32];
-                    if (affine) {           // per-channel scale / shift from shared memory, 16 bytes per load
-                        const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
-                        const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
+                float o[32];
+                if (affine) {           // per-channel scale / shift from shared memory, 16 bytes per load
+                    const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+                    const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 sc = sc4[j], sh = sh4[j];
-                            o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-                            o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-                            o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-                            o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 sc = sc4[j], sh = sh4[j];
+                        o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+                        o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+                        o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+                        o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
                     }
-                    if (a.relu) {
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.0f);
-                    }
-                    if (a.y_bf16) {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride);
+                    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+                }
+                if (a.relu) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
-                            u.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
-                            u.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
-                            u.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
-                            dst[j] = u;
-                        }
-                    } else {
+                    for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.0f);
+                }
+                if (!a.y_bf16 && !a.stage_mode) {
+                    if (valid) {
                         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + pix * a.y_cstride);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -316,6 +309,50 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                             dst[j] = u;
                         }
                     }
+                } else if (a.y_bf16) {
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            u.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
+                            u.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+                            u.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+                            u.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+                            dst[j] = u;
+                        }
+                    }
+                } else {
+                    // f32 rows (raw conv outputs, data gradients; the lateral dgrads read-modify-write them): a thread owns
+                    // one pixel's 128 bytes, so a direct store is 32 lanes x 16 B on 32 different lines per instruction.
+                    // Transpose the warp's 32 x 32 block through shared memory instead: 8 lanes cover one pixel's 128 B and an
+                    // instruction covers 4 neighbouring pixels = 512 contiguous bytes (of a dense 32-channel tensor).
+                    float* stage = s_stage + q * (32 * STAGE_PITCH);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stage[lane * STAGE_PITCH + j] = o[j];
+                    __syncwarp();
+                    const int sub = lane >> 3, part = lane & 7;
+                    float4* dsts[8];
+                    float4 olds[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {                    // all 8 reads of the read-modify-write in flight at once
+                        const int rr = q * 32 + 4 * i + sub;         // row of the tile
+                        const int hh = it.h0 + rr / TW, ww = it.w0 + (rr - (rr / TW) * TW);
+                        dsts[i] = nullptr;
+                        olds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (hh < a.H && ww < a.W) {
+                            const long long pp = (((long long)it.b * a.To + t) * a.H + hh) * a.W + ww;
+                            dsts[i] = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + pp * a.y_cstride) + part;
+                            if (a.accumulate) olds[i] = *dsts[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float* sv = stage + (4 * i + sub) * STAGE_PITCH + 4 * part;
+                        if (dsts[i] != nullptr)
+                            *dsts[i] = make_float4(sv[0] + olds[i].x, sv[1] + olds[i].y, sv[2] + olds[i].z, sv[3] + olds[i].w);
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -386,7 +423,7 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.a_tx_bytes = (uint32_t)(a.LP * (TH + 2 * HALO) * ROW);
     a.a_stage_bytes = (int)((a.a_tx_bytes + 1023u) & ~1023u);
     // temporal taps stacked per MMA: all 9 spatial pieces of a (tap group, chunk) stay resident next to >= 2 (3) A stages
-    const int smem_budget = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers, scale/shift, stats*/;
+    const int smem_budget = 227 * 1024 - 1024 /*align*/ - SMALL_BYTES - STAGE_RESERVE /*epilogue transpose buffers*/;
     int gmax = env_int("SFVOS_TSTACK_G", BK == 64 ? 3 : 8);
     if (gmax < 1) gmax = 1;
     if (gmax > 8) gmax = 8;
@@ -402,6 +439,10 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.y = p->y; a.y_bf16 = (p->y_dtype == SFVOS_BF16); a.relu = p->relu; a.accumulate = p->accumulate;
     a.y_cstride = p->y_cstride;
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
+    {   // 0 = direct stores, 1 = staged only for read-modify-write outputs, 2 = staged for every f32 output
+        const int m = env_int("SFVOS_TSTACK_STAGE", 1);
+        a.stage_mode = (m >= 2 || (m == 1 && p->accumulate)) ? 1 : 0;
+    }
 
     CUtensorMap tx, tw;
     int rc;
@@ -425,7 +466,7 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
         rc = sfvos_make_tmap(&tw, p->w, 4, dims, str, box, ROW);
         if (rc) return rc;
     }
-    const int smem_bytes = a.a_stages * a.a_stage_bytes + NSP * a.piece_bytes + 1024 + 2048;
+    const int smem_bytes = a.a_stages * a.a_stage_bytes + NSP * a.piece_bytes + 1024 + SMALL_BYTES + STAGE_RESERVE;
     int grid = sfvos_num_sms();
     if (grid > a.nitems) grid = a.nitems;
 #define SF_TSTACK_LAUNCH(BK_, NSP_)                                                                                  \
