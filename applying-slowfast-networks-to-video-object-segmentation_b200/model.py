@@ -70,6 +70,7 @@ class SegmentationModel(nn.Module):
         # SlowFastLayers.temporally_enhance_sequence); False restores the reference's per-frame loop
         self.sequence_mode = True
         self.sequence_chunk = 32
+        self.transform_on_device = True      # eval sweep only: GeneralizedRCNNTransform on the GPU (the reference runs it on the host)
 
     # ---- feature cache / windowing (model.py:191-273) ----------------------------------------------------------------
     def compute_maskrcnn_features(self, images_tensors, indices):
@@ -154,8 +155,7 @@ class SegmentationModel(nn.Module):
             proposals = []
             for i in idxs:
                 centre = self._index_features(feats, i - f0, i - f0 + 1)
-                target = self._targets_to_device(targets[i:i + 1], self.device)
-                props, _ = self.compute_rpn_proposals(tensors[i:i + 1], sizes[i:i + 1], centre, target)
+                props, _ = self.compute_rpn_proposals(tensors[i:i + 1], sizes[i:i + 1], centre, None)   # eval: targets unused
                 proposals.append(props[0])
             if len(idxs) == c1 - c0:
                 sel = merged
@@ -173,6 +173,15 @@ class SegmentationModel(nn.Module):
     def forward(self, images, targets=None, optimizer=None):
         self.features_cache = {}
         original_image_sizes = [tuple(img.shape[-2:]) for img in images]
+        if not self.training and self.sequence_mode:
+            # eval sweep: targets only say which frames to skip (model.py:289-296) -- RPN and roi_heads ignore them in eval
+            # mode -- so the reference's second transform pass (model.py:299) is not needed; with ``transform_on_device`` the
+            # resize / normalise of GeneralizedRCNNTransform runs on the GPU instead of the host cores
+            valid = [int('boxes' in t and len(t['boxes']) > 0) for t in targets]
+            if self.transform_on_device:
+                images = [img.to(self.device, non_blocking=True) for img in images]
+            transformed_images, _ = self.maskrcnn_model.transform(images)
+            return (0., self._forward_eval_sequence(transformed_images, targets, valid, original_image_sizes))
         transformed_images, _ = self.maskrcnn_model.transform(images)
 
         valid = [int('boxes' in targets[i] and len(targets[i]['boxes']) > 0) for i in range(len(transformed_images.tensors))]
@@ -182,9 +191,6 @@ class SegmentationModel(nn.Module):
         it = iter(t_targets)
         targets = [next(it) if v else {} for v in valid]
         images = transformed_images
-
-        if not self.training and self.sequence_mode:
-            return (0., self._forward_eval_sequence(transformed_images, targets, valid, original_image_sizes))
 
         total_loss = 0.
         all_detections = []
