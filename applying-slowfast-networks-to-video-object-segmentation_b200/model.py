@@ -70,6 +70,9 @@ class SegmentationModel(nn.Module):
         # SlowFastLayers.temporally_enhance_sequence); False restores the reference's per-frame loop
         self.sequence_mode = True
         self.sequence_chunk = 32
+        self.backbone_batch = 8              # eval sweep only: frames per backbone call (1 = one call per frame like the reference)
+        self.batch_rpn = True                # eval sweep only: one RPN call per chunk instead of one per frame
+        self.phase_times = {}                # filled when SFVOS_PIPE_TIMING is set (tools/bench_pipeline.py)
         self.transform_on_device = True      # eval sweep only: GeneralizedRCNNTransform on the GPU (the reference runs it on the host)
 
     # ---- feature cache / windowing (model.py:191-273) ----------------------------------------------------------------
@@ -134,13 +137,31 @@ class SegmentationModel(nn.Module):
         tensors, sizes = transformed_images.tensors, transformed_images.image_sizes
         cache = {}
 
-        def backbone(i):
-            if i not in cache:
-                cache[i] = self.maskrcnn_model.backbone(tensors[i:i + 1].to(self.device))
-            return cache[i]
+        def backbone_range(lo_i, hi_i):
+            """Per-frame features of frames [lo_i, hi_i): the frozen backbone runs once per frame (what features_cache achieves
+            in the reference), ``backbone_batch`` frames per call."""
+            missing = [i for i in range(lo_i, hi_i) if i not in cache]
+            bb = max(1, int(self.backbone_batch))
+            for j in range(0, len(missing), bb):
+                grp = missing[j:j + bb]
+                out = self.maskrcnn_model.backbone(tensors[grp[0]:grp[-1] + 1].to(self.device))     # missing frames are contiguous
+                for n_, i in enumerate(grp):
+                    cache[i] = OrderedDict((k, v[n_:n_ + 1]) for k, v in out.items())
+            return [cache[i] for i in range(lo_i, hi_i)]
 
         detections = [{} for _ in range(n)]
         step = max(1, int(self.sequence_chunk))
+        prof = self.phase_times if os.environ.get("SFVOS_PIPE_TIMING") else None   # opt-in per-phase wall clock (synchronising)
+
+        def tick(name, t0):
+            if prof is None:
+                return 0.0
+            import time
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            if t0:
+                prof[name] = prof.get(name, 0.0) + now - t0
+            return now
         for c0 in range(0, n, step):
             c1 = min(n, c0 + step)
             idxs = [i for i in range(c0, c1) if valid[i]]
@@ -149,24 +170,41 @@ class SegmentationModel(nn.Module):
             f0, f1 = max(0, c0 - lo), min(n, c1 + hi)
             for key in [k for k in cache if k < f0]:
                 cache.pop(key)
-            frames = [backbone(i) for i in range(f0, f1)]
+            t = tick("", 0.0)
+            frames = backbone_range(f0, f1)
             feats = OrderedDict((k, torch.cat([f[k] for f in frames])) for k in frames[0].keys())
+            t = tick("backbone", t)
             merged = self.slow_fast.temporally_enhance_sequence(feats, halo=(c0 - f0, f1 - c1))
+            t = tick("slowfast_sweep", t)
             proposals = []
-            for i in idxs:
-                centre = self._index_features(feats, i - f0, i - f0 + 1)
-                props, _ = self.compute_rpn_proposals(tensors[i:i + 1], sizes[i:i + 1], centre, None)   # eval: targets unused
-                proposals.append(props[0])
+            if self.batch_rpn:          # one RPN call for the chunk's valid frames (per-image top-k / NMS inside, as per frame)
+                if idxs == list(range(idxs[0], idxs[-1] + 1)):
+                    centre = self._index_features(feats, idxs[0] - f0, idxs[-1] + 1 - f0)
+                    imgs = tensors[idxs[0]:idxs[-1] + 1]
+                else:
+                    rel = torch.tensor([i - f0 for i in idxs], device=self.device)
+                    centre = OrderedDict((k, v[rel]) for k, v in feats.items())
+                    imgs = tensors[idxs]
+                proposals, _ = self.compute_rpn_proposals(imgs, [sizes[i] for i in idxs], centre, None)   # eval: targets unused
+            else:
+                for i in idxs:
+                    centre = self._index_features(feats, i - f0, i - f0 + 1)
+                    props, _ = self.compute_rpn_proposals(tensors[i:i + 1], sizes[i:i + 1], centre, None)
+                    proposals.append(props[0])
             if len(idxs) == c1 - c0:
                 sel = merged
             else:
                 pick = torch.tensor([i - c0 for i in idxs], device=self.device)
                 sel = OrderedDict((k, v[pick]) for k, v in merged.items())
+            t = tick("rpn", t)
             image_sizes = sizes[0:1] * len(idxs)        # all images of one sequence have the same size (model.py:342)
             dets, _ = self.maskrcnn_model.roi_heads(sel, proposals, image_sizes)
-            dets = sf_roi_heads.postprocess(dets, image_sizes, [original_image_sizes[i] for i in idxs])   # one paste launch per chunk
-            for i, d in zip(idxs, self._targets_to_device(dets, torch.device('cpu'))):
+            t = tick("roi_heads", t)
+            # one paste launch and one pinned D2H copy of the masks per chunk (the reference moves every detection to the host, model.py:348)
+            dets = sf_roi_heads.postprocess(dets, image_sizes, [original_image_sizes[i] for i in idxs], to_cpu=True)
+            for i, d in zip(idxs, dets):
                 detections[i] = d
+            t = tick("paste_d2h", t)
         return detections
 
     # ---- forward (model.py:275-389) --------------------------------------------------------------------------------------

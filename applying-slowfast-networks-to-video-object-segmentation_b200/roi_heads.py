@@ -728,9 +728,11 @@ def paste_masks_in_image(masks, boxes, img_shape, padding=1):
     return out.to(masks.dtype)
 
 
-def postprocess(result, image_shapes, original_image_sizes):
+def postprocess(result, image_shapes, original_image_sizes, to_cpu=False):
     """GeneralizedRCNNTransform.postprocess in eval mode (TV transform.py:257-279): boxes rescaled to the original image,
-    masks pasted back.  Images that share one original size (all frames of a sequence, model.py:342) are pasted in ONE launch."""
+    masks pasted back.  Images that share one original size (all frames of a sequence, model.py:342) are pasted in ONE launch.
+    ``to_cpu=True`` also performs the reference's move of the detections to the host (model.py:348) -- the pasted masks of a
+    group cross PCIe as ONE asynchronous copy into pinned memory instead of one pageable copy per tensor."""
     from torchvision.models.detection.transform import resize_boxes
     for pred, im_s, o_im_s in zip(result, image_shapes, original_image_sizes):
         pred["boxes"] = resize_boxes(pred["boxes"], im_s, o_im_s)
@@ -738,11 +740,24 @@ def postprocess(result, image_shapes, original_image_sizes):
     for i, (pred, o_im_s) in enumerate(zip(result, original_image_sizes)):
         if "masks" in pred:
             groups.setdefault((int(o_im_s[0]), int(o_im_s[1])), []).append(i)
+    pending = []
     for size, idxs in groups.items():
         counts = [result[i]["masks"].shape[0] for i in idxs]
         pasted = paste_masks_in_image(torch.cat([result[i]["masks"] for i in idxs]), torch.cat([result[i]["boxes"] for i in idxs]), size)
+        if to_cpu and pasted.is_cuda:
+            host = torch.empty(pasted.shape, dtype=pasted.dtype, pin_memory=True)     # caching host allocator: reused across chunks
+            host.copy_(pasted, non_blocking=True)
+            pending.append(pasted)                                                    # keep the source alive until the sync below
+            pasted = host
         for i, part in zip(idxs, pasted.split(counts)):
             result[i]["masks"] = part
+    if to_cpu:
+        for pred in result:
+            for k in list(pred.keys()):
+                if torch.is_tensor(pred[k]) and pred[k].is_cuda:
+                    pred[k] = pred[k].cpu()
+        if pending:
+            torch.cuda.current_stream().synchronize()
     return result
 
 

@@ -72,6 +72,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        model.phase_times.clear()
         t0 = time.perf_counter()
         run(mode)
         torch.cuda.synchronize()
@@ -82,6 +83,7 @@ def main():
             print(json.dumps({"config": "C4 full inference pipeline, sharded by sequence", "sequence_sweep": mode, "sp": a.sp, "fp": a.fp,
                               "n_gpus": world, "sequences": lengths, "frames_total": sum(lengths), "seconds": round(sec.item(), 3),
                               "frames_per_s": round(sum(lengths) / sec.item(), 2),
+                              "phase_seconds_rank0": {k: round(v, 3) for k, v in model.phase_times.items()},
                               "note": "wall clock incl. the torchvision fp32 backbone/RPN, per-frame D2H of the pasted masks (as the reference does)"}),
                   flush=True)
     if world > 1:
