@@ -108,3 +108,15 @@ def test_workload_flop_formulas_match_survey():
     assert abs(wl.conv_flops(4, 32) / 1e9 - 9260.4) < 0.5
     assert abs(wl.conv_flops(2, 16) / 1e9 - 3196.4) < 0.5
     assert abs(wl.MASK_HEAD_FLOPS_PER_ROI / 1e9 - 1.028) < 1e-3
+    assert abs(wl.BOX_HEAD_FLOPS_PER_ROI / 1e9 - 0.0278) < 1e-4          # box head 0.0278 GFLOP/ROI fwd
+    lab, tgt = wl.synthetic_box_targets(2, 512, 128)
+    assert [int(l.sum()) for l in lab] == [128, 128] and tgt[0].shape == (512, 4) and not torch.equal(tgt[0], tgt[1])
+
+
+def test_bench_configs_map_to_baseline():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.CONFIGS["c2"][:3] == (1, 8, 8) and bench.CONFIGS["c3"][:2] == (4, 32) and bench.CONFIGS["c5"][:2] == (2, 16)
+    assert bench.METRIC == "clip_frames_per_sec_fwd_bwd" and bench.UNIT == "clip-frames/s"
