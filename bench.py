@@ -299,6 +299,12 @@ def run_ours(args, rank, local_rank, world):
             roi["roi_align_" + tag] = {"bound": "hbm", "achieved": round(by / (t * 1e-3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
                                        "frac": round(by / (t * 1e-3) / 1e9 / peaks["hbm"], 4), "bytes_per_step": by / args.steps,
                                        "ms_per_step": round(t / args.steps, 3)}
+    by_all = sum(v[0] for k, v in fam.items() if k.startswith("roi_align_"))
+    t_all = sum(v[1] for k, v in fam.items() if k.startswith("roi_align_"))
+    if t_all:                                               # all four ROIAlign launches of the step together
+        roi["roi_align_fwd_bwd"] = {"bound": "hbm", "achieved": round(by_all / (t_all * 1e-3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                    "frac": round(by_all / (t_all * 1e-3) / 1e9 / peaks["hbm"], 4), "bytes_per_step": by_all / args.steps,
+                                    "ms_per_step": round(t_all / args.steps, 3)}
     roofline["roi_align"] = roi
 
     # ---- end to end through the public API from pinned host buffers ----
