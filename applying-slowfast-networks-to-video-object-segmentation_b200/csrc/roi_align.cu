@@ -343,6 +343,111 @@ __global__ void __launch_bounds__(256, 2) roi_align_fwd2_kernel(const RoiArgs a)
     }
 }
 
+// Tap-list variant of the forward kernel.  ncu showed roi_align_fwd2 ISSUE-bound on the 14 x 14 mask pooling (61 % issue-slot
+// utilisation at 3.7 warps per scheduler, ~330 instructions per bin and 128-channel chunk): every warp re-derived the 16
+// (row, column) products, predicates and 64-bit addresses of a bin and ran all 64 FMAs including the zero-weight ones.  Here
+// one thread per bin first compacts the bin's distinct cells into a list of (cell offset, weight) pairs in shared memory
+// (typically 9 of 16), and the pooling loop is: broadcast-read a pair, one address multiply-add, one 16-byte load, 4 FMAs.
+// Same cells, same weights, same accumulation order as roi_align_fwd2 (bit-identical results).
+constexpr int MAX_TAPS = 16;
+
+template <typename FT, bool NCHW>
+__global__ void __launch_bounds__(256, 2) roi_align_fwd3_kernel(const RoiArgs a) {
+    extern __shared__ float s_dyn[];                      // [NCHW: C * P*P floats] [P*P * 16 (offset, weight) pairs] [P*P counts]
+    __shared__ RoiPlan plan;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long k = blockIdx.x;
+    const int pp = a.P * a.P;
+    float* s_tile = s_dyn;
+    uint2* s_taps = reinterpret_cast<uint2*>(s_dyn + (NCHW ? a.C * pp : 0));
+    int* s_cnt = reinterpret_cast<int*>(s_taps + pp * MAX_TAPS);
+    build_plan(a, k, &plan);
+    __syncthreads();
+    for (int b = threadIdx.x; b < pp; b += blockDim.x) {
+        const int ph = b / a.P, pw = b - ph * a.P;
+        const AxisRec ry = plan.y[ph], rx = plan.x[pw];
+        int n = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (ry.w[r] != 0.f && rx.w[q] != 0.f)
+                    s_taps[b * MAX_TAPS + n++] = make_uint2((unsigned)(ry.off[r] + rx.off[q]), __float_as_uint(ry.w[r] * rx.w[q]));
+        s_cnt[b] = n;
+        for (; n < MAX_TAPS; ++n) s_taps[b * MAX_TAPS + n] = make_uint2(0u, 0u);     // padding: cell 0, weight 0 (value discarded)
+    }
+    __syncthreads();
+    const FT* base = reinterpret_cast<const FT*>(a.feat[plan.lvl]) + (long long)plan.b * plan.H * plan.W * a.cstride;
+    for (int b = warp; b < pp; b += nwarp) {
+        const int n = s_cnt[b];
+        const uint2* tp = s_taps + b * MAX_TAPS;
+        for (int c = lane * 4; c < a.C; c += 128) {
+            // all of the bin's loads in flight before the first FMA.  The first 9 slots (the typical 3 x 3 neighbourhood) are
+            // loaded unconditionally -- a padding slot reads cell 0 and its value is discarded below, so NaNs cannot leak in --
+            // which lets the compiler issue them back to back; slots 9..15 (bins wider than 2 cells) are predicated.
+            float4 v[MAX_TAPS];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) v[t] = ld4(base + (long long)tp[t].x * a.cstride + c);
+#pragma unroll
+            for (int t = 9; t < MAX_TAPS; ++t) {
+                v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < n) v[t] = ld4(base + (long long)tp[t].x * a.cstride + c);
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float w = __uint_as_float(tp[t].y);
+                const float4 x = (t < n) ? v[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
+                acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+            }
+            if (n > 9) {
+#pragma unroll
+                for (int t = 9; t < MAX_TAPS; ++t)
+                    if (t < n) {
+                        const float w = __uint_as_float(tp[t].y);
+                        acc.x = fmaf(w, v[t].x, acc.x); acc.y = fmaf(w, v[t].y, acc.y);
+                        acc.z = fmaf(w, v[t].z, acc.z); acc.w = fmaf(w, v[t].w, acc.w);
+                    }
+            }
+            acc.x *= 0.25f; acc.y *= 0.25f; acc.z *= 0.25f; acc.w *= 0.25f;
+            if (NCHW) {
+                s_tile[(c + 0) * pp + b] = acc.x; s_tile[(c + 1) * pp + b] = acc.y;
+                s_tile[(c + 2) * pp + b] = acc.z; s_tile[(c + 3) * pp + b] = acc.w;
+            } else {
+                const long long o = (k * pp + b) * a.C + c;
+                if (a.out_bf16) {
+                    uint2 u;
+                    u.x = pack_bf16x2(acc.x, acc.y); u.y = pack_bf16x2(acc.z, acc.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = u;
+                } else {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o) = acc;
+                }
+            }
+        }
+    }
+    if (NCHW) {
+        __syncthreads();
+        const long long o = k * a.C * pp;
+        const int n = a.C * pp;
+        if (a.out_bf16 && (n & 7) == 0) {
+            uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o);
+            for (int i = threadIdx.x; i < n / 8; i += blockDim.x) {
+                const float* sv = s_tile + 8 * i;
+                uint4 u;
+                u.x = pack_bf16x2(sv[0], sv[1]); u.y = pack_bf16x2(sv[2], sv[3]);
+                u.z = pack_bf16x2(sv[4], sv[5]); u.w = pack_bf16x2(sv[6], sv[7]);
+                d[i] = u;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                if (a.out_bf16) reinterpret_cast<__nv_bfloat16*>(a.out)[o + i] = __float2bfloat16(s_tile[i]);
+                else reinterpret_cast<float*>(a.out)[o + i] = s_tile[i];
+            }
+        }
+    }
+}
+
 // Backward: one warp per bin (the atomics are fire-and-forget, so what counts is how many warps issue them); the
 // merged taps cut the 16 vector atomics per bin and channel chunk of the reference loop to ~9.
 __global__ void __launch_bounds__(256) roi_align_bwd2_kernel(const RoiArgs a) {
@@ -556,7 +661,22 @@ extern "C" int sfvos_roi_align_fwd(const sfvos_roi_params* p, sfvos_stream strea
     const size_t tile_bytes = a.out_nchw ? (size_t)a.C * a.P * a.P * sizeof(float) : 0;
     const bool fast = a.sr == 2 && a.C % 4 == 0 && a.P <= MAX_P && tile_bytes <= 160 * 1024 && a.K < (1LL << 31) &&
                       getenv("SFVOS_ROI_GENERIC") == nullptr;
-    if (fast) {
+    const char* tl = getenv("SFVOS_ROI_TAPLIST");
+    const size_t list_bytes = (size_t)a.P * a.P * (MAX_TAPS * sizeof(uint2) + sizeof(int));
+    if (fast && (tl == nullptr || atoi(tl) != 0) && tile_bytes + list_bytes <= 200 * 1024) {
+        const size_t smem = tile_bytes + list_bytes;
+#define SF_ROI_FWD3(FT, NCHW)                                                                                          \
+    do {                                                                                                               \
+        SF_CUDA(cudaFuncSetAttribute(roi_align_fwd3_kernel<FT, NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)smem));                                                                      \
+        roi_align_fwd3_kernel<FT, NCHW><<<(int)a.K, 256, smem, st>>>(a);                                               \
+    } while (0)
+        if (a.feat_bf16 && a.out_nchw) SF_ROI_FWD3(__nv_bfloat16, true);
+        else if (a.feat_bf16) SF_ROI_FWD3(__nv_bfloat16, false);
+        else if (a.out_nchw) SF_ROI_FWD3(float, true);
+        else SF_ROI_FWD3(float, false);
+#undef SF_ROI_FWD3
+    } else if (fast) {
 #define SF_ROI_FWD(FT, NCHW)                                                                                           \
     do {                                                                                                               \
         SF_CUDA(cudaFuncSetAttribute(roi_align_fwd2_kernel<FT, NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
