@@ -154,13 +154,13 @@ __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NQ][8], int 
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
-channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long long cstride, float* sum, float* sumsq) {
+channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long long cstride, float* sum, float* sumsq, int ppc) {
     extern __shared__ float red_smem[];
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
     float acc[2][8] = {};
-    const long long p0 = (long long)blockIdx.x * red_ppc(C);
-    long long p1 = p0 + red_ppc(C); if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * ppc;
+    long long p1 = p0 + ppc; if (p1 > npix) p1 = npix;
     if (lp < L)
         for (long long p = p0 + lp; p < p1; p += L) {
             float v[8];
@@ -176,7 +176,7 @@ template <typename DyT>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, int relu, long long npix, int C, float* sums) {
+                     const float* __restrict__ rstd, int relu, long long npix, int C, float* sums, int ppc) {
     extern __shared__ float red_smem[];
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
@@ -186,8 +186,8 @@ bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const flo
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j]; mu[j] = mean[g * 8 + j]; rs[j] = rstd[g * 8 + j]; }
     }
-    const long long p0 = (long long)blockIdx.x * red_ppc(C);
-    long long p1 = p0 + red_ppc(C); if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * ppc;
+    long long p1 = p0 + ppc; if (p1 > npix) p1 = npix;
     if (lp < L)
         for (long long p = p0 + lp; p < p1; p += 2 * L) {
             const long long q = p + L;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, int relu, long long npix, int C,
-                    const float* __restrict__ sums, DxT* dx, long long dx_cstride, float* dgamma, float* dbeta) {
+                    const float* __restrict__ sums, DxT* dx, long long dx_cstride, float* dgamma, float* dbeta, int ppc) {
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
     const float inv_n = 1.0f / (float)npix;
@@ -238,8 +238,8 @@ bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const floa
         k2[j] = k1[j] * sums[c] * inv_n;
         k3[j] = k1[j] * rstd[c] * sums[C + c] * inv_n;
     }
-    const long long p0 = (long long)blockIdx.x * 512;
-    long long p1 = p0 + 512; if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * ppc;
+    long long p1 = p0 + ppc; if (p1 > npix) p1 = npix;
     for (long long p = p0 + lp; p < p1; p += 2 * L) {
         const long long q = p + L;
         const bool two = q < p1;
@@ -267,13 +267,13 @@ bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const floa
 template <typename DyT, typename YT, typename DxT>
 __global__ void __launch_bounds__(RED_THREADS)
 relu_bwd_kernel(const DyT* __restrict__ dy, long long dy_cstride, const YT* __restrict__ y, long long y_cstride, DxT* dx,
-                long long dx_cstride, float* dbias, long long npix, int C) {
+                long long dx_cstride, float* dbias, long long npix, int C, int ppc) {
     extern __shared__ float red_smem[];
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
     float acc[1][8] = {};
-    const long long p0 = (long long)blockIdx.x * red_ppc(C);
-    long long p1 = p0 + red_ppc(C); if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * ppc;
+    long long p1 = p0 + ppc; if (p1 > npix) p1 = npix;
     if (lp < L)
         for (long long p = p0 + lp; p < p1; p += L) {
             float d[8], v[8];
@@ -292,15 +292,15 @@ relu_bwd_kernel(const DyT* __restrict__ dy, long long dy_cstride, const YT* __re
 template <typename XT, typename YT>
 __global__ void __launch_bounds__(RED_THREADS)
 affine_act_kernel(const XT* __restrict__ x, long long x_cstride, YT* y, long long y_cstride, const float* __restrict__ scale,
-                  const float* __restrict__ shift, int relu, long long npix, int C) {
+                  const float* __restrict__ shift, int relu, long long npix, int C, int ppc) {
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
     if (lp >= L) return;
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j]; }
-    const long long p0 = (long long)blockIdx.x * 512;
-    long long p1 = p0 + 512; if (p1 > npix) p1 = npix;
+    const long long p0 = (long long)blockIdx.x * ppc;
+    long long p1 = p0 + ppc; if (p1 > npix) p1 = npix;
     for (long long p = p0 + lp; p < p1; p += 2 * L) {
         const long long q = p + L;
         const bool two = q < p1;
@@ -505,6 +505,16 @@ extern "C" int sfvos_unpack_wgrad(const float* dw, float* grad, int32_t mode, in
     return SFVOS_OK;
 }
 
+// Pixels per CTA.  A thread walks its CTA's pixels L = 256 / (C/8) at a time, i.e. ppc / L dependent load round trips: fine
+// when thousands of CTAs hide each other's latency, but a small pyramid level (grid < #SMs) exposed the whole chain --
+// ncu: ~32 us for EVERY 192-channel launch of levels 2..4 whatever its size.  Shrink the chunk until the grid covers the
+// machine a few times over (floor: 32 pixels).
+static inline int pick_ppc(long long npix, int base) {
+    int ppc = base;
+    const long long want = 6LL * sfvos_num_sms();
+    while (ppc > 32 && (npix + ppc - 1) / ppc < want) ppc >>= 1;
+    return ppc;
+}
 static inline size_t red_smem_bytes(int nq, int C) { return (size_t)nq * (RED_THREADS / (C / 8)) * C * sizeof(float); }
 
 extern "C" int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride, float* sum, float* sumsq,
@@ -512,8 +522,9 @@ extern "C" int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int6
     CHECK_C8(C);
     SF_CHECK(cstride % 4 == 0, "channel_stats: cstride must be a multiple of 4");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + red_ppc((int)C) - 1) / red_ppc((int)C));
-    channel_stats_kernel<<<grid, RED_THREADS, red_smem_bytes(2, (int)C), CS(stream)>>>(x, npix, (int)C, cstride, sum, sumsq);
+    const int ppc = pick_ppc(npix, red_ppc((int)C));
+    const int grid = (int)((npix + ppc - 1) / ppc);
+    channel_stats_kernel<<<grid, RED_THREADS, red_smem_bytes(2, (int)C), CS(stream)>>>(x, npix, (int)C, cstride, sum, sumsq, ppc);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -543,9 +554,10 @@ extern "C" int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstrid
     CHECK_C8(C);
     SF_CHECK(x_cstride % 8 == 0 && y_cstride % 8 == 0, "affine_act: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + 511) / 512);
+    const int ppc = pick_ppc(npix, 512);
+    const int grid = (int)((npix + ppc - 1) / ppc);
     using bf = __nv_bfloat16;
-#define LAUNCH(XT, YT) affine_act_kernel<XT, YT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const XT*>(x), x_cstride, reinterpret_cast<YT*>(y), y_cstride, scale, shift, relu, npix, (int)C)
+#define LAUNCH(XT, YT) affine_act_kernel<XT, YT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const XT*>(x), x_cstride, reinterpret_cast<YT*>(y), y_cstride, scale, shift, relu, npix, (int)C, ppc)
     if (x_dtype == SFVOS_F32 && y_dtype == SFVOS_F32) LAUNCH(float, float);
     else if (x_dtype == SFVOS_F32) LAUNCH(float, bf);
     else if (y_dtype == SFVOS_F32) LAUNCH(bf, float);
@@ -561,12 +573,13 @@ extern "C" int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_
     CHECK_C8(C);
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0, "bn_bwd_reduce: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + red_ppc((int)C) - 1) / red_ppc((int)C));
+    const int ppc = pick_ppc(npix, red_ppc((int)C));
+    const int grid = (int)((npix + ppc - 1) / ppc);
     const size_t sm = red_smem_bytes(2, (int)C);
     if (dy_dtype == SFVOS_F32)
-        bn_bwd_reduce_kernel<float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums);
+        bn_bwd_reduce_kernel<float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, ppc);
     else
-        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums);
+        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, ppc);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -579,9 +592,10 @@ extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_c
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0 && dx_cstride % 8 == 0, "bn_bwd_apply: strides must be multiples of 8");
     SF_CHECK((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply: dgamma and dbeta go together");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + 511) / 512);
+    const int ppc = pick_ppc(npix, 512);
+    const int grid = (int)((npix + ppc - 1) / ppc);
     using bf = __nv_bfloat16;
-#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta)
+#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta, ppc)
     if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float);
     else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf);
     else if (dx_dtype == SFVOS_F32) LAUNCH(bf, float);
@@ -597,10 +611,11 @@ extern "C" int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstri
     CHECK_C8(C);
     SF_CHECK(dy_cstride % 8 == 0 && y_cstride % 8 == 0 && dx_cstride % 8 == 0, "relu_bwd: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int grid = (int)((npix + red_ppc((int)C) - 1) / red_ppc((int)C));
+    const int ppc = pick_ppc(npix, red_ppc((int)C));
+    const int grid = (int)((npix + ppc - 1) / ppc);
     const size_t sm = red_smem_bytes(1, (int)C);
     using bf = __nv_bfloat16;
-#define LAUNCH(DT, YT, XT) relu_bwd_kernel<DT, YT, XT><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, reinterpret_cast<const YT*>(y), y_cstride, reinterpret_cast<XT*>(dx), dx_cstride, dbias, npix, (int)C)
+#define LAUNCH(DT, YT, XT) relu_bwd_kernel<DT, YT, XT><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, reinterpret_cast<const YT*>(y), y_cstride, reinterpret_cast<XT*>(dx), dx_cstride, dbias, npix, (int)C, ppc)
     if (dy_dtype == SFVOS_F32 && y_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float, float);
     else if (dy_dtype == SFVOS_F32 && y_dtype == SFVOS_BF16 && dx_dtype == SFVOS_BF16) LAUNCH(float, bf, bf);
     else if (dy_dtype == SFVOS_BF16 && y_dtype == SFVOS_BF16 && dx_dtype == SFVOS_BF16) LAUNCH(bf, bf, bf);
