@@ -38,6 +38,15 @@ class RoiParams(ctypes.Structure):
                 ("out", vp), ("out_dtype", i32), ("out_nchw", i32)]
 
 
+BN_MAX_CALLS = 8
+
+
+class BnRunningParams(ctypes.Structure):
+    _fields_ = [("sum", vp * BN_MAX_CALLS), ("sumsq", vp * BN_MAX_CALLS), ("count", f64 * BN_MAX_CALLS),
+                ("n_calls", i32), ("reserved", i32), ("conv_bias", vp), ("running_mean", vp), ("running_var", vp),
+                ("num_batches_tracked", vp), ("momentum", f64), ("C", i64)]
+
+
 _SIGS = {
     "sfvos_version": [],
     "sfvos_device_check": [],
@@ -49,6 +58,7 @@ _SIGS = {
     "sfvos_unpack_wgrad": [vp, vp, i32, i64, i64, i64, i64, i64, i64, i64, vp],
     "sfvos_channel_stats": [vp, i64, i64, i64, vp, vp, vp],
     "sfvos_bn_finalize": [vp, vp, f64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp, vp, i64, vp],
+    "sfvos_bn_running_update": [ctypes.POINTER(BnRunningParams), vp],
     "sfvos_bn_fold_eval": [vp, vp, vp, vp, vp, f64, vp, vp, i64, vp],
     "sfvos_affine_act": [vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, i64, vp],
     "sfvos_bn_bwd_reduce": [vp, i32, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, vp, vp],

@@ -227,7 +227,10 @@ bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const floa
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
     const float inv_n = 1.0f / (float)npix;
     if (blockIdx.x == 0 && dgamma != nullptr)
-        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] += sums[c]; dgamma[c] += sums[C + c]; }
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {     // atomics: pyramid levels on different streams share these accumulators
+            atomicAdd(dbeta + c, sums[c]);
+            atomicAdd(dgamma + c, sums[C + c]);
+        }
     if (lp >= L) return;
     float sc[8], sh[8], mu[8], k1[8], k2[8], k3[8];
 #pragma unroll
@@ -340,6 +343,29 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, double 
         running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mb);
         running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
     }
+}
+
+// Running-statistics update of ONE BatchNorm for several consecutive forward calls (the pyramid levels of one
+// temporally_enhance_features call), applied in call order: exactly the sequence of exponential-moving-average steps that
+// bn_finalize performs when the calls run one after another, but issued once after the levels - which run concurrently on
+// their own streams - have joined.
+__global__ void bn_running_update_kernel(const sfvos_bn_running_params p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && p.num_batches_tracked != nullptr) *reinterpret_cast<long long*>(p.num_batches_tracked) += p.n_calls;
+    if (c >= p.C) return;
+    float rm = p.running_mean[c], rv = p.running_var[c];
+    for (int i = 0; i < p.n_calls; ++i) {
+        const double count = p.count[i];
+        const double m = (double)p.sum[i][c] / count;
+        double var = (double)p.sumsq[i][c] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        const double mb = m + (p.conv_bias ? (double)p.conv_bias[c] : 0.0);
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        rm = (float)((1.0 - p.momentum) * (double)rm + p.momentum * mb);
+        rv = (float)((1.0 - p.momentum) * (double)rv + p.momentum * unbiased);
+    }
+    p.running_mean[c] = rm;
+    p.running_var[c] = rv;
 }
 
 __global__ void bn_fold_eval_kernel(const float* conv_bias, const float* gamma, const float* beta, const float* rm,
@@ -536,6 +562,15 @@ extern "C" int sfvos_bn_finalize(const float* sum, const float* sumsq, double co
     SF_CHECK(count > 0, "bn_finalize: empty batch");
     bn_finalize_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(sum, sumsq, count, conv_bias, gamma, beta,
         running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, mean, rstd, (int)C);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_bn_running_update(const sfvos_bn_running_params* p, sfvos_stream stream) {
+    SF_CHECK(p != nullptr && p->n_calls >= 1 && p->n_calls <= SFVOS_BN_MAX_CALLS, "bn_running_update: 1..%d calls", SFVOS_BN_MAX_CALLS);
+    SF_CHECK(p->running_mean != nullptr && p->running_var != nullptr, "bn_running_update: running buffers required");
+    for (int i = 0; i < p->n_calls; ++i) SF_CHECK(p->count[i] > 0 && p->sum[i] && p->sumsq[i], "bn_running_update: empty call %d", i);
+    bn_running_update_kernel<<<(int)((p->C + 127) / 128), 128, 0, CS(stream)>>>(*p);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

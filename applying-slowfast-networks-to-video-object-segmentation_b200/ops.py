@@ -178,6 +178,22 @@ def bn_finalize(stats, count, conv_bias, gamma, beta, running_mean, running_var,
          _p(out4), _p(out4, C * 4), _p(out4, 2 * C * 4), _p(out4, 3 * C * 4), C, stream())
 
 
+def bn_running_update(calls, conv_bias, running_mean, running_var, nbt, momentum):
+    """calls: list of (stats f32 [2C] = (sum, sumsq), count) in forward-call order (see sfvos_bn_running_update)."""
+    C = running_mean.numel()
+    for i in range(0, len(calls), _lib.BN_MAX_CALLS):
+        part = calls[i:i + _lib.BN_MAX_CALLS]
+        p = _lib.BnRunningParams()
+        for j, (stats, count) in enumerate(part):
+            p.sum[j] = stats.data_ptr()
+            p.sumsq[j] = stats.data_ptr() + C * 4
+            p.count[j] = float(count)
+        p.n_calls = len(part)
+        p.conv_bias = _p(conv_bias); p.running_mean = _p(running_mean); p.running_var = _p(running_var)
+        p.num_batches_tracked = _p(nbt); p.momentum = float(momentum); p.C = C
+        call("sfvos_bn_running_update", ctypes.byref(p), stream())
+
+
 def bn_fold_eval(conv_bias, gamma, beta, running_mean, running_var, eps, out2):
     C = gamma.numel()
     call("sfvos_bn_fold_eval", _p(conv_bias), _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps),

@@ -296,6 +296,7 @@ class _Scratch:
     def __init__(self, n, device):
         self.buf = torch.zeros(n, dtype=torch.float32, device=device)
         self.off = 0
+        self.deferred = None         # see _conv_bn_forward
 
     def take(self, n):
         v = self.buf[self.off:self.off + n]
@@ -304,12 +305,24 @@ class _Scratch:
         return v
 
 
+def _apply_deferred_running_stats(mod, deferred):
+    """deferred: {layer: [(stats, count) per level, in LEVEL order]} -> one EMA kernel per layer (level order preserved)."""
+    for name, calls in deferred.items():
+        spec = mod._specs[name]
+        conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
+        ops.bn_running_update(calls, conv.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                              BN_MOMENTUM if bn.momentum is None else bn.momentum)
+
+
 def _fwd_scratch_size(mod, n_levels):
     return n_levels * sum(6 * s.cout + 8 for s in mod._specs.values())
 
 
 def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
-    """conv -> BN (-> ReLU) of one layer, writing into ``out`` (an Act, possibly a channel slice)."""
+    """conv -> BN (-> ReLU) of one layer, writing into ``out`` (an Act, possibly a channel slice).
+    If ``scratch.deferred`` is a dict, the running-statistics update is NOT done here: (stats, count) is appended to
+    ``scratch.deferred[layer]`` and the caller applies the updates of all pyramid levels in level order after they joined
+    (``_apply_deferred_running_stats``) - the levels run concurrently, the EMA is order-dependent."""
     conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
     umma = mod._umma
     wp, cp = mod._packed(spec.conv, 0)
@@ -326,6 +339,10 @@ def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
             ops.channel_stats(raw, stats)
         bn4 = scratch.take(4 * spec.cout) if scratch is not None else torch.empty(4 * spec.cout, dtype=torch.float32, device=dev)
         track = bn.track_running_stats and bn.running_mean is not None
+        deferred = getattr(scratch, "deferred", None) if scratch is not None else None
+        if track and deferred is not None:
+            deferred.setdefault(spec.conv, []).append((stats, raw.npix))
+            track = False
         ops.bn_finalize(stats, raw.npix, conv.bias, bn.weight, bn.bias, bn.running_mean if track else None,
                         bn.running_var if track else None, bn.num_batches_tracked if track else None,
                         BN_MOMENTUM if bn.momentum is None else bn.momentum, bn.eps, bn4)
@@ -339,34 +356,57 @@ def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
                  shift=fold[spec.cout:])
 
 
-def _level_forward(mod, slow_in, fast_in, training, saved, scratch=None):
+def _level_forward(mod, slow_in, fast_in, training, saved, scratch=None, fast_stream=None):
     """One pyramid level (model.py:118-149 + the concat of :162).  Returns the merged f32 Act [B,T3,H,W,256]: T3 = 1 for
     the reference's windows (sp / fp frames in); in sequence mode (temporally_enhance_sequence) the inputs are whole
-    zero-padded sequences and T3 = the number of frames."""
+    zero-padded sequences and T3 = the number of frames.
+
+    ``fast_stream``: run the fast pathway (and the lateral convolutions it feeds into the slow buffers) on that CUDA stream,
+    concurrently with the slow pathway on the current one.  The two only meet at the fuse points - slow_conv{2,3} read the
+    lateral channels - so the current stream waits for the fast one there; the fast stream never waits.  The HBM-bound
+    BatchNorm passes of one pathway then run under the tensor-bound convolutions of the other."""
     sp = mod._specs
     dt_act = mod._act_dtype
     dev = fast_in.buf.device
     B, H, W = fast_in.B, fast_in.H, fast_in.W
     t1s, t1f = slow_in.T - sp["slow_conv1"].kt + 1, fast_in.T - sp["fast_conv1"].kt + 1
     t2s, t2f = t1s - sp["slow_conv2"].kt + 1, t1f - sp["fast_conv2"].kt + 1
-    # layer 1 (+ lateral 1 straight into channels 192..255 of the slow buffer)
-    f1 = Act.empty(B, t1f, H, W, 32, dt_act, dev)
-    s1 = Act.empty(B, t1s, H, W, 256, dt_act, dev)
-    _conv_bn_forward(mod, sp["slow_conv1"], slow_in, s1.slice(0, 192), training, saved, scratch)
-    _conv_bn_forward(mod, sp["fast_conv1"], fast_in, f1, training, saved, scratch)
-    _conv_bn_forward(mod, sp["conv_f2s1"], f1, s1.slice(192, 64), training, saved, scratch)
-    # layer 2
-    f2 = Act.empty(B, t2f, H, W, 32, dt_act, dev)
-    s2 = Act.empty(B, t2s, H, W, 256, dt_act, dev)
-    _conv_bn_forward(mod, sp["slow_conv2"], s1, s2.slice(0, 192), training, saved, scratch)
-    _conv_bn_forward(mod, sp["fast_conv2"], f1, f2, training, saved, scratch)
-    _conv_bn_forward(mod, sp["conv_f2s2"], f2, s2.slice(192, 64), training, saved, scratch)
-    # layer 3: both pathways land in one f32 [B,T3,H,W,256] buffer = cat([slow, fast], 1).squeeze(2) when T3 = 1
     t3 = t2s - sp["slow_conv3"].kt + 1
     assert t3 >= 1 and t3 == t2f - sp["fast_conv3"].kt + 1, "slow / fast temporal extents do not meet after layer 3"
-    out = Act.empty(B, t3, H, W, 256, torch.float32, dev)
+    # every buffer both pathways write is allocated BEFORE the fork (the caching allocator orders reuse per stream)
+    s1 = Act.empty(B, t1s, H, W, 256, dt_act, dev)
+    s2 = Act.empty(B, t2s, H, W, 256, dt_act, dev)
+    out = Act.empty(B, t3, H, W, 256, torch.float32, dev)     # = cat([slow, fast], 1).squeeze(2) when T3 = 1
+    main = torch.cuda.current_stream(dev) if fast_stream is not None else None
+
+    def fast(fn):
+        if fast_stream is None:
+            return fn()
+        with torch.cuda.stream(fast_stream):
+            return fn()
+
+    def join():
+        if fast_stream is not None:
+            main.wait_stream(fast_stream)
+
+    if fast_stream is not None:
+        fast_stream.wait_stream(main)                          # inputs (layout conversion) are ready
+    f1 = fast(lambda: Act.empty(B, t1f, H, W, 32, dt_act, dev))
+    f2 = fast(lambda: Act.empty(B, t2f, H, W, 32, dt_act, dev))
+    # layer 1 (+ lateral 1 straight into channels 192..255 of the slow buffer)
+    fast(lambda: (_conv_bn_forward(mod, sp["fast_conv1"], fast_in, f1, training, saved, scratch),
+                  _conv_bn_forward(mod, sp["conv_f2s1"], f1, s1.slice(192, 64), training, saved, scratch)))
+    _conv_bn_forward(mod, sp["slow_conv1"], slow_in, s1.slice(0, 192), training, saved, scratch)
+    join()
+    # layer 2
+    fast(lambda: (_conv_bn_forward(mod, sp["fast_conv2"], f1, f2, training, saved, scratch),
+                  _conv_bn_forward(mod, sp["conv_f2s2"], f2, s2.slice(192, 64), training, saved, scratch)))
+    _conv_bn_forward(mod, sp["slow_conv2"], s1, s2.slice(0, 192), training, saved, scratch)
+    join()
+    # layer 3: both pathways land in one f32 [B,T3,H,W,256] buffer
+    fast(lambda: _conv_bn_forward(mod, sp["fast_conv3"], f2, out.slice(224, 32), training, saved, scratch))
     _conv_bn_forward(mod, sp["slow_conv3"], s2, out.slice(0, 224), training, saved, scratch)
-    _conv_bn_forward(mod, sp["fast_conv3"], f2, out.slice(224, 32), training, saved, scratch)
+    join()
     if saved is not None:
         saved["_acts"] = dict(slow_in=slow_in, fast_in=fast_in, f1=f1, s1=s1, f2=f2, s2=s2)
     return out
@@ -426,22 +466,40 @@ def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=Fal
     return dx
 
 
-def _level_backward(mod, saved, g_out, need_input_grad, bank):
+def _level_backward(mod, saved, g_out, need_input_grad, bank, fast_stream=None):
     """g_out: f32 Act [B,1,H,W,256] = gradient of the merged output; parameter gradients accumulate into ``bank``.
-    Returns (d_slow, d_fast)."""
+    Returns (d_slow, d_fast).  ``fast_stream``: the fast pathway's (and the laterals') backward on that stream, mirroring
+    _level_forward: it waits for the slow pathway only where a lateral needs the slow gradient (d_s2 / d_s1)."""
     sp = mod._specs
     a = saved["_acts"]
+    dev = g_out.buf.device
+    main = torch.cuda.current_stream(dev) if fast_stream is not None else None
+
+    def fast(fn):
+        if fast_stream is None:
+            return fn()
+        with torch.cuda.stream(fast_stream):
+            return fn()
+
     # the slow pathway's data gradients are consumed once, by the BN-backward passes of the layer below, which round
     # to the activation dtype anyway: store them in it (bf16 on the product path) -- half the bytes of three passes
     gdt = mod._act_dtype if os.environ.get("SFVOS_BF16_DGRAD", "1") != "0" else torch.float32
+    if fast_stream is not None:
+        fast_stream.wait_stream(main)                          # g_out is ready
+    d_f2 = fast(lambda: _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, bank))
     d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, bank, dx_dtype=gdt)
-    d_f2 = _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, bank)
-    _layer_backward(mod, sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], saved, bank, dx=d_f2, dx_accumulate=True)
+    if fast_stream is not None:
+        fast_stream.wait_stream(main)                          # lateral 2 reads d_s2[192:]
+    d_f1 = fast(lambda: (_layer_backward(mod, sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], saved, bank, dx=d_f2, dx_accumulate=True),
+                         _layer_backward(mod, sp["fast_conv2"], d_f2, a["f1"], saved, bank))[1])
     d_s1 = _layer_backward(mod, sp["slow_conv2"], d_s2.slice(0, 192), a["s1"], saved, bank, dx_dtype=gdt)
-    d_f1 = _layer_backward(mod, sp["fast_conv2"], d_f2, a["f1"], saved, bank)
-    _layer_backward(mod, sp["conv_f2s1"], d_s1.slice(192, 64), a["f1"], saved, bank, dx=d_f1, dx_accumulate=True)
+    if fast_stream is not None:
+        fast_stream.wait_stream(main)                          # lateral 1 reads d_s1[192:]
+    d_fast = fast(lambda: (_layer_backward(mod, sp["conv_f2s1"], d_s1.slice(192, 64), a["f1"], saved, bank, dx=d_f1, dx_accumulate=True),
+                           _layer_backward(mod, sp["fast_conv1"], d_f1, a["fast_in"], saved, bank, need_dx=need_input_grad))[1])
     d_slow = _layer_backward(mod, sp["slow_conv1"], d_s1.slice(0, 192), a["slow_in"], saved, bank, need_dx=need_input_grad)
-    d_fast = _layer_backward(mod, sp["fast_conv1"], d_f1, a["fast_in"], saved, bank, need_dx=need_input_grad)
+    if fast_stream is not None:
+        main.wait_stream(fast_stream)
     return d_slow, d_fast
 
 
@@ -536,6 +594,18 @@ def _level_streams(dev, shapes):
     return out
 
 
+def _pathway_stream(dev):
+    """Side stream for the fast pathway of the level that runs on the current stream.  Opt-in (SFVOS_PATH_STREAMS=1): measured
+    on the bench step it does not pay (21.3-21.4 ms without, 21.6-21.7 ms with, same box) - both pathways' kernels are
+    persistent, whole-GPU launches, and the chip is at its power cap - unlike the level streams above."""
+    if os.environ.get("SFVOS_PATH_STREAMS", "0") != "1":
+        return None
+    key = "path:" + str(dev)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 class _on_stream:
     """``with _on_stream(side, main)``: fork ``side`` from ``main`` and make it current (no-op for side = None)."""
 
@@ -572,15 +642,28 @@ class _SlowFastPyramidFn(torch.autograd.Function):
         n_lv = len(fast_lists)
         outs, saved_all = [None] * n_lv, [None] * n_lv
         # small levels are enqueued FIRST (their streams fork from here), the large ones follow on the current stream
+        concurrent = any(st is not None for st in streams)
+        per_level = [dict() for _ in range(n_lv)]
         for i in sorted(range(n_lv), key=lambda j: (streams[j] is None, j)):
             with _on_stream(streams[i], main):
+                if scratch is not None:
+                    scratch.deferred = per_level[i] if concurrent else None
                 fast_in, slow_in = _lists_to_acts(slow_lists[i], fast_lists[i], dt_act)
                 saved = {} if want_grad else None
-                outs[i] = _level_forward(mod, slow_in, fast_in, training, saved, scratch).as_nchw()
+                outs[i] = _level_forward(mod, slow_in, fast_in, training, saved, scratch,
+                                         fast_stream=_pathway_stream(dev) if streams[i] is None and any(st is not None for st in streams) else None).as_nchw()
                 saved_all[i] = saved
         for st in streams:
             if st is not None:
                 main.wait_stream(st)
+        if scratch is not None and concurrent:
+            scratch.deferred = None
+            merged = OrderedDict()
+            for name in mod._specs:                          # level order inside every layer = the reference's call order
+                calls = [c for lv in per_level for c in lv.get(name, [])]
+                if calls:
+                    merged[name] = calls
+            _apply_deferred_running_stats(mod, merged)
         ctx.mod, ctx.saved_all, ctx.streams = mod, (saved_all if want_grad else None), streams
         if not want_grad:
             ctx.mark_non_differentiable(*outs)
@@ -597,7 +680,8 @@ class _SlowFastPyramidFn(torch.autograd.Function):
         main = torch.cuda.current_stream(dev)
         for i in reversed(live):
             with _on_stream(ctx.streams[i], main):
-                _level_backward(mod, saved_all[i], _grad_to_act(gs[i]), False, bank)
+                _level_backward(mod, saved_all[i], _grad_to_act(gs[i]), False, bank,
+                                fast_stream=_pathway_stream(dev) if ctx.streams[i] is None and any(st is not None for st in ctx.streams) else None)
             saved_all[i] = None
         for i in live:
             if ctx.streams[i] is not None:

@@ -134,6 +134,24 @@ int sfvos_bn_finalize(const float* sum, const float* sumsq, double count, const 
                       const float* gamma, const float* beta, float* running_mean, float* running_var,
                       int64_t* num_batches_tracked, double momentum, double eps, float* scale, float* shift,
                       float* mean, float* rstd, int64_t C, sfvos_stream stream);
+/* Running-statistics update of ONE BatchNorm for n_calls consecutive train-mode forward calls (the pyramid levels of one
+ * temporally_enhance_features call, code/helpers/model.py:155-162), applied in call order: the same sequence of EMA steps
+ * as n_calls sfvos_bn_finalize calls with running buffers.  Lets the calls themselves run concurrently (finalize with NULL
+ * running buffers) and keeps the buffers bit-identical to the sequential order.  num_batches_tracked += n_calls. */
+#define SFVOS_BN_MAX_CALLS 8
+typedef struct sfvos_bn_running_params {
+    const float* sum[SFVOS_BN_MAX_CALLS];      /* per call: [C] sums of the bias-free conv output */
+    const float* sumsq[SFVOS_BN_MAX_CALLS];
+    double count[SFVOS_BN_MAX_CALLS];          /* per call: elements per channel */
+    int32_t n_calls, reserved;
+    const float* conv_bias;                    /* may be NULL */
+    float* running_mean;
+    float* running_var;
+    int64_t* num_batches_tracked;              /* may be NULL */
+    double momentum;
+    int64_t C;
+} sfvos_bn_running_params;
+int sfvos_bn_running_update(const sfvos_bn_running_params* p, sfvos_stream stream);
 /* eval: scale=gamma/sqrt(rv+eps), shift=beta+(conv_bias-rm)*scale. */
 int sfvos_bn_fold_eval(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, double eps, float* scale, float* shift, int64_t C,

@@ -177,3 +177,65 @@ def test_state_dict_roundtrip_and_no_cpu_fallback():
     x = torch.randn(1, 256, 8, 4, 6)
     with pytest.raises(RuntimeError):
         cpu(x[:, :, 4:5], x)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_concurrent_levels_and_pathways_match_single_stream_and_oracle(precision, monkeypatch):
+    """With >= 3 pyramid levels the smaller levels run on side streams and the fast pathway of the largest one on its own
+    stream (slowfast._level_streams / _pathway_stream).  Two consecutive training steps must leave the same outputs, parameter
+    gradients and BatchNorm running statistics (to reduction-order noise) as the single-stream order (the running-stat EMA is
+    order-dependent: it is applied in level order after the join), and match the CPU oracle."""
+    levels = OrderedDict([("0", (24, 40)), ("1", (12, 20)), ("2", (8, 12)), ("3", (6, 10)), ("pool", (4, 6))])
+    sp, fp = 1, 8
+    slow, fast = _inputs(sp, fp, levels)
+    slow_c, fast_c = _to_cuda(slow), _to_cuda(fast)
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SFVOS_LEVEL_STREAMS", mode)
+        monkeypatch.setenv("SFVOS_PATH_STREAMS", mode)
+        m = _module(sp, fp, precision).train()
+        for _ in range(2):                                   # two steps: the second EMA step sees the first one's buffers
+            for p in m.parameters():
+                p.grad = None
+            out = m.temporally_enhance_features(slow_c, fast_c)
+            so.module_loss(out).backward()
+        torch.cuda.synchronize()
+        results[mode] = (OrderedDict((k, v.detach().clone()) for k, v in out.items()),
+                         OrderedDict((n, p.grad.detach().clone()) for n, p in m.named_parameters()),
+                         OrderedDict((n, b.detach().clone()) for n, b in m.named_buffers()))
+    (o0, g0, b0), (o1, g1, b1) = results["0"], results["1"]
+    # (not bit-equal even on one stream: the BatchNorm statistics are reduced with atomics)
+    # fp32 pins the ordering tightly; in bf16 a last-bit difference of a statistic moves individual activations by a bf16 ulp.
+    # Gradients are compared in relative L2 in both precisions: the statistics are reduced with atomics, and a last-bit
+    # difference can flip the mask of a ReLU whose pre-activation sits at ~0, which moves single gradient entries by
+    # percents of the max (measured: 3.5e-3 max-normalised on slow_conv2.weight between two single-stream fp32 runs).
+    otol, btol, gtol = (1e-5, 1e-6, 1e-2) if precision == "fp32" else (1e-2, 2e-3, 0.1)
+    for k in o0:
+        assert _nerr(o1[k], o0[k]) <= otol, (k, _nerr(o1[k], o0[k]))
+    for n in b0:
+        # an EMA applied in the wrong level order (or a lost update) would show at ~momentum * |mean_i - mean_j| ~ 1e-2
+        assert (b1[n].double() - b0[n].double()).abs().max().item() <= btol * (1.0 + b0[n].double().abs().max().item()), n
+    for n in g0:
+        if n.endswith(".weight"):
+            ref = g0[n].float()
+            assert (g1[n].float() - ref).norm().item() <= gtol * ref.norm().item() + 1e-9, n
+    # and against the oracle (one step, fresh state)
+    monkeypatch.setenv("SFVOS_LEVEL_STREAMS", "1")
+    monkeypatch.setenv("SFVOS_PATH_STREAMS", "1")
+    sd = so.init_state_dict(sp, fp, seed=63)
+    ref_out, ref_loss, ref_grads, ref_sd = so.grads_of(sd, slow, fast)
+    m = _module(sp, fp, precision).train()
+    out = m.temporally_enhance_features(slow_c, fast_c)
+    so.module_loss(out).backward()
+    for k in out:
+        assert _nerr(out[k], ref_out[k]) <= TOL[precision], k
+    for n, p in m.named_parameters():
+        if n.endswith(".weight"):
+            ref = ref_grads[n].float()
+            rel = (p.grad.detach().float().cpu() - ref).norm().item() / (ref.norm().item() + 1e-20)
+            assert rel <= (1e-2 if precision == "fp32" else 0.2), (n, rel)
+    for n, b in m.named_buffers():
+        if "running" in n:
+            assert _nerr(b, ref_sd[n]) <= (1e-4 if precision == "fp32" else 1e-2), n
+        elif n.endswith("num_batches_tracked"):
+            assert int(b) == 5, (n, int(b))                  # one increment per pyramid level, like the reference
