@@ -210,26 +210,37 @@ class SlowFastLayers(nn.Module):
         assert n >= 1 and 0 <= hl <= lo and 0 <= hr <= hi, "halo must leave >= 1 frame and fit inside one window"
         chunk = n if not max_frames else max(1, int(max_frames))
         outs = OrderedDict((k, []) for k in keys)
+        main = torch.cuda.current_stream(dev)
+        streams = _level_streams(dev, [tuple(frame_features[k].shape[-2:]) for k in keys])   # smaller levels on side streams
+        order = sorted(range(len(keys)), key=lambda j: (streams[j] is None, j))
         for c0 in range(0, n, chunk):
             c1 = min(n, c0 + chunk)
+            chunk_outs = {}
+            for ki in order:
+                key = keys[ki]
+                with _on_stream(streams[ki], main):
+                    x = frame_features[key]
+                    _, c, h, w = x.shape
+                    t_in = (c1 - c0) + fp - 1                    # padded frames [c0 - lo, c1 + hi) of the output numbering
+                    fast_in = Act.empty(1, t_in, h, w, c, self._act_dtype, dev)
+                    f0, f1 = max(-hl, c0 - lo), min(n + hr, c1 + hi)   # given frames inside the padded range
+                    per = h * w * c
+                    left, right = f0 - (c0 - lo), (c1 + hi) - f1
+                    if left:
+                        fast_in.buf[:left * per].zero_()
+                    if right:
+                        fast_in.buf[(t_in - right) * per:].zero_()
+                    src = x[f0 + hl:f1 + hl].to(dev)
+                    if src.dtype != torch.float32 or not src.is_contiguous():
+                        src = src.float().contiguous()
+                    ops.nchw_to_nhwc(src, fast_in, frame_off=left)
+                    slow_in = fast_in.frames(s_off, s_off + (c1 - c0) + sp - 1)
+                    chunk_outs[key] = _level_forward(self, slow_in, fast_in, False, None).as_nchw()
+            for st in streams:
+                if st is not None:
+                    main.wait_stream(st)
             for key in keys:
-                x = frame_features[key]
-                _, c, h, w = x.shape
-                t_in = (c1 - c0) + fp - 1                    # padded frames [c0 - lo, c1 + hi) of the output numbering
-                fast_in = Act.empty(1, t_in, h, w, c, self._act_dtype, dev)
-                f0, f1 = max(-hl, c0 - lo), min(n + hr, c1 + hi)   # given frames inside the padded range
-                per = h * w * c
-                left, right = f0 - (c0 - lo), (c1 + hi) - f1
-                if left:
-                    fast_in.buf[:left * per].zero_()
-                if right:
-                    fast_in.buf[(t_in - right) * per:].zero_()
-                src = x[f0 + hl:f1 + hl].to(dev)
-                if src.dtype != torch.float32 or not src.is_contiguous():
-                    src = src.float().contiguous()
-                ops.nchw_to_nhwc(src, fast_in, frame_off=left)
-                slow_in = fast_in.frames(s_off, s_off + (c1 - c0) + sp - 1)
-                outs[key].append(_level_forward(self, slow_in, fast_in, False, None).as_nchw())
+                outs[key].append(chunk_outs[key])
         return OrderedDict((k, v[0] if len(v) == 1 else torch.cat(v)) for k, v in outs.items())
 
 
