@@ -219,11 +219,21 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(3, args.warmup)):
         one_step(feats)
     # ---- eager pass: K steps with CUDA events around every tensor-core / ROIAlign launch (per-kernel rooflines) ----
+    # (single stream for this pass: with the pyramid levels on concurrent streams an event pair around a small level's launch
+    # brackets the time it waits for SMs behind level 0's persistent kernels, not the kernel.  The timed region below runs the
+    # levels concurrently.)
+    prev_streams = os.environ.get("SFVOS_LEVEL_STREAMS")
+    os.environ["SFVOS_LEVEL_STREAMS"] = "0"
+    one_step(feats)
     ops.TIMING = []
     l0 = ops.launches()
     ms_eager = timed(lambda: one_step(feats), args.steps)
     launches = ops.launches() - l0
     timing, ops.TIMING = ops.TIMING, None
+    if prev_streams is None:
+        os.environ.pop("SFVOS_LEVEL_STREAMS")
+    else:
+        os.environ["SFVOS_LEVEL_STREAMS"] = prev_streams
     step_peak = torch.cuda.max_memory_allocated(dev)           # features + one eager step
     torch.cuda.empty_cache()                                    # the graph below captures into its own pool
 
@@ -384,7 +394,8 @@ def run_ours(args, rank, local_rank, world):
                            "clips_per_gpu": B_PER_GPU, "frames_per_clip": FP, "levels": "192x336,96x168,48x84,24x42,12x21 x256ch",
                            "rois_per_clip": {"box": K_BOX, "mask": K_MASK}, "parallelism": f"dp{world} by clip, 1 NCCL grad all-reduce/step",
                            "l2": f"inputs ({h2d / 1e9:.1f} GB of features per step) far exceed the 126 MB L2; no explicit flush",
-                           "launch": mode, "eager_ms_per_step": round(ms_eager, 3)},
+                           "launch": mode, "eager_ms_per_step": round(ms_eager, 3),
+                           "streams": "timed region: pyramid levels 1..4 on side streams inside the graph; per-kernel event pass: eager, one stream"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "model_tflops": round((conv_f + mask_f) * world / (ms * 1e-3) / 1e12, 1)}
         print(json.dumps(line), flush=True)
