@@ -29,7 +29,6 @@ from torch import nn, Tensor
 from torchvision.models.detection import faster_rcnn as tv_faster_rcnn
 from torchvision.models.detection import mask_rcnn as tv_mask_rcnn
 from torchvision.models.detection import roi_heads as tv_roi_heads
-from torchvision.ops import boxes as box_ops
 
 from . import ops
 from ._lib import BF16, F32, call

@@ -8,7 +8,6 @@ from collections import OrderedDict
 
 import torch
 
-from . import ops
 from .roi_heads import (FastRCNNPredictor, MaskRCNNHeads, MaskRCNNPredictor, MultiScaleRoIAlign, TwoMLPHead,
                         fastrcnn_loss, maskrcnn_loss, pool_pair)
 from .slowfast import SlowFastLayers
