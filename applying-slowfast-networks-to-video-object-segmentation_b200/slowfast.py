@@ -213,6 +213,8 @@ class SlowFastLayers(nn.Module):
         main = torch.cuda.current_stream(dev)
         streams = _level_streams(dev, [tuple(frame_features[k].shape[-2:]) for k in keys])   # smaller levels on side streams
         order = sorted(range(len(keys)), key=lambda j: (streams[j] is None, j))
+        if any(st is not None for st in streams):
+            _prepack(self, (0,))
         for c0 in range(0, n, chunk):
             c1 = min(n, c0 + chunk)
             chunk_outs = {}
@@ -605,6 +607,19 @@ def _level_streams(dev, shapes):
     return out
 
 
+def _prepack(mod, modes):
+    """Fill the packed-weight cache on the CURRENT stream before the level streams fork: a cached operand packed on one
+    side stream would otherwise be read by the other streams without any ordering.  (During a CUDA-graph capture the cache is
+    bypassed and every use packs on its own stream.)"""
+    if torch.cuda.is_current_stream_capturing():
+        return
+    for name, spec in mod._specs.items():
+        for mode in modes:
+            if mode == 1 and name in ("slow_conv1", "fast_conv1"):
+                continue                                        # first-layer inputs carry no gradient on this path
+            mod._packed(name, mode)
+
+
 def _pathway_stream(dev):
     """Side stream for the fast pathway of the level that runs on the current stream.  Opt-in (SFVOS_PATH_STREAMS=1): measured
     on the bench step it does not pay (21.3-21.4 ms without, 21.6-21.7 ms with, same box) - both pathways' kernels are
@@ -654,6 +669,8 @@ class _SlowFastPyramidFn(torch.autograd.Function):
         outs, saved_all = [None] * n_lv, [None] * n_lv
         # small levels are enqueued FIRST (their streams fork from here), the large ones follow on the current stream
         concurrent = any(st is not None for st in streams)
+        if concurrent:
+            _prepack(mod, (0,))
         per_level = [dict() for _ in range(n_lv)]
         for i in sorted(range(n_lv), key=lambda j: (streams[j] is None, j)):
             with _on_stream(streams[i], main):
@@ -689,6 +706,8 @@ class _SlowFastPyramidFn(torch.autograd.Function):
         dev = gs[live[0]].device
         bank = _GradBank(mod, max(1, len(live)), dev)
         main = torch.cuda.current_stream(dev)
+        if any(ctx.streams[i] is not None for i in live):
+            _prepack(mod, (1,))
         for i in reversed(live):
             with _on_stream(ctx.streams[i], main):
                 _level_backward(mod, saved_all[i], _grad_to_act(gs[i]), False, bank,
