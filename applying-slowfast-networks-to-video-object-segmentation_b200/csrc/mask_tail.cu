@@ -132,19 +132,25 @@ mask_bce_fwd_kernel(const float* __restrict__ logits, const long long* __restric
 }
 
 // one CTA per ROI (8 warps stride over its S*S pixels): dx = sum_cls g_cls * w[cls], dw[cls] += g_cls * x, db[cls] += g_cls
-template <typename XT, typename DxT>
+// RELU: x is the output of a ReLU (the ConvTranspose2d + ReLU of the mask predictor) and the kernel also applies that ReLU's
+// backward: dx = (x > 0) ? sum_cls g_cls * w[cls] : 0 and dbias_x[c] += sum_pixels dx -- the separate relu_bwd pass (read dx,
+// read x, write dx again: 1.2 GB at the bench size) disappears.
+template <typename XT, typename DxT, bool RELU>
 __global__ void __launch_bounds__(256)
 mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ glogits, DxT* dx,
-                       float* dw, float* db, long long K, int S, int C, int n_cls) {
-    extern __shared__ float s_dw[];          // [8 warps][n_cls][C]
+                       float* dw, float* db, float* dbias_x, long long K, int S, int C, int n_cls) {
+    extern __shared__ float s_dw[];          // [8 warps][n_cls][C] (+ [8 warps][C] for RELU)
     __shared__ float s_db[8][MAX_CLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long k = blockIdx.x;
     const int ss = S * S;
     float dbacc[MAX_CLS] = {};
+    float* s_dbx = s_dw + 8 * n_cls * C;
     for (int c8 = lane; c8 < C / 8; c8 += 32) {
+        float dbx[8] = {};
         for (int cls0 = 0; cls0 < n_cls; cls0 += 2) {            // two classes per pass keeps registers bounded
             const int ncl = min(2, n_cls - cls0);
+            const bool last_pass = cls0 + 2 >= n_cls;
             float wv[2][8], dwacc[2][8] = {};
             for (int q = 0; q < ncl; ++q) ld8(w + (long long)(cls0 + q) * C + c8 * 8, wv[q]);
             for (int p = warp; p < ss; p += 8) {
@@ -162,11 +168,23 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
                     for (int j = 0; j < 8; ++j) { o[j] = fmaf(g, wv[q][j], o[j]); dwacc[q][j] = fmaf(g, v[j], dwacc[q][j]); }
                     if (c8 == 0) dbacc[cls0 + q] += g;
                 }
+                if (RELU && last_pass) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        o[j] = v[j] > 0.f ? o[j] : 0.f;
+                        // accumulate what is stored (rounded to the dx dtype), like the separate relu_bwd pass did
+                        dbx[j] += sizeof(DxT) == 2 ? __bfloat162float(__float2bfloat16(o[j])) : o[j];
+                    }
+                }
                 st8(dx + (k * ss + p) * C + c8 * 8, o);
             }
             for (int q = 0; q < ncl; ++q)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s_dw[(warp * n_cls + cls0 + q) * C + c8 * 8 + j] = dwacc[q][j];
+        }
+        if (RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_dbx[warp * C + c8 * 8 + j] = dbx[j];
         }
     }
     if (lane == 0)
@@ -181,6 +199,13 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
         float s = 0.f;
         for (int wi = 0; wi < 8; ++wi) s += s_db[wi][threadIdx.x];
         atomicAdd(db + threadIdx.x, s);
+    }
+    if (RELU) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            float s = 0.f;
+            for (int wi = 0; wi < 8; ++wi) s += s_dbx[wi * C + i];
+            atomicAdd(dbias_x + i, s);
+        }
     }
 }
 
@@ -250,9 +275,26 @@ extern "C" int sfvos_mask_logits_bwd(const void* x, int32_t x_dtype, const float
     const size_t sm = (size_t)8 * n_cls * C * sizeof(float);
     SF_CHECK(sm <= 48 * 1024, "mask_logits_bwd: n_cls*C too large");
     if (x_dtype == SFVOS_BF16)
-        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16, false><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, nullptr, K, (int)S, (int)C, n_cls);
     else
-        mask_logits_bwd_kernel<float, float><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<float, float, false><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, nullptr, K, (int)S, (int)C, n_cls);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_mask_logits_relu_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
+                                          int32_t dx_dtype, float* dw, float* db, float* dbias_x, int64_t K, int64_t S,
+                                          int64_t C, int32_t n_cls, sfvos_stream stream) {
+    SF_CHECK(C % 8 == 0 && n_cls >= 1 && n_cls <= MAX_CLS, "mask_logits_relu_bwd: C %% 8 == 0 and n_cls <= 8 required");
+    SF_CHECK(x_dtype == dx_dtype, "mask_logits_relu_bwd: x and dx must share a dtype");
+    SF_CHECK(dbias_x != nullptr, "mask_logits_relu_bwd: dbias_x required");
+    if (K == 0) return SFVOS_OK;
+    const size_t sm = (size_t)8 * (n_cls + 1) * C * sizeof(float);
+    SF_CHECK(sm <= 48 * 1024, "mask_logits_relu_bwd: n_cls*C too large");
+    if (x_dtype == SFVOS_BF16)
+        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16, true><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, dbias_x, K, (int)S, (int)C, n_cls);
+    else
+        mask_logits_bwd_kernel<float, float, true><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, dbias_x, K, (int)S, (int)C, n_cls);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -347,11 +347,10 @@ class _MaskPredictorFn(torch.autograd.Function):
         gx = None
         if K:
             gl = glogits.float().contiguous()
-            dup = Act.empty(K, 1, 2 * H, 2 * W, co, dt_act, dev)
-            call("sfvos_mask_logits_bwd", up.ptr(), ops.dt(up.buf), _p(wl.detach().float().contiguous()), _p(gl),
-                 dup.ptr(), ops.dt(dup.buf), _p(gwl), _p(gbl), K, 2 * H, co, n_cls, stream())
+            # logits-layer backward and the ReLU backward of the ConvTranspose output in ONE pass over ``up``
             dconv = Act.empty(K, 1, 2 * H, 2 * W, co, dt_act, dev)
-            ops.relu_bwd(dup, up, dconv, gbt)
+            call("sfvos_mask_logits_relu_bwd", up.ptr(), ops.dt(up.buf), _p(wl.detach().float().contiguous()), _p(gl),
+                 dconv.ptr(), ops.dt(dconv.buf), _p(gwl), _p(gbl), _p(gbt), K, 2 * H, co, n_cls, stream())
             # the (i,j) tap of dconv as a [K,1,H,W,co] activation: rows 2h+i, columns 2w+j
             cs = 2 * co
             hs, bs = 2 * (2 * W) * co, (2 * H) * (2 * W) * co

@@ -234,6 +234,11 @@ int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, const float* 
 int sfvos_mask_logits_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
                           int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C, int32_t n_cls,
                           sfvos_stream stream);
+/* The same with the backward of the ReLU that produced x fused in (x = relu(conv5_mask(...)), TV mask_rcnn.py:342-343):
+ * dx = (x > 0) ? sum_cls glogits*w : 0 and dbias_x[c] += sum dx (the ConvTranspose2d bias gradient). */
+int sfvos_mask_logits_relu_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
+                               int32_t dx_dtype, float* dw, float* db, float* dbias_x, int64_t K, int64_t S, int64_t C,
+                               int32_t n_cls, sfvos_stream stream);
 /* backward of the loss: glogits[k,cls,p] = gloss*(sigmoid(z)-t)/(K*S*S) on the label channel, 0 elsewhere. */
 int sfvos_mask_bce_bwd(const float* logits, const int64_t* labels, const float* targets, const float* gloss,
                        float* glogits, int64_t K, int64_t S, int32_t n_cls, sfvos_stream stream);
