@@ -19,7 +19,8 @@ class ConvParams(ctypes.Structure):
                 ("y", vp), ("y_dtype", i32), ("relu", i32), ("y_cstride", i64),
                 ("scale", vp), ("shift", vp), ("sum", vp), ("sumsq", vp),
                 ("accumulate", i32), ("reserved", i32),
-                ("OH", i64), ("OW", i64), ("oy_mul", i64), ("oy_off", i64), ("ox_mul", i64), ("ox_off", i64)]
+                ("OH", i64), ("OW", i64), ("oy_mul", i64), ("oy_off", i64), ("ox_mul", i64), ("ox_off", i64),
+                ("relu_mask", vp), ("relu_mask_cstride", i64)]
 
 
 class WgradParams(ctypes.Structure):

@@ -41,6 +41,8 @@ struct PairArgs {
     const float* shift;
     float* sum;
     float* sumsq;
+    const __nv_bfloat16* relu_mask;          // fused ReLU backward (see sfvos_conv_params)
+    long long mask_cstride;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -224,7 +226,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int q = warp - EPI_WARP0;
         const int r = q * 32 + lane;
         const int hl = r / TW, wl = r - hl * TW;
-        const bool do_stats = (a.sum != nullptr);
+        const bool do_stats = (a.sum != nullptr) && (a.relu_mask == nullptr);
         const bool affine = (a.scale != nullptr) || (a.shift != nullptr);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -253,6 +255,33 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     for (int j = 0; j < 32; ++j) { float x = valid ? __uint_as_float(v[j]) : 0.0f; f[j] = x * x; }
                     s = warp_transpose_reduce32(f, lane);
                     atomicAdd(&s_sq[c0 + lane], s);
+                }
+                if (a.relu_mask != nullptr) {
+                    // fused ReLU backward of the layer below: zero the gradient where its activation is not positive, and
+                    // reduce the column sums of the masked gradient (= that layer's bias gradient)
+                    float f[32];
+                    if (valid) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(a.relu_mask + pix * a.mask_cstride + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 m = __ldg(mp + j);
+                            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                // bf16 > 0  <=>  sign bit clear and not zero
+                                const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
+                                const bool p0 = lo != 0 && lo < 0x8000u, p1 = hi != 0 && hi < 0x8000u;
+                                if (!p0) v[8 * j + 2 * e] = 0u;
+                                if (!p1) v[8 * j + 2 * e + 1] = 0u;
+                            }
+                        }
+                    }
+                    if (a.sum != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.0f;     // fp32, like relu_bwd
+                        const float s = warp_transpose_reduce32(f, lane);
+                        atomicAdd(&s_sum[c0 + lane], s);
+                    }
                 }
                 if (valid) {
                     float o[32];
@@ -310,11 +339,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (do_stats) {
+        if (do_stats || (a.relu_mask != nullptr && a.sum != nullptr)) {
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.N; i += EPI_THREADS) {
                 atomicAdd(&a.sum[i], s_sum[i]);
-                atomicAdd(&a.sumsq[i], s_sq[i]);
+                if (do_stats) atomicAdd(&a.sumsq[i], s_sq[i]);
             }
         }
     }
@@ -372,6 +401,7 @@ int sfvos_conv_pair_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.y = p->y; a.y_bf16 = (p->y_dtype == SFVOS_BF16); a.relu = p->relu; a.accumulate = p->accumulate;
     a.y_cstride = p->y_cstride;
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
+    a.relu_mask = reinterpret_cast<const __nv_bfloat16*>(p->relu_mask); a.mask_cstride = p->relu_mask_cstride;
 
     CUtensorMap tx, tw;
     int rc;

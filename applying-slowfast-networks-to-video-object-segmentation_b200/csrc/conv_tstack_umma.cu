@@ -386,7 +386,7 @@ int env_int(const char* name, int dflt) {
 // 1 if sfvos_conv_umma should hand this problem to the temporally-stacked kernel.
 int sfvos_conv_tstack_applicable(const sfvos_conv_params* p) {
     if (!env_int("SFVOS_TSTACK", 1)) return 0;
-    if (p->N != NC) return 0;
+    if (p->N != NC || p->relu_mask != nullptr) return 0;
     const bool k3 = p->kh == 3 && p->kw == 3 && p->pad_h == 1 && p->pad_w == 1;
     const bool k1 = p->kh == 1 && p->kw == 1 && p->pad_h == 0 && p->pad_w == 0 && p->kt > 1;    // lateral dgrad
     if (!k3 && !k1) return 0;

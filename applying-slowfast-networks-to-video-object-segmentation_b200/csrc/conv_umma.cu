@@ -49,6 +49,8 @@ struct ConvArgs {
     float* sum;
     float* sumsq;
     int OH, OW, oy_mul, oy_off, ox_mul, ox_off;
+    const __nv_bfloat16* relu_mask;          // fused ReLU backward (see sfvos_conv_params)
+    long long mask_cstride;
 };
 
 // BK = channels per K step: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle; Cin = 32 layers).
@@ -230,7 +232,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int r = q * 32 + lane;                     // accumulator row = pixel within the tile
         const int hl = r / a.TW;
         const int wl = r - hl * a.TW;
-        const bool do_stats = (a.sum != nullptr);
+        const bool do_stats = (a.sum != nullptr) && (a.relu_mask == nullptr);
         const bool affine = (a.scale != nullptr) || (a.shift != nullptr);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -261,6 +263,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     for (int j = 0; j < 32; ++j) { float x = valid ? __uint_as_float(v[j]) : 0.0f; f[j] = x * x; }
                     s = warp_transpose_reduce32(f, lane);
                     atomicAdd(&s_sq[c0 + lane], s);
+                }
+                if (a.relu_mask != nullptr) {
+                    // fused ReLU backward of the layer below (see conv_pair_umma.cu): mask, then column sums of the masked gradient
+                    if (valid) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(a.relu_mask + pix * a.mask_cstride + nbase + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 m = __ldg(mp + j);
+                            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
+                                if (!(lo != 0 && lo < 0x8000u)) v[8 * j + 2 * e] = 0u;
+                                if (!(hi != 0 && hi < 0x8000u)) v[8 * j + 2 * e + 1] = 0u;
+                            }
+                        }
+                    }
+                    if (a.sum != nullptr) {
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.0f;
+                        const float s = warp_transpose_reduce32(f, lane);
+                        atomicAdd(&a.sum[nbase + c0 + lane], s);      // straight to global: N chunks do not share s_sum
+                    }
                 }
                 if (valid) {
                     float o[32];
@@ -372,14 +398,22 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     SF_CHECK(p != nullptr, "conv_umma: null params");
     SF_CHECK(p->N >= 32 && p->N % 32 == 0 && (p->N <= 256 || p->N % 256 == 0),
              "conv_umma: N=%lld must be a multiple of 32 in [32,256] or a multiple of 256", (long long)p->N);
-    SF_CHECK(p->N <= 256 || p->sum == nullptr, "conv_umma: fused statistics need N <= 256");
+    SF_CHECK(p->N <= 256 || p->sum == nullptr || p->relu_mask != nullptr, "conv_umma: fused statistics need N <= 256");
     SF_CHECK(p->Cp % 32 == 0 && p->Cp >= p->C, "conv_umma: Cp=%lld must be a multiple of 32 and >= C=%lld", (long long)p->Cp, (long long)p->C);
     const int BK = (p->Cp % 64 == 0) ? 64 : 32;
     SF_CHECK(p->C % 8 == 0 && p->x_cstride % 8 == 0, "conv_umma: C and x_cstride must be multiples of 8");
     SF_CHECK(p->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0, "conv_umma: y must be 16-byte aligned with cstride %% 8 == 0");
     SF_CHECK(!(p->accumulate && p->y_dtype != SFVOS_F32), "conv_umma: accumulate needs an f32 output");
-    SF_CHECK((p->sum == nullptr) == (p->sumsq == nullptr), "conv_umma: sum and sumsq must be given together");
+    SF_CHECK((p->sum == nullptr) == (p->sumsq == nullptr) || p->relu_mask != nullptr, "conv_umma: sum and sumsq must be given together");
     SF_CHECK(p->B > 0 && p->To > 0 && p->H > 0 && p->W > 0 && p->T > 0, "conv_umma: empty tensor");
+    if (p->relu_mask != nullptr) {
+        SF_CHECK(p->scale == nullptr && p->shift == nullptr && !p->relu && !p->accumulate && p->sumsq == nullptr,
+                 "conv_umma: relu_mask (fused ReLU backward) excludes scale/shift/relu/accumulate/sumsq");
+        SF_CHECK(p->relu_mask_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->relu_mask) & 15) == 0,
+                 "conv_umma: relu_mask must be 16-byte aligned with cstride %% 8 == 0");
+        SF_CHECK((!p->OH || p->OH == p->H) && (!p->OW || p->OW == p->W) && (!p->oy_mul || p->oy_mul == 1) && (!p->ox_mul || p->ox_mul == 1),
+                 "conv_umma: relu_mask needs the identity output mapping");
+    }
     SF_CHECK(p->B * p->To * p->H * p->W < (1LL << 31), "conv_umma: too many output pixels");
     int rc = sfvos_device_check();
     if (rc) return rc;
@@ -446,6 +480,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     a.y = p->y; a.y_bf16 = (p->y_dtype == SFVOS_BF16); a.relu = p->relu; a.accumulate = p->accumulate;
     a.y_cstride = p->y_cstride;
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
+    a.relu_mask = reinterpret_cast<const __nv_bfloat16*>(p->relu_mask); a.mask_cstride = p->relu_mask_cstride;
     a.OH = (int)(p->OH ? p->OH : p->H); a.OW = (int)(p->OW ? p->OW : p->W);
     a.oy_mul = (int)(p->oy_mul ? p->oy_mul : 1); a.ox_mul = (int)(p->ox_mul ? p->ox_mul : 1);
     a.oy_off = (int)p->oy_off; a.ox_off = (int)p->ox_off;

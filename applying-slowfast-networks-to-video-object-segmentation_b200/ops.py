@@ -127,7 +127,7 @@ def unpack_wgrad(dw, grad, mode, tap=(0, 0)):
 
 
 def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shift=None, stats=None, accumulate=False,
-         x_strides=None, scatter=None):
+         x_strides=None, scatter=None, relu_mask=None, dbias=None):
     """x: Act (input), y: Act (output, B*To*OH*OW pixels).  k=(kt,kh,kw), pad=(pt,ph,pw).
     stats: optional f32 [2,N] tensor receiving (sum, sumsq) of the raw accumulators (umma only)."""
     p = ConvParams()
@@ -146,6 +146,11 @@ def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shi
     p.accumulate = int(accumulate)
     if scatter is not None:
         p.OH, p.OW, p.oy_mul, p.oy_off, p.ox_mul, p.ox_off = scatter
+    if relu_mask is not None:       # fused ReLU backward: relu_mask = Act of the post-ReLU activation, dbias f32 [N] accumulates
+        assert umma and stats is None and relu_mask.dtype == torch.bfloat16
+        p.relu_mask = relu_mask.ptr(); p.relu_mask_cstride = relu_mask.cstride
+        if dbias is not None:
+            p.sum = _p(dbias)
     flops = 2.0 * x.B * To * x.H * x.W * N * x.C * k[0] * k[1] * k[2]
     _timed_call("conv_umma" if umma else "conv_simt", flops, "sfvos_conv_umma" if umma else "sfvos_conv_simt", p)
 

@@ -263,25 +263,37 @@ class _MaskHeadFn(torch.autograd.Function):
             dy = _to_cl_act(g.float(), torch.float32)
         grads = [None] * len(wb)
         n = len(wb) // 2
+        dconv = db = None          # gradient wrt the pre-activation output of layer i (and its bias gradient), if already known
         for i in range(n - 1, -1, -1):
             w, b = wb[2 * i], wb[2 * i + 1]
             x_in, y = acts[i], acts[i + 1]
-            dconv = Act.empty(K, 1, H, W, y.C, dt_act, g.device)
-            db = torch.zeros_like(b, dtype=torch.float32)
             gw = torch.zeros_like(w, dtype=torch.float32)
+            if dconv is None:
+                dconv = Act.empty(K, 1, H, W, y.C, dt_act, g.device)
+                db = torch.zeros_like(b, dtype=torch.float32)
+                if K:
+                    ops.relu_bwd(dy, y, dconv, db)
             if K:
-                ops.relu_bwd(dy, y, dconv, db)
                 dwp = torch.zeros(9 * x_in.C * y.C, dtype=torch.float32, device=g.device)
                 ops.wgrad(x_in, dconv, (1, 3, 3), (0, 1, 1), dwp, umma=umma)
                 ops.unpack_wgrad(dwp, gw, 0)
             grads[2 * i], grads[2 * i + 1] = gw.to(w.dtype), db.to(b.dtype)
-            if i > 0 or ctx.needs_input_grad[0]:
+            if i > 0 and umma and K:
+                # data gradient with the ReLU backward of the layer below fused into the epilogue: the result IS that layer's
+                # pre-activation gradient (bf16) and its bias gradient - no f32 round trip, no separate relu_bwd pass
+                wd, cpd = _pack(w, 1, umma, w.shape[0])
+                nxt = Act.empty(K, 1, H, W, x_in.C, dt_act, g.device)
+                db = torch.zeros_like(wb[2 * i - 1], dtype=torch.float32)
+                ops.conv(dconv, wd, cpd, x_in.C, (1, 3, 3), (0, 1, 1), 1, nxt, umma=True, relu_mask=x_in, dbias=db)
+                dconv = nxt
+            elif i > 0 or ctx.needs_input_grad[0]:
                 wd, cpd = _pack(w, 1, umma, w.shape[0])
                 last = i == 0
                 dx = Act.empty(K, 1, H, W, x_in.C, (dt_act if last else torch.float32), g.device)
                 if K:
                     ops.conv(dconv, wd, cpd, x_in.C, (1, 3, 3), (0, 1, 1), 1, dx, umma=umma)
                 dy = dx
+                dconv = db = None
         gx = None
         if ctx.needs_input_grad[0]:
             gx = _nchw_view(dy.buf, K, H, W, dy.C).to(ctx.x_dtype)

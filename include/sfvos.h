@@ -84,6 +84,12 @@ typedef struct sfvos_conv_params {
     int32_t reserved;
     /* output pixel scatter (identity: OH=H, OW=W, mul=1, off=0); ConvTranspose2d k2 s2 uses mul=2, off=i|j */
     int64_t OH, OW, oy_mul, oy_off, ox_mul, ox_off;
+    /* optional fused ReLU backward (umma, dgrad use): relu_mask = the bf16 post-ReLU activation this gradient flows into,
+     * same pixels / channels as y (cstride in elements).  y = (relu_mask > 0) ? result : 0, and `sum` (if given; sumsq must
+     * then be NULL) receives the column sums of the STORED y = the bias gradient of the layer below.  Replaces the separate
+     * relu_bwd pass between two 3x3 convolutions of MaskRCNNHeads (TV mask_rcnn.py:284-296). */
+    const void* relu_mask;
+    int64_t relu_mask_cstride;
 } sfvos_conv_params;
 
 /* tcgen05/TMEM/TMA bf16 kernel (the product path). */
