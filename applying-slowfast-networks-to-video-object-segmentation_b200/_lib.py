@@ -71,10 +71,10 @@ _SIGS = {
     "sfvos_roi_align_fwd": [ctypes.POINTER(RoiParams), vp],
     "sfvos_roi_align_bwd": [ctypes.POINTER(RoiParams), vp],
     "sfvos_mask_targets": [vp, i64, i64, i64, vp, i64, i32, vp, vp],
-    "sfvos_mask_logits_fwd": [vp, i32, vp, vp, vp, i64, i64, i64, i32, vp],
+    "sfvos_mask_logits_fwd": [vp, i32, vp, vp, vp, i64, i64, i64, i32, i32, vp],
     "sfvos_mask_bce_fwd": [vp, vp, vp, vp, i64, i64, i32, vp],
-    "sfvos_mask_logits_bwd": [vp, i32, vp, vp, vp, i32, vp, vp, i64, i64, i64, i32, vp],
-    "sfvos_mask_logits_relu_bwd": [vp, i32, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i32, vp],
+    "sfvos_mask_logits_bwd": [vp, i32, vp, vp, vp, i32, vp, vp, i64, i64, i64, i32, i32, vp],
+    "sfvos_mask_logits_relu_bwd": [vp, i32, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i32, i32, vp],
     "sfvos_mask_bce_bwd": [vp, vp, vp, vp, vp, i64, i64, i32, vp],
     "sfvos_mask_probs": [vp, vp, vp, i64, i64, i32, vp],
     "sfvos_fastrcnn_loss_fwd": [vp, i64, vp, i64, vp, vp, i64, i32, f32, vp, vp],

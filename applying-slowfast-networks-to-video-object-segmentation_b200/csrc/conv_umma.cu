@@ -114,11 +114,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (a.b_resident) {
                 // small weight sets (1x1 lateral convs, the 2x2 ConvTranspose taps, the box predictor): every (tap, chunk)
                 // tile is loaded ONCE per CTA and reused by all its pixel tiles -- the per-tile L2 -> SM traffic drops to A
+                // (with several N chunks the grid is a multiple of nchunks, so this CTA only ever sees chunk blockIdx.x % nchunks)
                 const int nb = a.kt * taps_hw * a.cchunks;
+                const int n_res = (int)(blockIdx.x % a.nchunks) * a.N;
                 mbar_arrive_expect_tx(&b_full[0], (uint32_t)(nb * b_bytes));
                 for (int tp = 0; tp < a.kt * taps_hw; ++tp)
                     for (int cc = 0; cc < a.cchunks; ++cc)
-                        tma_load_3d(smem_b + (tp * a.cchunks + cc) * b_bytes, &tmap_w, &b_full[0], cc * BK, 0, tp);
+                        tma_load_3d(smem_b + (tp * a.cchunks + cc) * b_bytes, &tmap_w, &b_full[0], cc * BK, n_res, tp);
             }
             for (int item = blockIdx.x; item < a.ntiles * a.nchunks; item += gridDim.x) {
                 // consecutive items = the N chunks of one pixel tile: concurrent CTAs share the activation tile in L2
@@ -459,7 +461,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         a.a_stage_bytes = BM * BK * 2;
         a.b_group = 1;
         const long long all_b = (long long)p->kt * p->kh * p->kw * a.cchunks * b_bytes;
-        if (a.nchunks == 1 && all_b <= 144 * 1024 && env_int("SFVOS_B_RESIDENT", 1)) {
+        if (all_b <= 144 * 1024 && env_int("SFVOS_B_RESIDENT", 1) && (a.nchunks == 1 || sfvos_num_sms() >= a.nchunks)) {
             a.b_resident = 1;
             a.b_stages = (int)(all_b / b_bytes);
             int st = (int)((smem_budget - all_b) / a.a_stage_bytes);
@@ -509,6 +511,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_group * b_bytes + 1024 + 8192;
     int grid = sfvos_num_sms();
     if (grid > a.ntiles * a.nchunks) grid = a.ntiles * a.nchunks;
+    if (a.b_resident && a.nchunks > 1) grid -= grid % a.nchunks;     // every CTA keeps ONE N chunk (its resident weights)
     if (BK == 64) {
         SF_CUDA(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         conv_umma_kernel<64><<<grid, NUM_THREADS, smem_bytes, stream>>>(tx, tw, a);

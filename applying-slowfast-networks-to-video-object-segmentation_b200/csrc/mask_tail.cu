@@ -30,10 +30,21 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
 
 constexpr int MAX_CLS = 8;
 
+// pixel_order 1: the rows of x are the 2x2 space-to-depth order of the S x S map -- row (h*(S/2) + w)*4 + 2i + j holds spatial
+// pixel (2h+i, 2w+j) -- which is how the ConvTranspose2d(k2,s2) of the mask predictor leaves its output when its four taps are
+// computed as ONE 1x1 convolution with 4*C output channels.  logits / glogits stay in the reference's spatial order.
+__device__ __forceinline__ long long row_to_spatial(long long r, int S, int pixel_order) {
+    if (!pixel_order) return r;
+    const int tap = (int)(r & 3);
+    const int lw = (int)(r >> 2), hs = S >> 1;
+    const int h = lw / hs, w = lw - h * hs;
+    return (long long)(2 * h + (tap >> 1)) * S + 2 * w + (tap & 1);
+}
+
 template <typename XT>
 __global__ void __launch_bounds__(256)
 mask_logits_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* logits,
-                       long long K, int S, int C, int n_cls) {
+                       long long K, int S, int C, int n_cls, int pixel_order) {
     const int lane = threadIdx.x & 31;
     const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long ss = (long long)S * S;
@@ -52,7 +63,7 @@ mask_logits_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
     const long long k = pix / ss, p = pix - k * ss;
     for (int cls = 0; cls < n_cls; ++cls) {
         const float s = warp_sum(acc[cls]);
-        if (lane == 0) logits[(k * n_cls + cls) * ss + p] = s + b[cls];
+        if (lane == 0) logits[(k * n_cls + cls) * ss + row_to_spatial(p, S, pixel_order)] = s + b[cls];
     }
 }
 
@@ -62,7 +73,7 @@ mask_logits_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
 template <typename XT>
 __global__ void __launch_bounds__(256)
 mask_logits_fwd2_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* logits,
-                        long long npix, long long ss) {
+                        long long npix, long long ss, int S, int pixel_order) {
     constexpr int C = 256;
     const int lane = threadIdx.x & 31;
     const long long pix0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8;
@@ -104,7 +115,7 @@ mask_logits_fwd2_kernel(const XT* __restrict__ x, const float* __restrict__ w, c
         const long long pix = pix0 + i;
         if (pix < npix) {
             const long long k = pix / ss, q = pix - k * ss;
-            logits[(k * 2 + cls) * ss + q] = s[0] + b[cls];
+            logits[(k * 2 + cls) * ss + row_to_spatial(q, S, pixel_order)] = s[0] + b[cls];
         }
     }
 }
@@ -138,7 +149,7 @@ mask_bce_fwd_kernel(const float* __restrict__ logits, const long long* __restric
 template <typename XT, typename DxT, bool RELU>
 __global__ void __launch_bounds__(256)
 mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ glogits, DxT* dx,
-                       float* dw, float* db, float* dbias_x, long long K, int S, int C, int n_cls) {
+                       float* dw, float* db, float* dbias_x, long long K, int S, int C, int n_cls, int pixel_order) {
     extern __shared__ float s_dw[];          // [8 warps][n_cls][C] (+ [8 warps][C] for RELU)
     __shared__ float s_db[8][MAX_CLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -163,7 +174,7 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
                     ld8(dx + (k * ss + p) * C + c8 * 8, o);
                 }
                 for (int q = 0; q < ncl; ++q) {
-                    const float g = glogits[(k * n_cls + cls0 + q) * ss + p];
+                    const float g = glogits[(k * n_cls + cls0 + q) * ss + row_to_spatial(p, S, pixel_order)];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { o[j] = fmaf(g, wv[q][j], o[j]); dwacc[q][j] = fmaf(g, v[j], dwacc[q][j]); }
                     if (c8 == 0) dbacc[cls0 + q] += g;
@@ -236,20 +247,21 @@ __global__ void mask_probs_kernel(const float* __restrict__ logits, const long l
 #define CS(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int sfvos_mask_logits_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, float* logits,
-                                     int64_t K, int64_t S, int64_t C, int32_t n_cls, sfvos_stream stream) {
+                                     int64_t K, int64_t S, int64_t C, int32_t n_cls, int32_t pixel_order, sfvos_stream stream) {
+    SF_CHECK(pixel_order == 0 || (pixel_order == 1 && S % 2 == 0), "mask_logits: pixel_order 1 needs an even S");
     SF_CHECK(C % 8 == 0 && n_cls >= 1 && n_cls <= MAX_CLS, "mask_logits: C %% 8 == 0 and n_cls <= 8 required");
     if (K == 0) return SFVOS_OK;
     const long long npix = K * S * S;
     const int grid = (int)((npix + 7) / 8);
     if (n_cls == 2 && C == 256) {
         const int grid2 = (int)((npix + 63) / 64);
-        if (x_dtype == SFVOS_BF16) mask_logits_fwd2_kernel<__nv_bfloat16><<<grid2, 256, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, logits, npix, S * S);
-        else mask_logits_fwd2_kernel<float><<<grid2, 256, 0, CS(stream)>>>(reinterpret_cast<const float*>(x), w, b, logits, npix, S * S);
+        if (x_dtype == SFVOS_BF16) mask_logits_fwd2_kernel<__nv_bfloat16><<<grid2, 256, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, logits, npix, S * S, (int)S, pixel_order);
+        else mask_logits_fwd2_kernel<float><<<grid2, 256, 0, CS(stream)>>>(reinterpret_cast<const float*>(x), w, b, logits, npix, S * S, (int)S, pixel_order);
         SF_LAUNCH_CHECK();
         return SFVOS_OK;
     }
-    if (x_dtype == SFVOS_BF16) mask_logits_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, logits, K, (int)S, (int)C, n_cls);
-    else mask_logits_fwd_kernel<float><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const float*>(x), w, b, logits, K, (int)S, (int)C, n_cls);
+    if (x_dtype == SFVOS_BF16) mask_logits_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, logits, K, (int)S, (int)C, n_cls, pixel_order);
+    else mask_logits_fwd_kernel<float><<<grid, 256, 0, CS(stream)>>>(reinterpret_cast<const float*>(x), w, b, logits, K, (int)S, (int)C, n_cls, pixel_order);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -268,23 +280,25 @@ extern "C" int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, co
 
 extern "C" int sfvos_mask_logits_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
                                      int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C,
-                                     int32_t n_cls, sfvos_stream stream) {
+                                     int32_t n_cls, int32_t pixel_order, sfvos_stream stream) {
+    SF_CHECK(pixel_order == 0 || (pixel_order == 1 && S % 2 == 0), "mask_logits_bwd: pixel_order 1 needs an even S");
     SF_CHECK(C % 8 == 0 && n_cls >= 1 && n_cls <= MAX_CLS, "mask_logits_bwd: C %% 8 == 0 and n_cls <= 8 required");
     SF_CHECK(x_dtype == dx_dtype, "mask_logits_bwd: x and dx must share a dtype");
     if (K == 0) return SFVOS_OK;
     const size_t sm = (size_t)8 * n_cls * C * sizeof(float);
     SF_CHECK(sm <= 48 * 1024, "mask_logits_bwd: n_cls*C too large");
     if (x_dtype == SFVOS_BF16)
-        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16, false><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, nullptr, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16, false><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, nullptr, K, (int)S, (int)C, n_cls, pixel_order);
     else
-        mask_logits_bwd_kernel<float, float, false><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, nullptr, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<float, float, false><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, nullptr, K, (int)S, (int)C, n_cls, pixel_order);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
 
 extern "C" int sfvos_mask_logits_relu_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
                                           int32_t dx_dtype, float* dw, float* db, float* dbias_x, int64_t K, int64_t S,
-                                          int64_t C, int32_t n_cls, sfvos_stream stream) {
+                                          int64_t C, int32_t n_cls, int32_t pixel_order, sfvos_stream stream) {
+    SF_CHECK(pixel_order == 0 || (pixel_order == 1 && S % 2 == 0), "mask_logits_relu_bwd: pixel_order 1 needs an even S");
     SF_CHECK(C % 8 == 0 && n_cls >= 1 && n_cls <= MAX_CLS, "mask_logits_relu_bwd: C %% 8 == 0 and n_cls <= 8 required");
     SF_CHECK(x_dtype == dx_dtype, "mask_logits_relu_bwd: x and dx must share a dtype");
     SF_CHECK(dbias_x != nullptr, "mask_logits_relu_bwd: dbias_x required");
@@ -292,9 +306,9 @@ extern "C" int sfvos_mask_logits_relu_bwd(const void* x, int32_t x_dtype, const 
     const size_t sm = (size_t)8 * (n_cls + 1) * C * sizeof(float);
     SF_CHECK(sm <= 48 * 1024, "mask_logits_relu_bwd: n_cls*C too large");
     if (x_dtype == SFVOS_BF16)
-        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16, true><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, dbias_x, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16, true><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, dbias_x, K, (int)S, (int)C, n_cls, pixel_order);
     else
-        mask_logits_bwd_kernel<float, float, true><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, dbias_x, K, (int)S, (int)C, n_cls);
+        mask_logits_bwd_kernel<float, float, true><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const float*>(x), w, glogits, reinterpret_cast<float*>(dx), dw, db, dbias_x, K, (int)S, (int)C, n_cls, pixel_order);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -323,6 +323,24 @@ _TAPS = [(0, 0), (0, 1), (1, 0), (1, 1)]
 
 
 class _MaskPredictorFn(torch.autograd.Function):
+    """ConvTranspose2d(k2, s2) + ReLU -> 1x1 conv to n_cls logits.  The four taps of the transposed convolution are ONE 1x1
+    convolution C -> 4*co whose output stays in 2x2 space-to-depth order ([K,H,W,(tap, co)]: every low-res pixel holds its
+    2x2 block of high-res pixels); the logits kernels read it in that order (``pixel_order=1``) and write the reference's raster
+    order.  Backward: the weight gradient of all taps is one GEMM (N = 4*co), the data gradient one GEMM with K = 4*co -
+    no per-tap launches, no read-modify-write of the input gradient."""
+
+    @staticmethod
+    def _fprop_weights(wt, umma, C):
+        """ConvTranspose2d weight [C, co, 2, 2] -> operand of the 1x1 convolution C -> 4*co (output channel = tap*co + n)."""
+        parts = [_pack(wt, 2, umma, C, tap)[0] for tap in _TAPS]         # umma: bf16 [co][C] each; simt: f32 [C][co]
+        return torch.cat(parts, dim=0) if umma else torch.cat(parts, dim=1).contiguous()
+
+    @staticmethod
+    def _dgrad_weights(wt, umma, co):
+        """-> operand of the 1x1 convolution 4*co -> C of the data gradient (input channel = tap*co + n)."""
+        parts = [_pack(wt, 3, umma, co, tap)[0] for tap in _TAPS]        # umma: bf16 [C][co] each; simt: f32 [co][C]
+        return torch.cat(parts, dim=1).contiguous() if umma else torch.cat(parts, dim=0)
+
     @staticmethod
     def forward(ctx, x, precision, wt, bt, wl, bl):
         ops.device_check()
@@ -331,16 +349,15 @@ class _MaskPredictorFn(torch.autograd.Function):
         K, C, H, W = x.shape
         co = wt.shape[1]
         n_cls = wl.shape[0]
+        assert not umma or (C % 64 == 0 and co % 64 == 0), "conv5_mask channels must be multiples of 64 on the tensor-core path"
         xin = _to_cl_act(x, dt_act)
-        up = Act.empty(K, 1, 2 * H, 2 * W, co, dt_act, x.device)
+        up = Act.empty(K, 1, H, W, 4 * co, dt_act, x.device)             # space-to-depth: channel = tap * co + c
         logits = torch.empty(K, n_cls, 2 * H, 2 * W, dtype=torch.float32, device=x.device)
         if K:
-            for (i, j) in _TAPS:
-                wp, cp = _pack(wt, 2, umma, C, (i, j))
-                ops.conv(xin, wp, cp, co, (1, 1, 1), (0, 0, 0), 1, up, umma=umma, relu=True, shift=bt.detach().float(),
-                         scatter=(2 * H, 2 * W, 2, i, 2, j))
+            wf = _MaskPredictorFn._fprop_weights(wt, umma, C)
+            ops.conv(xin, wf, C, 4 * co, (1, 1, 1), (0, 0, 0), 1, up, umma=umma, relu=True, shift=bt.detach().float().repeat(4))
             call("sfvos_mask_logits_fwd", up.ptr(), ops.dt(up.buf), _p(wl.detach().float().contiguous()),
-                 _p(bl.detach().float().contiguous()), _p(logits), K, 2 * H, co, n_cls, stream())
+                 _p(bl.detach().float().contiguous()), _p(logits), K, 2 * H, co, n_cls, 1, stream())
         ctx.acts = (xin, up)
         ctx.meta = (umma, dt_act, x.dtype, K, C, H, W, co, n_cls)
         ctx.save_for_backward(wt, bt, wl, bl)
@@ -360,24 +377,19 @@ class _MaskPredictorFn(torch.autograd.Function):
         if K:
             gl = glogits.float().contiguous()
             # logits-layer backward and the ReLU backward of the ConvTranspose output in ONE pass over ``up``
-            dconv = Act.empty(K, 1, 2 * H, 2 * W, co, dt_act, dev)
+            dconv = Act.empty(K, 1, H, W, 4 * co, dt_act, dev)
             call("sfvos_mask_logits_relu_bwd", up.ptr(), ops.dt(up.buf), _p(wl.detach().float().contiguous()), _p(gl),
-                 dconv.ptr(), ops.dt(dconv.buf), _p(gwl), _p(gbl), _p(gbt), K, 2 * H, co, n_cls, stream())
-            # the (i,j) tap of dconv as a [K,1,H,W,co] activation: rows 2h+i, columns 2w+j
-            cs = 2 * co
-            hs, bs = 2 * (2 * W) * co, (2 * H) * (2 * W) * co
-            need_dx = ctx.needs_input_grad[0]
-            dx = Act.empty(K, 1, H, W, C, torch.float32, dev) if need_dx else None
+                 dconv.ptr(), ops.dt(dconv.buf), _p(gwl), _p(gbl), _p(gbt), K, 2 * H, co, n_cls, 1, stream())
+            # weight gradient of the four taps: dw[c][tap*co + n]
+            dwp = torch.zeros(C * 4 * co, dtype=torch.float32, device=dev)
+            ops.wgrad(xin, dconv, (1, 1, 1), (0, 0, 0), dwp, umma=umma)
+            dw4 = dwp.view(C, 4, co)
             for n, (i, j) in enumerate(_TAPS):
-                tap = Act(dconv.buf, K, 1, H, W, co, cs, (i * 2 * W + j) * co)
-                dwp = torch.zeros(C * co, dtype=torch.float32, device=dev)
-                ops.wgrad(xin, tap, (1, 1, 1), (0, 0, 0), dwp, umma=umma, dy_strides=(hs, bs, bs))
-                ops.unpack_wgrad(dwp, gwt, 2, (i, j))
-                if need_dx:
-                    wd, cpd = _pack(wt, 3, umma, co, (i, j))
-                    ops.conv(tap, wd, cpd, C, (1, 1, 1), (0, 0, 0), 1, dx, umma=umma, accumulate=(n > 0),
-                             x_strides=(hs, bs, bs))
-            if need_dx:
+                ops.unpack_wgrad(dw4[:, n].contiguous(), gwt, 2, (i, j))
+            if ctx.needs_input_grad[0]:
+                wb = _MaskPredictorFn._dgrad_weights(wt, umma, co)
+                dx = Act.empty(K, 1, H, W, C, dt_act, dev)
+                ops.conv(dconv, wb, 4 * co, C, (1, 1, 1), (0, 0, 0), 1, dx, umma=umma)
                 gx = _nchw_view(dx.buf, K, H, W, C).to(x_dtype)
         elif ctx.needs_input_grad[0]:
             gx = torch.zeros(K, C, H, W, dtype=x_dtype, device=dev)

@@ -229,9 +229,14 @@ int sfvos_mask_targets(const uint8_t* masks, int64_t n_obj, int64_t H, int64_t W
  * the class-channel gather and F.binary_cross_entropy_with_logits of maskrcnn_loss (TV/.../roi_heads.py:100-129)
  * and the sigmoid/select of maskrcnn_inference (:56-82).
  * ------------------------------------------------------------------------------------------------------- */
-/* x (bf16|f32) [K,S,S,C] -> logits f32 [K,n_cls,S,S] (NCHW like the reference). */
+/* x (bf16|f32) [K,S,S,C] -> logits f32 [K,n_cls,S,S] (NCHW like the reference).
+ * pixel_order (this and the two backward entries): 0 = the rows of x are the S x S pixels in raster order; 1 = 2x2
+ * space-to-depth order, row (h*(S/2)+w)*4 + 2i+j = pixel (2h+i, 2w+j) -- the layout in which ConvTranspose2d(k2,s2)
+ * (conv5_mask) leaves its output when its four taps run as ONE 1x1 convolution with 4*C output channels.  logits and
+ * glogits are always in the reference's raster order. */
 int sfvos_mask_logits_fwd(const void* x, int32_t x_dtype, const float* w /*[n_cls,C]*/, const float* b,
-                          float* logits, int64_t K, int64_t S, int64_t C, int32_t n_cls, sfvos_stream stream);
+                          float* logits, int64_t K, int64_t S, int64_t C, int32_t n_cls, int32_t pixel_order,
+                          sfvos_stream stream);
 /* loss[0] = mean over K*S*S of BCE-with-logits(logits[k,labels[k]], targets[k]). */
 int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, const float* targets, float* loss, int64_t K,
                        int64_t S, int32_t n_cls, sfvos_stream stream);
@@ -239,12 +244,12 @@ int sfvos_mask_bce_fwd(const float* logits, const int64_t* labels, const float* 
  * dw [n_cls,C] += sum glogits*x; db [n_cls] += sum glogits. */
 int sfvos_mask_logits_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
                           int32_t dx_dtype, float* dw, float* db, int64_t K, int64_t S, int64_t C, int32_t n_cls,
-                          sfvos_stream stream);
+                          int32_t pixel_order, sfvos_stream stream);
 /* The same with the backward of the ReLU that produced x fused in (x = relu(conv5_mask(...)), TV mask_rcnn.py:342-343):
  * dx = (x > 0) ? sum_cls glogits*w : 0 and dbias_x[c] += sum dx (the ConvTranspose2d bias gradient). */
 int sfvos_mask_logits_relu_bwd(const void* x, int32_t x_dtype, const float* w, const float* glogits, void* dx,
                                int32_t dx_dtype, float* dw, float* db, float* dbias_x, int64_t K, int64_t S, int64_t C,
-                               int32_t n_cls, sfvos_stream stream);
+                               int32_t n_cls, int32_t pixel_order, sfvos_stream stream);
 /* backward of the loss: glogits[k,cls,p] = gloss*(sigmoid(z)-t)/(K*S*S) on the label channel, 0 elsewhere. */
 int sfvos_mask_bce_bwd(const float* logits, const int64_t* labels, const float* targets, const float* gloss,
                        float* glogits, int64_t K, int64_t S, int32_t n_cls, sfvos_stream stream);
