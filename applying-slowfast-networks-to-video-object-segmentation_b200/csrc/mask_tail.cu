@@ -164,9 +164,13 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
             const bool last_pass = cls0 + 2 >= n_cls;
             float wv[2][8], dwacc[2][8] = {};
             for (int q = 0; q < ncl; ++q) ld8(w + (long long)(cls0 + q) * C + c8 * 8, wv[q]);
+            float vn[8];                                          // next pixel's activations, loaded one trip ahead
+            if (warp < ss) ld8(x + (k * ss + warp) * C + c8 * 8, vn);
             for (int p = warp; p < ss; p += 8) {
                 float v[8], o[8];
-                ld8(x + (k * ss + p) * C + c8 * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = vn[j];
+                if (p + 8 < ss) ld8(x + (k * ss + p + 8) * C + c8 * 8, vn);
                 if (cls0 == 0) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = 0.f;
@@ -183,8 +187,7 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         o[j] = v[j] > 0.f ? o[j] : 0.f;
-                        // accumulate what is stored (rounded to the dx dtype), like the separate relu_bwd pass did
-                        dbx[j] += sizeof(DxT) == 2 ? __bfloat162float(__float2bfloat16(o[j])) : o[j];
+                        dbx[j] += o[j];
                     }
                 }
                 st8(dx + (k * ss + p) * C + c8 * 8, o);
