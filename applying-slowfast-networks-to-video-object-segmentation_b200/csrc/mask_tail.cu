@@ -164,13 +164,20 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
             const bool last_pass = cls0 + 2 >= n_cls;
             float wv[2][8], dwacc[2][8] = {};
             for (int q = 0; q < ncl; ++q) ld8(w + (long long)(cls0 + q) * C + c8 * 8, wv[q]);
-            float vn[8];                                          // next pixel's activations, loaded one trip ahead
-            if (warp < ss) ld8(x + (k * ss + warp) * C + c8 * 8, vn);
+            float vn[8], gn[2] = {0.f, 0.f};                      // next pixel's activations / logit gradients, loaded one trip ahead
+            if (warp < ss) {
+                ld8(x + (k * ss + warp) * C + c8 * 8, vn);
+                for (int q = 0; q < ncl; ++q) gn[q] = glogits[(k * n_cls + cls0 + q) * ss + row_to_spatial(warp, S, pixel_order)];
+            }
             for (int p = warp; p < ss; p += 8) {
                 float v[8], o[8];
+                const float gc[2] = {gn[0], gn[1]};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = vn[j];
-                if (p + 8 < ss) ld8(x + (k * ss + p + 8) * C + c8 * 8, vn);
+                if (p + 8 < ss) {
+                    ld8(x + (k * ss + p + 8) * C + c8 * 8, vn);
+                    for (int q = 0; q < ncl; ++q) gn[q] = glogits[(k * n_cls + cls0 + q) * ss + row_to_spatial(p + 8, S, pixel_order)];
+                }
                 if (cls0 == 0) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = 0.f;
@@ -178,7 +185,7 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
                     ld8(dx + (k * ss + p) * C + c8 * 8, o);
                 }
                 for (int q = 0; q < ncl; ++q) {
-                    const float g = glogits[(k * n_cls + cls0 + q) * ss + row_to_spatial(p, S, pixel_order)];
+                    const float g = gc[q];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { o[j] = fmaf(g, wv[q][j], o[j]); dwacc[q][j] = fmaf(g, v[j], dwacc[q][j]); }
                     if (c8 == 0) dbacc[cls0 + q] += g;
