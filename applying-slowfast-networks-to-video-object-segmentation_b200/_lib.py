@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsfvos.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F64 = 0, 1, 2
 i64, i32, f32, f64, vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
 
@@ -29,7 +29,7 @@ class WgradParams(ctypes.Structure):
                 ("dy", vp), ("To", i64), ("N", i64), ("dy_cstride", i64),
                 ("dy_hstride", i64), ("dy_tstride", i64), ("dy_bstride", i64),
                 ("kt", i64), ("kh", i64), ("kw", i64), ("pad_t", i64), ("pad_h", i64), ("pad_w", i64),
-                ("dw", vp)]
+                ("dw", vp), ("workspace", vp), ("workspace_bytes", i64)]
 
 
 class RoiParams(ctypes.Structure):
@@ -44,7 +44,7 @@ BN_MAX_CALLS = 8
 
 class BnRunningParams(ctypes.Structure):
     _fields_ = [("sum", vp * BN_MAX_CALLS), ("sumsq", vp * BN_MAX_CALLS), ("count", f64 * BN_MAX_CALLS),
-                ("n_calls", i32), ("reserved", i32), ("conv_bias", vp), ("running_mean", vp), ("running_var", vp),
+                ("n_calls", i32), ("stats_dtype", i32), ("conv_bias", vp), ("running_mean", vp), ("running_var", vp),
                 ("num_batches_tracked", vp), ("momentum", f64), ("C", i64)]
 
 
@@ -57,13 +57,13 @@ _SIGS = {
     "sfvos_wgrad_simt": [ctypes.POINTER(WgradParams), vp],
     "sfvos_pack_weights": [vp, vp, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, vp],
     "sfvos_unpack_wgrad": [vp, vp, i32, i64, i64, i64, i64, i64, i64, i64, vp],
-    "sfvos_channel_stats": [vp, i64, i64, i64, vp, vp, vp],
-    "sfvos_bn_finalize": [vp, vp, f64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp, vp, i64, vp],
+    "sfvos_channel_stats": [vp, i64, i64, i64, vp, vp, i64, vp],
+    "sfvos_bn_finalize": [vp, vp, i32, f64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp, vp, i64, vp],
     "sfvos_bn_running_update": [ctypes.POINTER(BnRunningParams), vp],
-    "sfvos_bn_fold_eval": [vp, vp, vp, vp, vp, f64, vp, vp, i64, vp],
+    "sfvos_bn_fold_eval": [vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, i64, vp],
     "sfvos_affine_act": [vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, i64, vp],
-    "sfvos_bn_bwd_reduce": [vp, i32, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, vp, vp],
-    "sfvos_bn_bwd_apply": [vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, i32, i64, vp, vp, vp],
+    "sfvos_bn_bwd_reduce": [vp, i32, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, vp, vp, i64, vp],
+    "sfvos_bn_bwd_apply": [vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, i32, i64, vp, vp, i32, vp, vp],
     "sfvos_relu_bwd": [vp, i32, i64, vp, i32, i64, vp, i32, i64, vp, i64, i64, vp],
     "sfvos_nchw_to_nhwc": [vp, i64, vp, i32, i64, i64, i64, i64, vp],
     "sfvos_nhwc_to_nchw": [vp, i32, i64, vp, i64, i64, i64, vp],
@@ -83,7 +83,13 @@ _SIGS = {
     "sfvos_axpby": [vp, vp, f32, f32, i64, vp],
 }
 
-EXPORTED = sorted(list(_SIGS) + ["sfvos_last_error", "sfvos_last_kernel"])
+# size queries: host-only, return int64 byte counts
+_SIZE_SIGS = {
+    "sfvos_reduce_workspace_bytes": [i64, i64],
+    "sfvos_wgrad_simt_workspace_bytes": [ctypes.POINTER(WgradParams)],
+}
+
+EXPORTED = sorted(list(_SIGS) + list(_SIZE_SIGS) + ["sfvos_last_error", "sfvos_last_kernel"])
 _lib = None
 
 
@@ -100,6 +106,10 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = ctypes.c_int
+    for name, args in _SIZE_SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int64
     lib.sfvos_last_error.argtypes = []
     lib.sfvos_last_error.restype = ctypes.c_char_p
     lib.sfvos_last_kernel.argtypes = []

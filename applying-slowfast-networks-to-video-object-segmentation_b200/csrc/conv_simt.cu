@@ -1,6 +1,14 @@
-// fp32 CUDA-core implicit-GEMM convolution (fprop/dgrad) and weight gradient: the "fp32 validation mode" of the
+// CUDA-core implicit-GEMM convolution (fprop/dgrad) and weight gradient: the "fp32 validation mode" of the
 // north star (max-normalised error <= 1e-4 against the reference).  Same semantics as the tcgen05 kernels in
 // conv_umma.cu / wgrad_umma.cu, same packed-weight K ordering, but f32 activations and f32 [K][N] weights.
+//
+// Validation mode means two things here, both needed for a gradient check through ReLU layers to be meaningful:
+//   * products are accumulated in fp64 and rounded ONCE to the f32 result, so a pre-activation is the correctly
+//     rounded value of the exact sum over the stored f32 operands -- its sign cannot be an artefact of the order
+//     of an fp32 summation (a ReLU whose pre-activation sits at 1e-7 flips under fp32 accumulation noise, and one
+//     flipped mask moves single weight-gradient entries by ~1e-3 of the maximum);
+//   * no float atomics: split-K partial sums go to a caller-provided workspace and are reduced in a fixed order,
+//     so two runs are bit-identical.
 #include "common.cuh"
 
 namespace {
@@ -37,11 +45,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtArgs a) {
         ph = (int)(r % a.H); r /= a.H;
         pt = (int)(r % a.To); pb = (int)(r / a.To);
     }
-    float acc[4][4];
+    double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
     int tap = 0;
     for (int ta = 0; ta < a.kt; ++ta)
@@ -63,12 +71,12 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtArgs a) {
                     for (int k = 0; k < TK; ++k) {
                         const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
                         const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-                        const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
-                        const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+                        const double ar[4] = {a4.x, a4.y, a4.z, a4.w};
+                        const double br[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+                            for (int j = 0; j < 4; ++j) acc[i][j] = fma(ar[i], br[j], acc[i][j]);
                     }
                     __syncthreads();
                 }
@@ -85,29 +93,32 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtArgs a) {
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n >= a.N) continue;
-            float v = acc[i][j];
-            if (a.scale) v *= a.scale[n];
-            if (a.shift) v += a.shift[n];
-            if (a.relu) v = fmaxf(v, 0.f);
+            double v = acc[i][j];
+            if (a.scale) v *= (double)a.scale[n];
+            if (a.shift) v += (double)a.shift[n];
+            if (a.relu) v = fmax(v, 0.0);
             if (a.yf) {
                 float* d = a.yf + opix * a.y_cstride + n;
-                *d = a.accumulate ? (*d + v) : v;
+                *d = (float)(a.accumulate ? ((double)*d + v) : v);
             } else {
-                a.yb[opix * a.y_cstride + n] = __float2bfloat16(v);
+                a.yb[opix * a.y_cstride + n] = __float2bfloat16((float)v);
             }
         }
     }
 }
 
 struct WgArgs {
-    const float* x; const float* dy; float* dw;
+    const float* x; const float* dy; float* dw; double* partial;   // partial: [splits][taps*C*N] when splits > 1
     long long npix, pix_per_split;
     int B, T, H, W, C, To, N;
     long long x_cstride, x_hstride, x_tstride, x_bstride, dy_cstride, dy_hstride, dy_tstride, dy_bstride;
     int kt, kh, kw, pad_t, pad_h, pad_w, ctiles;
+    long long total;      // taps*C*N
 };
 
-// dw[tap][c][n] += sum_pix x[pix + tap offset][c] * dy[pix][n];  grid = (ctiles*ntiles, taps, splits)
+// dw[tap][c][n] += sum_pix x[pix + tap offset][c] * dy[pix][n];  grid = (ctiles*ntiles, taps, splits).
+// One split: the CTA owns its dw tile and adds to it directly.  Several splits: each writes its fp64 partial tile to the
+// workspace and wgrad_reduce_kernel sums them in split order (no atomics -> bit-reproducible).
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgArgs a) {
     __shared__ float As[TK][TM + 4];   // [pixel][c]
     __shared__ float Bs[TK][TN + 4];   // [pixel][n]
@@ -121,11 +132,11 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgArgs a) {
     if (p_end > a.npix) p_end = a.npix;
     const int tx = tid & 15, ty = tid >> 4;
     const int lk = tid >> 4, l4 = (tid & 15) * 4;   // loader: pixel row lk, 4 consecutive channels l4..
-    float acc[4][4];
+    double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     for (long long p0 = p_begin; p0 < p_end; p0 += TK) {
         const long long pix = p0 + lk;
         float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
@@ -146,12 +157,12 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgArgs a) {
         for (int k = 0; k < TK; ++k) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+            const double ar[4] = {a4.x, a4.y, a4.z, a4.w};
+            const double br[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(ar[i], br[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -162,8 +173,19 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < a.N) atomicAdd(a.dw + ((long long)tap * a.C + c) * a.N + n, acc[i][j]);
+            if (n >= a.N) continue;
+            const long long e = ((long long)tap * a.C + c) * a.N + n;
+            if (a.partial) a.partial[(long long)blockIdx.z * a.total + e] = acc[i][j];
+            else a.dw[e] = (float)((double)a.dw[e] + acc[i][j]);
         }
+    }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const double* __restrict__ partial, float* dw, long long total, int splits) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int z = 0; z < splits; ++z) s += partial[(long long)z * total + e];
+        dw[e] = (float)((double)dw[e] + s);
     }
 }
 
@@ -202,6 +224,25 @@ extern "C" int sfvos_conv_simt(const sfvos_conv_params* p, sfvos_stream stream_)
     return SFVOS_OK;
 }
 
+// split-K factor that fills the machine a few times over (the same on every call with the same shape)
+static long long wgrad_simt_splits(const sfvos_wgrad_params* p) {
+    const long long npix = p->B * p->To * p->H * p->W;
+    const long long base = ((p->C + TM - 1) / TM) * ((p->N + TN - 1) / TN) * (p->kt * p->kh * p->kw);
+    if (npix <= 0 || base <= 0) return 1;
+    long long splits = (8LL * sfvos_num_sms() + base - 1) / base;
+    const long long max_splits = (npix + 255) / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    return splits;
+}
+
+extern "C" int64_t sfvos_wgrad_simt_workspace_bytes(const sfvos_wgrad_params* p) {
+    if (p == nullptr) return 0;
+    const long long splits = wgrad_simt_splits(p);
+    return splits > 1 ? splits * (p->kt * p->kh * p->kw) * p->C * p->N * (long long)sizeof(double) : 0;
+}
+
 extern "C" int sfvos_wgrad_simt(const sfvos_wgrad_params* p, sfvos_stream stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     SF_CHECK(p != nullptr, "wgrad_simt: null params");
@@ -226,17 +267,25 @@ extern "C" int sfvos_wgrad_simt(const sfvos_wgrad_params* p, sfvos_stream stream
     a.ctiles = (a.C + TM - 1) / TM;
     const int ntn = (a.N + TN - 1) / TN;
     const int taps = a.kt * a.kh * a.kw;
-    long long base = (long long)a.ctiles * ntn * taps;
-    long long splits = (8LL * sfvos_num_sms() + base - 1) / base;
-    long long max_splits = (a.npix + 255) / 256;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    if (splits > 65535) splits = 65535;
+    long long splits = wgrad_simt_splits(p);
+    a.total = (long long)taps * a.C * a.N;
+    // split-K needs room for the fp64 partial tiles; without a (large enough) workspace every CTA walks all pixels
+    const long long ws_splits = p->workspace ? (long long)(p->workspace_bytes / (a.total * (long long)sizeof(double))) : 0;
+    if (splits > ws_splits) splits = ws_splits;
+    if (splits < 2) splits = 1;
+    SF_CHECK(p->workspace == nullptr || (reinterpret_cast<uintptr_t>(p->workspace) & 7) == 0, "wgrad_simt: workspace must be 8-byte aligned");
     a.pix_per_split = ((a.npix + splits - 1) / splits + TK - 1) / TK * TK;
     splits = (a.npix + a.pix_per_split - 1) / a.pix_per_split;
+    a.partial = splits > 1 ? reinterpret_cast<double*>(p->workspace) : nullptr;
     dim3 grid((unsigned)(a.ctiles * ntn), (unsigned)taps, (unsigned)splits);
     wgrad_simt_kernel<<<grid, 256, 0, stream>>>(a);
-    sfvos_set_kernel("wgrad_simt");
     SF_LAUNCH_CHECK();
+    if (splits > 1) {
+        long long g = (a.total + 255) / 256;
+        if (g > 8LL * sfvos_num_sms()) g = 8LL * sfvos_num_sms();
+        wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(a.partial, a.dw, a.total, (int)splits);
+        SF_LAUNCH_CHECK();
+    }
+    sfvos_set_kernel("wgrad_simt");
     return SFVOS_OK;
 }

@@ -153,12 +153,43 @@ __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NQ][8], int 
     }
 }
 
+// Deterministic variant of the reduction tail (fp32 validation mode): the CTA's per-channel sums are formed in a fixed
+// order in fp64 and written to partial[blockIdx.x][q][c]; reduce_partials_kernel then adds the CTAs' rows in index order.
+// No atomics anywhere, so the result does not depend on scheduling.
+template <int NQ>
+__device__ __forceinline__ void block_reduce_to_partial(double (&acc)[NQ][8], int g, int lane_pix, int G, int L,
+                                                        double* partial, double* smem) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (g < G && lane_pix < L) smem[(q * L + lane_pix) * G * 8 + g * 8 + j] = acc[q][j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NQ * G * 8; i += blockDim.x) {
+        const int q = i / (G * 8), c = i - q * G * 8;
+        double s = 0.0;
+        for (int l = 0; l < L; ++l) s += smem[(q * L + l) * G * 8 + c];
+        partial[(long long)blockIdx.x * NQ * G * 8 + i] = s;
+    }
+}
+
+// out[i] = sum over CTAs (in index order) of partial[cta][i], i < n; OutT = double (BN statistics) or float (backward sums)
+template <typename OutT>
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_ctas, int n, OutT* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < n_ctas; ++b) s += partial[(long long)b * n + i];
+    out[i] = static_cast<OutT>(s);
+}
+
+// fp32 validation mode: fp64 sums (|mean| >> std must not cancel), fixed reduction order
 __global__ void __launch_bounds__(RED_THREADS)
-channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long long cstride, float* sum, float* sumsq, int ppc) {
-    extern __shared__ float red_smem[];
+channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long long cstride, double* partial, int ppc) {
+    extern __shared__ double red_smem_d[];
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
-    float acc[2][8] = {};
+    double acc[2][8] = {};
     const long long p0 = (long long)blockIdx.x * ppc;
     long long p1 = p0 + ppc; if (p1 > npix) p1 = npix;
     if (lp < L)
@@ -166,21 +197,22 @@ channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long lo
             float v[8];
             load8(x + p * cstride + g * 8, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
+            for (int j = 0; j < 8; ++j) { const double d = v[j]; acc[0][j] += d; acc[1][j] = fma(d, d, acc[1][j]); }
         }
-    float* const dst[2] = {sum, sumsq};
-    block_reduce_to_global<2>(acc, g, lp, G, L, dst, red_smem);
+    block_reduce_to_partial<2>(acc, g, lp, G, L, partial, red_smem_d);
 }
 
-template <typename DyT>
+// AccT = float: per-CTA sums merged into ``sums`` with atomics (product path).  AccT = double: fp64 sums written to
+// ``partial`` for the fixed-order merge (validation mode).
+template <typename DyT, typename AccT>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, int relu, long long npix, int C, float* sums, int ppc) {
-    extern __shared__ float red_smem[];
+                     const float* __restrict__ rstd, int relu, long long npix, int C, float* sums, double* partial, int ppc) {
+    extern __shared__ double red_smem_d[];
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
-    float acc[2][8] = {};
+    AccT acc[2][8] = {};
     float sc[8], sh[8], mu[8], rs[8];
     if (lp < L) {
 #pragma unroll
@@ -200,19 +232,23 @@ bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const flo
             for (int j = 0; j < 8; ++j) {
                 const float dm = (relu && fmaf(v0[j], sc[j], sh[j]) <= 0.f) ? 0.f : d0[j];
                 acc[0][j] += dm;
-                acc[1][j] = fmaf(dm, (v0[j] - mu[j]) * rs[j], acc[1][j]);
+                acc[1][j] += (AccT)dm * ((AccT)(v0[j] - mu[j]) * (AccT)rs[j]);
             }
             if (two) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float dm = (relu && fmaf(v1[j], sc[j], sh[j]) <= 0.f) ? 0.f : d1[j];
                     acc[0][j] += dm;
-                    acc[1][j] = fmaf(dm, (v1[j] - mu[j]) * rs[j], acc[1][j]);
+                    acc[1][j] += (AccT)dm * ((AccT)(v1[j] - mu[j]) * (AccT)rs[j]);
                 }
             }
         }
-    float* const dst[2] = {sums, sums + C};
-    block_reduce_to_global<2>(acc, g, lp, G, L, dst, red_smem);
+    if constexpr (sizeof(AccT) == 8) {
+        block_reduce_to_partial<2>(acc, g, lp, G, L, partial, red_smem_d);
+    } else {
+        float* const dst[2] = {sums, sums + C};
+        block_reduce_to_global<2>(acc, g, lp, G, L, dst, reinterpret_cast<float*>(red_smem_d));
+    }
 }
 
 // dx = k1*dm - k2 - k3*(x - mean) with k1 = gamma*rstd, k2 = k1*sum(dm)/n, k3 = k1*rstd*sum(dm*xhat)/n.
@@ -222,14 +258,17 @@ __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, int relu, long long npix, int C,
-                    const float* __restrict__ sums, DxT* dx, long long dx_cstride, float* dgamma, float* dbeta, int ppc) {
+                    const float* __restrict__ sums, DxT* dx, long long dx_cstride, float* dgamma, float* dbeta,
+                    int fixed_stats, float* dbias, int ppc) {
     const int G = C / 8, L = RED_THREADS / G;
     const int g = threadIdx.x % G, lp = threadIdx.x / G;
-    const float inv_n = 1.0f / (float)npix;
+    // fixed_stats (eval-mode BN: mean / rstd are constants, not functions of x): dx = gamma*rstd*dm, nothing else
+    const float inv_n = fixed_stats ? 0.f : 1.0f / (float)npix;
     if (blockIdx.x == 0 && dgamma != nullptr)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {     // atomics: pyramid levels on different streams share these accumulators
             atomicAdd(dbeta + c, sums[c]);
             atomicAdd(dgamma + c, sums[C + c]);
+            if (fixed_stats && dbias != nullptr) atomicAdd(dbias + c, gamma[c] * rstd[c] * sums[c]);   // = sum over pixels of dx
         }
     if (lp >= L) return;
     float sc[8], sh[8], mu[8], k1[8], k2[8], k3[8];
@@ -321,15 +360,19 @@ affine_act_kernel(const XT* __restrict__ x, long long x_cstride, YT* y, long lon
     }
 }
 
-__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, double count, const float* conv_bias,
+__device__ __forceinline__ double stat_at(const void* p, int f64, int c) {
+    return f64 ? reinterpret_cast<const double*>(p)[c] : (double)reinterpret_cast<const float*>(p)[c];
+}
+
+__global__ void bn_finalize_kernel(const void* sum, const void* sumsq, int stats_f64, double count, const float* conv_bias,
                                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                                    long long* nbt, double momentum, double eps, float* scale, float* shift, float* mean,
                                    float* rstd, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt != nullptr) *nbt += 1;
     if (c >= C) return;
-    const double m = (double)sum[c] / count;
-    double var = (double)sumsq[c] / count - m * m;
+    const double m = stat_at(sum, stats_f64, c) / count;
+    double var = stat_at(sumsq, stats_f64, c) / count - m * m;
     if (var < 0.0) var = 0.0;
     const double rs = 1.0 / sqrt(var + eps);
     const double g = gamma[c];
@@ -356,8 +399,9 @@ __global__ void bn_running_update_kernel(const sfvos_bn_running_params p) {
     float rm = p.running_mean[c], rv = p.running_var[c];
     for (int i = 0; i < p.n_calls; ++i) {
         const double count = p.count[i];
-        const double m = (double)p.sum[i][c] / count;
-        double var = (double)p.sumsq[i][c] / count - m * m;
+        const int f64 = p.stats_dtype == SFVOS_F64;
+        const double m = stat_at(p.sum[i], f64, c) / count;
+        double var = stat_at(p.sumsq[i], f64, c) / count - m * m;
         if (var < 0.0) var = 0.0;
         const double mb = m + (p.conv_bias ? (double)p.conv_bias[c] : 0.0);
         const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -369,12 +413,16 @@ __global__ void bn_running_update_kernel(const sfvos_bn_running_params p) {
 }
 
 __global__ void bn_fold_eval_kernel(const float* conv_bias, const float* gamma, const float* beta, const float* rm,
-                                    const float* rv, double eps, float* scale, float* shift, int C) {
+                                    const float* rv, double eps, float* scale, float* shift, float* mean, float* rstd, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double s = (double)gamma[c] / sqrt((double)rv[c] + eps);
+    const double rs = 1.0 / sqrt((double)rv[c] + eps);
+    const double s = (double)gamma[c] * rs;
+    const double b = conv_bias ? (double)conv_bias[c] : 0.0;
     scale[c] = (float)s;
-    shift[c] = (float)((double)beta[c] + ((conv_bias ? (double)conv_bias[c] : 0.0) - (double)rm[c]) * s);
+    shift[c] = (float)((double)beta[c] + (b - (double)rm[c]) * s);
+    if (mean != nullptr) mean[c] = (float)((double)rm[c] - b);      // in terms of the bias-free conv output
+    if (rstd != nullptr) rstd[c] = (float)rs;
 }
 
 // ---- layout -----------------------------------------------------------------------------------------------------
@@ -541,26 +589,47 @@ static inline int pick_ppc(long long npix, int base) {
     while (ppc > 32 && (npix + ppc - 1) / ppc < want) ppc >>= 1;
     return ppc;
 }
-static inline size_t red_smem_bytes(int nq, int C) { return (size_t)nq * (RED_THREADS / (C / 8)) * C * sizeof(float); }
+static inline size_t red_smem_bytes(int nq, int C, size_t esz = sizeof(float)) { return (size_t)nq * (RED_THREADS / (C / 8)) * C * esz; }
 
-extern "C" int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride, float* sum, float* sumsq,
-                                   sfvos_stream stream) {
+// grid of the per-channel reductions (channel_stats, bn_bwd_reduce) = rows of fp64 partials the deterministic mode needs
+static inline int red_grid(long long npix, int C, int* ppc_out) {
+    const int ppc = pick_ppc(npix, red_ppc(C));
+    if (ppc_out) *ppc_out = ppc;
+    return (int)((npix + ppc - 1) / ppc);
+}
+
+extern "C" int64_t sfvos_reduce_workspace_bytes(int64_t npix, int64_t C) {
+    if (npix <= 0 || C <= 0 || C % 8) return 0;
+    return (int64_t)red_grid(npix, (int)C, nullptr) * 2 * C * (int64_t)sizeof(double);
+}
+
+extern "C" int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride, double* stats,
+                                   void* workspace, int64_t workspace_bytes, sfvos_stream stream) {
     CHECK_C8(C);
     SF_CHECK(cstride % 4 == 0, "channel_stats: cstride must be a multiple of 4");
+    SF_CHECK(C <= 512, "channel_stats: at most 512 channels (fp64 staging in shared memory)");
     if (npix == 0) return SFVOS_OK;
-    const int ppc = pick_ppc(npix, red_ppc((int)C));
-    const int grid = (int)((npix + ppc - 1) / ppc);
-    channel_stats_kernel<<<grid, RED_THREADS, red_smem_bytes(2, (int)C), CS(stream)>>>(x, npix, (int)C, cstride, sum, sumsq, ppc);
+    int ppc;
+    const int grid = red_grid(npix, (int)C, &ppc);
+    SF_CHECK(workspace != nullptr && workspace_bytes >= sfvos_reduce_workspace_bytes(npix, C) &&
+             (reinterpret_cast<uintptr_t>(workspace) & 7) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+             "channel_stats: needs an 8-byte aligned workspace of sfvos_reduce_workspace_bytes(npix, C) = %lld bytes",
+             (long long)sfvos_reduce_workspace_bytes(npix, C));
+    double* partial = reinterpret_cast<double*>(workspace);
+    channel_stats_kernel<<<grid, RED_THREADS, red_smem_bytes(2, (int)C, sizeof(double)), CS(stream)>>>(x, npix, (int)C, cstride, partial, ppc);
+    SF_LAUNCH_CHECK();
+    reduce_partials_kernel<double><<<(int)((2 * C + 127) / 128), 128, 0, CS(stream)>>>(partial, grid, (int)(2 * C), stats);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
 
-extern "C" int sfvos_bn_finalize(const float* sum, const float* sumsq, double count, const float* conv_bias,
+extern "C" int sfvos_bn_finalize(const void* sum, const void* sumsq, int32_t stats_dtype, double count, const float* conv_bias,
                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
                                  int64_t* num_batches_tracked, double momentum, double eps, float* scale, float* shift,
                                  float* mean, float* rstd, int64_t C, sfvos_stream stream) {
     SF_CHECK(count > 0, "bn_finalize: empty batch");
-    bn_finalize_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(sum, sumsq, count, conv_bias, gamma, beta,
+    SF_CHECK(stats_dtype == SFVOS_F32 || stats_dtype == SFVOS_F64, "bn_finalize: statistics are f32 or f64");
+    bn_finalize_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(sum, sumsq, stats_dtype == SFVOS_F64, count, conv_bias, gamma, beta,
         running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, mean, rstd, (int)C);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
@@ -569,6 +638,7 @@ extern "C" int sfvos_bn_finalize(const float* sum, const float* sumsq, double co
 extern "C" int sfvos_bn_running_update(const sfvos_bn_running_params* p, sfvos_stream stream) {
     SF_CHECK(p != nullptr && p->n_calls >= 1 && p->n_calls <= SFVOS_BN_MAX_CALLS, "bn_running_update: 1..%d calls", SFVOS_BN_MAX_CALLS);
     SF_CHECK(p->running_mean != nullptr && p->running_var != nullptr, "bn_running_update: running buffers required");
+    SF_CHECK(p->stats_dtype == SFVOS_F32 || p->stats_dtype == SFVOS_F64, "bn_running_update: statistics are f32 or f64");
     for (int i = 0; i < p->n_calls; ++i) SF_CHECK(p->count[i] > 0 && p->sum[i] && p->sumsq[i], "bn_running_update: empty call %d", i);
     bn_running_update_kernel<<<(int)((p->C + 127) / 128), 128, 0, CS(stream)>>>(*p);
     SF_LAUNCH_CHECK();
@@ -576,9 +646,9 @@ extern "C" int sfvos_bn_running_update(const sfvos_bn_running_params* p, sfvos_s
 }
 
 extern "C" int sfvos_bn_fold_eval(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
-                                  const float* running_var, double eps, float* scale, float* shift, int64_t C,
-                                  sfvos_stream stream) {
-    bn_fold_eval_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(conv_bias, gamma, beta, running_mean, running_var, eps, scale, shift, (int)C);
+                                  const float* running_var, double eps, float* scale, float* shift, float* mean,
+                                  float* rstd, int64_t C, sfvos_stream stream) {
+    bn_fold_eval_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(conv_bias, gamma, beta, running_mean, running_var, eps, scale, shift, mean, rstd, (int)C);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -604,17 +674,32 @@ extern "C" int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstrid
 
 extern "C" int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
                                    const float* scale, const float* shift, const float* mean, const float* rstd,
-                                   int32_t relu, int64_t npix, int64_t C, float* sums, sfvos_stream stream) {
+                                   int32_t relu, int64_t npix, int64_t C, float* sums, void* workspace,
+                                   int64_t workspace_bytes, sfvos_stream stream) {
     CHECK_C8(C);
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0, "bn_bwd_reduce: strides must be multiples of 8");
     if (npix == 0) return SFVOS_OK;
-    const int ppc = pick_ppc(npix, red_ppc((int)C));
-    const int grid = (int)((npix + ppc - 1) / ppc);
+    int ppc;
+    const int grid = red_grid(npix, (int)C, &ppc);
+    if (workspace != nullptr) {
+        // validation mode: fp64 partial rows + fixed-order merge; ``sums`` is overwritten (not accumulated into)
+        SF_CHECK(dy_dtype == SFVOS_F32 && C <= 512, "bn_bwd_reduce: the deterministic mode takes f32 gradients, <= 512 channels");
+        SF_CHECK(workspace_bytes >= sfvos_reduce_workspace_bytes(npix, C) && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
+                 "bn_bwd_reduce: workspace needs sfvos_reduce_workspace_bytes(npix, C) = %lld bytes, 8-byte aligned",
+                 (long long)sfvos_reduce_workspace_bytes(npix, C));
+        double* partial = reinterpret_cast<double*>(workspace);
+        bn_bwd_reduce_kernel<float, double><<<grid, RED_THREADS, red_smem_bytes(2, (int)C, sizeof(double)), CS(stream)>>>(
+            reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, partial, ppc);
+        SF_LAUNCH_CHECK();
+        reduce_partials_kernel<float><<<(int)((2 * C + 127) / 128), 128, 0, CS(stream)>>>(partial, grid, (int)(2 * C), sums);
+        SF_LAUNCH_CHECK();
+        return SFVOS_OK;
+    }
     const size_t sm = red_smem_bytes(2, (int)C);
     if (dy_dtype == SFVOS_F32)
-        bn_bwd_reduce_kernel<float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, ppc);
+        bn_bwd_reduce_kernel<float, float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, nullptr, ppc);
     else
-        bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, ppc);
+        bn_bwd_reduce_kernel<__nv_bfloat16, float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, nullptr, ppc);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -622,7 +707,8 @@ extern "C" int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_
 extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
                                   const float* scale, const float* shift, const float* mean, const float* rstd,
                                   const float* gamma, int32_t relu, int64_t npix, int64_t C, const float* sums, void* dx,
-                                  int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, sfvos_stream stream) {
+                                  int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, int32_t fixed_stats,
+                                  float* dbias, sfvos_stream stream) {
     CHECK_C8(C);
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0 && dx_cstride % 8 == 0, "bn_bwd_apply: strides must be multiples of 8");
     SF_CHECK((dgamma == nullptr) == (dbeta == nullptr), "bn_bwd_apply: dgamma and dbeta go together");
@@ -630,7 +716,7 @@ extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_c
     const int ppc = pick_ppc(npix, 512);
     const int grid = (int)((npix + ppc - 1) / ppc);
     using bf = __nv_bfloat16;
-#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta, ppc)
+#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta, fixed_stats, dbias, ppc)
     if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float);
     else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf);
     else if (dx_dtype == SFVOS_F32) LAUNCH(bf, float);

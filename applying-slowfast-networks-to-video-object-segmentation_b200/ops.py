@@ -1,11 +1,12 @@
 """Torch-facing wrappers over the C ABI (include/sfvos.h).  torch is used only for device memory and streams;
 every arithmetic kernel is in libsfvos.so.  All wrappers require CUDA tensors and raise otherwise (no fallback)."""
 import ctypes
+import functools
 
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, ConvParams, RoiParams, WgradParams, call
+from ._lib import BF16, F32, F64, ConvParams, RoiParams, WgradParams, call
 
 
 TIMING = None   # bench.py sets this to a list: every conv / wgrad launch then appends (kernel, flops, start, end)
@@ -13,6 +14,37 @@ TIMING = None   # bench.py sets this to a list: every conv / wgrad launch then a
 
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _find_cuda(obj, depth=0):
+    if torch.is_tensor(obj):
+        return obj if obj.is_cuda else None
+    if depth < 3:
+        if isinstance(obj, dict):
+            obj = tuple(obj.values())
+        if isinstance(obj, (list, tuple)):
+            for o in obj:
+                t = _find_cuda(o, depth + 1)
+                if t is not None:
+                    return t
+    return None
+
+
+def device_guard(fn):
+    """Run ``fn`` with the CUDA device of its first CUDA tensor argument current.  libsfvos launches on the CURRENT device
+    (``stream()`` above, sfvos_device_check, the TMA descriptors and the SM count all follow it), while the reference API
+    lets a module live on any device (``SlowFastLayers(256, device='cuda:1', ...)``): every entry that launches kernels -
+    the autograd Function forward/backward methods and the free functions of roi_heads - is wrapped with this."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _find_cuda(args)
+        if t is None and kwargs:
+            t = _find_cuda(tuple(kwargs.values()))
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _timed_call(kernel, flops, name, params):
@@ -166,43 +198,68 @@ def wgrad(x, dy, k, pad, dw, *, umma, dy_strides=None):
     p.kt, p.kh, p.kw = k
     p.pad_t, p.pad_h, p.pad_w = pad
     p.dw = _p(dw)
+    if not umma:
+        # validation mode: fp64 split-K partials reduced in a fixed order need scratch (the caller owns all memory)
+        nbytes = _lib.load().sfvos_wgrad_simt_workspace_bytes(ctypes.byref(p))
+        if nbytes:
+            ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dw.device)
+            p.workspace, p.workspace_bytes = _p(ws), nbytes
     flops = 2.0 * x.B * dy.T * x.H * x.W * dy.C * x.C * k[0] * k[1] * k[2]
     _timed_call("wgrad_umma" if umma else "wgrad_simt", flops, "sfvos_wgrad_umma" if umma else "sfvos_wgrad_simt", p)
 
 
+def _reduce_workspace(npix, C, device):
+    nbytes = _lib.load().sfvos_reduce_workspace_bytes(npix, C)
+    return torch.empty(max(1, nbytes // 8), dtype=torch.float64, device=device), nbytes
+
+
 def channel_stats(x, stats):
-    assert x.dtype == torch.float32
-    call("sfvos_channel_stats", x.ptr(), x.npix, x.C, x.cstride, _p(stats), _p(stats, x.C * 4), stream())
+    """stats: f64 [2C] <- per-channel (sums, sums of squares) of the f32 activation x; fixed reduction order."""
+    assert x.dtype == torch.float32 and stats.dtype == torch.float64 and stats.numel() >= 2 * x.C
+    if x.npix == 0:
+        stats.zero_()
+        return
+    ws, nbytes = _reduce_workspace(x.npix, x.C, x.buf.device)
+    call("sfvos_channel_stats", x.ptr(), x.npix, x.C, x.cstride, _p(stats), _p(ws), nbytes, stream())
+
+
+def _stats_dtype(stats):
+    return (F64, 8) if stats.dtype == torch.float64 else (F32, 4)
 
 
 def bn_finalize(stats, count, conv_bias, gamma, beta, running_mean, running_var, nbt, momentum, eps, out4):
-    """out4: f32 [4,C] = (scale, shift, mean, rstd)."""
+    """stats: [2C] (sum, sumsq), f32 (umma epilogues) or f64 (channel_stats); out4: f32 [4,C] = (scale, shift, mean, rstd)."""
     C = gamma.numel()
-    call("sfvos_bn_finalize", _p(stats), _p(stats, C * 4), float(count), _p(conv_bias), _p(gamma), _p(beta),
+    code, esz = _stats_dtype(stats)
+    call("sfvos_bn_finalize", _p(stats), _p(stats, C * esz), code, float(count), _p(conv_bias), _p(gamma), _p(beta),
          _p(running_mean), _p(running_var), _p(nbt), float(momentum), float(eps),
          _p(out4), _p(out4, C * 4), _p(out4, 2 * C * 4), _p(out4, 3 * C * 4), C, stream())
 
 
 def bn_running_update(calls, conv_bias, running_mean, running_var, nbt, momentum):
-    """calls: list of (stats f32 [2C] = (sum, sumsq), count) in forward-call order (see sfvos_bn_running_update)."""
+    """calls: list of (stats [2C] = (sum, sumsq), f32 or f64, count) in forward-call order (see sfvos_bn_running_update)."""
     C = running_mean.numel()
     for i in range(0, len(calls), _lib.BN_MAX_CALLS):
         part = calls[i:i + _lib.BN_MAX_CALLS]
         p = _lib.BnRunningParams()
+        code, esz = _stats_dtype(part[0][0])
         for j, (stats, count) in enumerate(part):
+            assert _stats_dtype(stats)[0] == code
             p.sum[j] = stats.data_ptr()
-            p.sumsq[j] = stats.data_ptr() + C * 4
+            p.sumsq[j] = stats.data_ptr() + C * esz
             p.count[j] = float(count)
-        p.n_calls = len(part)
+        p.n_calls = len(part); p.stats_dtype = code
         p.conv_bias = _p(conv_bias); p.running_mean = _p(running_mean); p.running_var = _p(running_var)
         p.num_batches_tracked = _p(nbt); p.momentum = float(momentum); p.C = C
         call("sfvos_bn_running_update", ctypes.byref(p), stream())
 
 
-def bn_fold_eval(conv_bias, gamma, beta, running_mean, running_var, eps, out2):
+def bn_fold_eval(conv_bias, gamma, beta, running_mean, running_var, eps, out):
+    """out: f32 [2C] = (scale, shift), or [4C] = (scale, shift, mean, rstd) like bn_finalize's (for the eval-mode backward)."""
     C = gamma.numel()
+    full = out.numel() >= 4 * C
     call("sfvos_bn_fold_eval", _p(conv_bias), _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps),
-         _p(out2), _p(out2, C * 4), C, stream())
+         _p(out), _p(out, C * 4), _p(out, 2 * C * 4) if full else None, _p(out, 3 * C * 4) if full else None, C, stream())
 
 
 def affine_act(x, y, scale, shift, relu):
@@ -210,17 +267,21 @@ def affine_act(x, y, scale, shift, relu):
          int(relu), x.npix, x.C, stream())
 
 
-def bn_bwd(dy, raw, bn4, gamma, relu, dx, dgamma, dbeta, sums=None):
+def bn_bwd(dy, raw, bn4, gamma, relu, dx, dgamma, dbeta, sums=None, deterministic=False, fixed_stats=False, dbias=None):
     """dy, raw (f32), dx: Acts over the same pixels; bn4 = (scale, shift, mean, rstd) [4,C]; ``sums``: optional
-    zero-filled f32 [2C] scratch."""
+    zero-filled f32 [2C] scratch.  ``deterministic`` (validation mode, f32 dy): the two per-channel sums are formed in
+    fp64 in a fixed order instead of with float atomics.  ``fixed_stats``: eval-mode BatchNorm (bn4 from bn_fold_eval): the
+    statistics are constants, dx = gamma*rstd*dy_m, and ``dbias`` receives the conv-bias gradient."""
     C = raw.C
     if sums is None:
         sums = torch.zeros(2 * C, dtype=torch.float32, device=raw.buf.device)
     sc, sh, mu, rs = _p(bn4), _p(bn4, C * 4), _p(bn4, 2 * C * 4), _p(bn4, 3 * C * 4)
+    ws, nbytes = _reduce_workspace(raw.npix, C, raw.buf.device) if deterministic and raw.npix else (None, 0)
     call("sfvos_bn_bwd_reduce", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), raw.cstride, sc, sh, mu, rs, int(relu),
-         raw.npix, C, _p(sums), stream())
+         raw.npix, C, _p(sums), _p(ws), nbytes, stream())
     call("sfvos_bn_bwd_apply", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), raw.cstride, sc, sh, mu, rs, _p(gamma),
-         int(relu), raw.npix, C, _p(sums), dx.ptr(), dt(dx.buf), dx.cstride, _p(dgamma), _p(dbeta), stream())
+         int(relu), raw.npix, C, _p(sums), dx.ptr(), dt(dx.buf), dx.cstride, _p(dgamma), _p(dbeta), int(fixed_stats),
+         _p(dbias), stream())
 
 
 def relu_bwd(dy, y, dx, dbias):

@@ -68,6 +68,7 @@ def _to_cl_act(x, dtype):
 # ----------------------------------------------------------------------------------------------------------------------
 class _RoiAlignFn(torch.autograd.Function):
     @staticmethod
+    @ops.device_guard
     def forward(ctx, rois, levels, scales, P, sr, out_nchw, out_dtype, *feats):
         ops.device_check()
         N, C = feats[0].shape[:2]
@@ -92,6 +93,7 @@ class _RoiAlignFn(torch.autograd.Function):
         return out if out_nchw else out.permute(0, 3, 1, 2)
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, g):
         rois, levels = ctx.saved_tensors
         shapes, scales, N, C, P, sr, out_nchw, dtypes = ctx.meta
@@ -139,6 +141,7 @@ class MultiScaleRoIAlign(nn.Module):
         self.k_min = int(-math.log2(self.scales[0]))
         self.k_max = int(-math.log2(self.scales[-1]))
 
+    @ops.device_guard
     def _prepare(self, x, boxes, image_shapes):
         """-> (feature maps, rois [K,5] = (image idx, x1, y1, x2, y2), level ids)."""
         feats = [v for k, v in x.items() if k in self.featmap_names]
@@ -170,6 +173,7 @@ class _RoiAlignPairFn(torch.autograd.Function):
     to add (a fill plus a read-read-write pass over every pyramid level saved)."""
 
     @staticmethod
+    @ops.device_guard
     def forward(ctx, specs, *feats):
         ops.device_check()
         ctx.set_materialize_grads(False)
@@ -195,6 +199,7 @@ class _RoiAlignPairFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, *gs):
         shapes, N, C, dtypes = ctx.meta
         dev = next(g for g in gs if g is not None).device
@@ -234,6 +239,7 @@ def _pack(w, mode, umma, kc, tap=(0, 0)):
 
 class _MaskHeadFn(torch.autograd.Function):
     @staticmethod
+    @ops.device_guard
     def forward(ctx, x, precision, *wb):
         ops.device_check()
         umma = precision != "fp32"
@@ -254,6 +260,7 @@ class _MaskHeadFn(torch.autograd.Function):
         return _nchw_view(cur.buf, K, H, W, cur.C)
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, g):
         wb = ctx.saved_tensors
         acts, umma, dt_act = ctx.acts, ctx.umma, ctx.dt_act
@@ -342,11 +349,13 @@ class _MaskPredictorFn(torch.autograd.Function):
         return torch.cat(parts, dim=1).contiguous() if umma else torch.cat(parts, dim=0)
 
     @staticmethod
+    @ops.device_guard
     def forward(ctx, x, precision, wt, bt, wl, bl):
         ops.device_check()
         umma = precision != "fp32"
         dt_act = _act_dtype(precision)
         K, C, H, W = x.shape
+        assert H == W, f"MaskRCNNPredictor: square ROI features only (the logits kernels take one side length), got {H}x{W}"
         co = wt.shape[1]
         n_cls = wl.shape[0]
         assert not umma or (C % 64 == 0 and co % 64 == 0), "conv5_mask channels must be multiples of 64 on the tensor-core path"
@@ -364,6 +373,7 @@ class _MaskPredictorFn(torch.autograd.Function):
         return logits
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, glogits):
         wt, bt, wl, bl = ctx.saved_tensors
         xin, up = ctx.acts
@@ -412,6 +422,7 @@ class MaskRCNNPredictor(tv_mask_rcnn.MaskRCNNPredictor):
 # ----------------------------------------------------------------------------------------------------------------------
 class _MaskBceFn(torch.autograd.Function):
     @staticmethod
+    @ops.device_guard
     def forward(ctx, logits, labels, targets):
         K, n_cls, S, _ = logits.shape
         logits = logits.float().contiguous()
@@ -421,6 +432,7 @@ class _MaskBceFn(torch.autograd.Function):
         return loss[0]
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, g):
         logits, labels, targets = ctx.saved_tensors
         K, n_cls, S, _ = logits.shape
@@ -430,6 +442,7 @@ class _MaskBceFn(torch.autograd.Function):
         return gl, None, None
 
 
+@ops.device_guard
 def project_masks_on_boxes(gt_masks, boxes, matched_idxs, M):
     """TV roi_heads.py:85-97 on the GPU: adaptive-sampling ROIAlign of the u8 GT masks to M x M."""
     rois = torch.cat([matched_idxs[:, None].to(boxes), boxes], dim=1).float().contiguous()
@@ -456,6 +469,7 @@ def maskrcnn_loss(mask_logits, proposals, gt_masks, gt_labels, mask_matched_idxs
     return _MaskBceFn.apply(mask_logits, labels.to(torch.int64).contiguous(), targets.contiguous())
 
 
+@ops.device_guard
 def maskrcnn_inference(x, labels):
     """TV roi_heads.py:56-82: sigmoid of the predicted-class channel, split per image."""
     per_img = [lab.shape[0] for lab in labels]
@@ -517,6 +531,7 @@ def _as_rows(x, dt_act):
 
 class _BoxHeadFn(torch.autograd.Function):
     @staticmethod
+    @ops.device_guard
     def forward(ctx, x, precision, w6, b6, w7, b7):
         ops.device_check()
         umma = precision != "fp32"
@@ -530,6 +545,7 @@ class _BoxHeadFn(torch.autograd.Function):
         return y7.buf.view(xin.W, w7.shape[0])
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, g):
         w6, b6, w7, b7 = ctx.saved_tensors
         xin, y6, y7 = ctx.acts
@@ -570,6 +586,7 @@ class _BoxPredictorFn(torch.autograd.Function):
     [n_cls, 5 n_cls) the box deltas; zero rows pad the output to a tensor-core tile.  Returns f32 [M, Npad]."""
 
     @staticmethod
+    @ops.device_guard
     def forward(ctx, x, precision, wc, bc, wb, bb):
         ops.device_check()
         umma = precision != "fp32"
@@ -591,6 +608,7 @@ class _BoxPredictorFn(torch.autograd.Function):
         return y.buf.view(xin.W, n_pad)
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, g):
         wc, bc, wb, bb = ctx.saved_tensors
         xin, w = ctx.acts
@@ -598,9 +616,9 @@ class _BoxPredictorFn(torch.autograd.Function):
         M, dev = xin.W, g.device
         nc, nb = wc.shape[0], wb.shape[0]
         g32 = _rows_act(g.float().contiguous())
-        stats = torch.zeros(2, n_pad, dtype=torch.float32, device=dev)     # row 0 = column sums = the bias gradients
+        stats = torch.zeros(2, n_pad, dtype=torch.float64, device=dev)     # row 0 = column sums = the bias gradients
         if M:
-            ops.channel_stats(g32, stats)
+            ops.channel_stats(g32, stats.view(-1))
         if umma:
             dy = Act.empty(1, 1, 1, M, n_pad, dt_act, dev)
             if M:
@@ -631,6 +649,7 @@ class FastRCNNPredictor(tv_faster_rcnn.FastRCNNPredictor):
 
 class _FastRCNNLossFn(torch.autograd.Function):
     @staticmethod
+    @ops.device_guard
     def forward(ctx, class_logits, box_regression, labels, regression_targets, beta):
         ops.device_check()
         M, n_cls = class_logits.shape
@@ -647,6 +666,7 @@ class _FastRCNNLossFn(torch.autograd.Function):
         return losses[0].clone(), losses[1].clone()
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, g_cls, g_box):
         cls, box, labels, tgt = ctx.saved_tensors
         M, n_cls = cls.shape
@@ -737,6 +757,7 @@ class RoIHeads(tv_roi_heads.RoIHeads):
 # ----------------------------------------------------------------------------------------------------------------------
 # mask paste-back (the step after the path: code/helpers/model.py:347 -> transform.postprocess)
 # ----------------------------------------------------------------------------------------------------------------------
+@ops.device_guard
 def paste_masks_in_image(masks, boxes, img_shape, padding=1):
     """Same signature and values as torchvision's paste_masks_in_image (TV roi_heads.py:474-501): masks [K,1,M,M], boxes
     [K,4] in output-image pixels -> [K,1,im_h,im_w].  One kernel for all K masks instead of a Python loop per mask."""

@@ -138,14 +138,14 @@ class SlowFastLayers(nn.Module):
 
     # ---- reference API ------------------------------------------------------------------------------------------------
     def fuse(self, slow, fast, conv, bn):
-        """Kept for API parity (model.py:111-116).  The fused pipeline never calls it; provided for callers that do:
-        runs the lateral conv+BN+ReLU and concatenates on the channel axis."""
-        name = next(n for n, s in self._specs.items() if getattr(self, n) is conv)
-        spec = self._specs[name]
-        f = _to_act(fast, self._act_dtype)
-        out = Act.empty(f.B, f.T - spec.kt + 1, f.H, f.W, 64, torch.float32, fast.device)
-        _conv_bn_forward(self, spec, f, out, self.training, None)
-        lateral = out.as_nchw().reshape(f.B, out.T, 64, f.H, f.W).permute(0, 2, 1, 3, 4)
+        """model.py:111-116: ``(cat([slow, relu(bn(conv(fast)))], 1), fast)`` for one of the two lateral connections
+        (``conv`` / ``bn`` = ``self.conv_f2s{1,2}`` / ``self.bn_f2s{1,2}``).  The fused pipeline (forward /
+        temporally_enhance_features) never calls it - there the lateral convolution writes straight into channels 192..255
+        of the slow buffer - but it is part of the reference's interface, so it is a differentiable op of its own here."""
+        name = next((n for n in self._specs if getattr(self, n) is conv), None)
+        if name is None or getattr(self, self._specs[name].bn) is not bn:
+            raise ValueError("fuse: conv / bn must be one of this module's lateral pairs (conv_f2s1, bn_f2s1) / (conv_f2s2, bn_f2s2)")
+        lateral = _FuseFn.apply(self, name, torch.is_grad_enabled(), fast, conv.weight, bn.weight, bn.bias)
         return torch.cat([slow, lateral.to(slow.dtype)], 1), fast
 
     def forward(self, slow, fast):
@@ -198,8 +198,11 @@ class SlowFastLayers(nn.Module):
         only the part of a window that the given frames do not cover is zero-filled."""
         if self.training:
             raise RuntimeError("temporally_enhance_sequence needs eval mode: train-mode BatchNorm statistics are per window")
-        ops.device_check()
         dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
+        if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):                    # libsfvos launches on the current device
+                return self.temporally_enhance_sequence(frame_features, max_frames, halo)
+        ops.device_check()
         sp, fp = self.slow_pathway_size, self.fast_pathway_size
         lo, hi = fp // 2, fp - fp // 2 - 1                  # zero frames before / after the sequence
         s_off = fp // 2 - sp // 2                           # first slow frame inside a fast window (_slice_features)
@@ -328,7 +331,7 @@ def _apply_deferred_running_stats(mod, deferred):
 
 
 def _fwd_scratch_size(mod, n_levels):
-    return n_levels * sum(6 * s.cout + 8 for s in mod._specs.values())
+    return n_levels * sum(8 * s.cout + 8 for s in mod._specs.values())       # (sum, sumsq) [f64 in validation mode] + bn4
 
 
 def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
@@ -344,10 +347,13 @@ def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
     pad = (0, spec.pad, spec.pad)
     if training:
         raw = Act.empty(x.B, to, x.H, x.W, spec.cout, torch.float32, dev)
-        stats = scratch.take(2 * spec.cout) if scratch is not None else torch.zeros(2 * spec.cout, dtype=torch.float32, device=dev)
         if umma:
+            stats = scratch.take(2 * spec.cout) if scratch is not None else torch.zeros(2 * spec.cout, dtype=torch.float32, device=dev)
             ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=True, stats=stats)
         else:
+            # validation mode: fp64 statistics reduced in a fixed order (bit-reproducible, no cancellation)
+            stats = (scratch.take(4 * spec.cout).view(torch.float64) if scratch is not None
+                     else torch.empty(2 * spec.cout, dtype=torch.float64, device=dev))
             ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=False)
             ops.channel_stats(raw, stats)
         bn4 = scratch.take(4 * spec.cout) if scratch is not None else torch.empty(4 * spec.cout, dtype=torch.float32, device=dev)
@@ -361,7 +367,17 @@ def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
                         BN_MOMENTUM if bn.momentum is None else bn.momentum, bn.eps, bn4)
         ops.affine_act(raw, out, bn4[:spec.cout], bn4[spec.cout:2 * spec.cout], spec.relu)
         if saved is not None:
-            saved[spec.conv] = (raw, bn4)
+            saved[spec.conv] = (raw, bn4, False)
+    elif saved is not None:
+        # eval mode WITH autograd (fine-tuning against frozen BatchNorm statistics; the reference module backpropagates
+        # through eval-mode BN like any nn.Module): keep the raw conv output like the train path does; BatchNorm is the fixed
+        # affine map of the running statistics and its backward has no batch-statistics terms (fixed_stats)
+        raw = Act.empty(x.B, to, x.H, x.W, spec.cout, torch.float32, dev)
+        ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=umma)
+        bn4 = torch.empty(4 * spec.cout, dtype=torch.float32, device=dev)
+        ops.bn_fold_eval(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn4)
+        ops.affine_act(raw, out, bn4[:spec.cout], bn4[spec.cout:2 * spec.cout], spec.relu)
+        saved[spec.conv] = (raw, bn4, True)
     else:
         fold = torch.empty(2 * spec.cout, dtype=torch.float32, device=dev)
         ops.bn_fold_eval(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, fold)
@@ -425,50 +441,80 @@ def _level_forward(mod, slow_in, fast_in, training, saved, scratch=None, fast_st
     return out
 
 
+class _GradSlot:
+    """One set of gradient accumulators: parameter-gradient views + packed weight-gradient accumulators."""
+    __slots__ = ("grads", "dwp", "deterministic")
+
+    def __init__(self, deterministic):
+        self.grads, self.dwp, self.deterministic = {}, {}, deterministic
+
+
 class _GradBank:
     """Every parameter gradient of the module as a view of ONE zero-filled f32 buffer, plus the packed weight-gradient
-    accumulators and the BN-backward sums.  All pyramid levels accumulate into the same views inside the kernels
-    (atomics / ``+=``), so the 5 levels cost no per-parameter torch.add and one fill."""
+    accumulators and the BN-backward sums.
 
-    def __init__(self, mod, n_levels, device):
+    Product path (bf16): all pyramid levels accumulate into the same views inside the kernels (atomics), so the 5 levels
+    cost no per-parameter torch.add and one fill.  Validation mode (``deterministic``): every level gets its own slot of
+    accumulators - the fp32 kernels add without atomics, and the levels may run concurrently - and ``finish`` sums the
+    slots in LEVEL order, so the result is bit-identical whatever the scheduling."""
+
+    def __init__(self, mod, n_levels, device, deterministic=False):
         specs = list(mod._specs.values())
-        n = 0
+        per_slot = 0
         for s in specs:
             conv = getattr(mod, s.conv)
-            taps = s.kt * s.khw * s.khw
-            n += 2 * (conv.weight.numel() + 4) + 3 * (s.cout + 4) + n_levels * (2 * s.cout + 4)
-        self.scratch = _Scratch(n, device)
-        self.grads, self.dwp = {}, {}
-        for s in specs:
-            conv, bn = getattr(mod, s.conv), getattr(mod, s.bn)
-            if conv.weight.requires_grad:
-                self.grads[s.conv + ".weight"] = self.scratch.take(conv.weight.numel()).view(conv.weight.shape)
-                self.dwp[s.conv] = self.scratch.take(s.kt * s.khw * s.khw * s.cin * s.cout)
-            if conv.bias is not None:
-                # a per-channel constant added before train-mode BN has exactly zero gradient
-                self.grads[s.conv + ".bias"] = self.scratch.take(s.cout)
-            self.grads[s.bn + ".weight"] = self.scratch.take(s.cout)
-            self.grads[s.bn + ".bias"] = self.scratch.take(s.cout)
+            per_slot += 2 * (conv.weight.numel() + 4) + 3 * (s.cout + 4)
+        per_slot = (per_slot + 3) // 4 * 4
+        n_slots = n_levels if deterministic else 1
+        sums = sum(n_levels * (2 * s.cout + 4) for s in specs)
+        self.scratch = _Scratch(n_slots * per_slot + sums, device)
+        self.per_slot, self.deterministic = per_slot, deterministic
+        self.slots = []
+        for i in range(n_slots):
+            assert self.scratch.off == i * per_slot
+            slot = _GradSlot(deterministic)
+            for s in specs:
+                conv, bn = getattr(mod, s.conv), getattr(mod, s.bn)
+                if conv.weight.requires_grad:
+                    slot.grads[s.conv + ".weight"] = self.scratch.take(conv.weight.numel()).view(conv.weight.shape)
+                    slot.dwp[s.conv] = self.scratch.take(s.kt * s.khw * s.khw * s.cin * s.cout)
+                if conv.bias is not None:
+                    # a per-channel constant added before train-mode BN has exactly zero gradient
+                    slot.grads[s.conv + ".bias"] = self.scratch.take(s.cout)
+                slot.grads[s.bn + ".weight"] = self.scratch.take(s.cout)
+                slot.grads[s.bn + ".bias"] = self.scratch.take(s.cout)
+            self.scratch.off = (i + 1) * per_slot
+            self.slots.append(slot)
+
+    def slot(self, i):
+        return self.slots[i if self.deterministic else 0]
 
     def finish(self, mod):
-        for name, dwp in self.dwp.items():
-            ops.unpack_wgrad(dwp, self.grads[name + ".weight"], 0)
-        return self.grads
+        first = self.scratch.buf[:self.per_slot]
+        for i in range(1, len(self.slots)):                    # fixed order: level 0 + level 1 + ...
+            ops.axpby(self.scratch.buf[i * self.per_slot:(i + 1) * self.per_slot], first, 1.0, 1.0)
+        grads = self.slots[0].grads
+        for name, dwp in self.slots[0].dwp.items():
+            ops.unpack_wgrad(dwp, grads[name + ".weight"], 0)
+        return grads
 
 
 def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=False, need_dx=True, dx_dtype=torch.float32):
     """BN(+ReLU) backward -> weight gradient -> (optionally) data gradient of one layer.
-    dy: Act gradient wrt the layer's post-activation output; returns dx Act (``dx_dtype``) or None."""
+    dy: Act gradient wrt the layer's post-activation output; returns dx Act (``dx_dtype``) or None.
+    ``bank``: a (_GradBank, _GradSlot) pair - the level's accumulators."""
+    bank, slot = bank
     conv, bn = getattr(mod, spec.conv), getattr(mod, spec.bn)
     umma = mod._umma
-    raw, bn4 = saved[spec.conv]
+    raw, bn4, fixed_stats = saved[spec.conv]
     dev = raw.buf.device
     dconv = Act.empty(raw.B, raw.T, raw.H, raw.W, spec.cout, mod._act_dtype, dev)
-    ops.bn_bwd(dy, raw, bn4, bn.weight, spec.relu, dconv, bank.grads[spec.bn + ".weight"], bank.grads[spec.bn + ".bias"],
-               sums=bank.scratch.take(2 * spec.cout))
+    ops.bn_bwd(dy, raw, bn4, bn.weight, spec.relu, dconv, slot.grads[spec.bn + ".weight"], slot.grads[spec.bn + ".bias"],
+               sums=bank.scratch.take(2 * spec.cout), deterministic=slot.deterministic, fixed_stats=fixed_stats,
+               dbias=slot.grads.get(spec.conv + ".bias") if fixed_stats else None)
     pad = (0, spec.pad, spec.pad)
     if conv.weight.requires_grad:
-        ops.wgrad(x_in, dconv, spec.k, pad, bank.dwp[spec.conv], umma=umma)
+        ops.wgrad(x_in, dconv, spec.k, pad, slot.dwp[spec.conv], umma=umma)
     if not need_dx:
         return None
     wd, cpd = mod._packed(spec.conv, 1)
@@ -480,7 +526,8 @@ def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=Fal
 
 
 def _level_backward(mod, saved, g_out, need_input_grad, bank, fast_stream=None):
-    """g_out: f32 Act [B,1,H,W,256] = gradient of the merged output; parameter gradients accumulate into ``bank``.
+    """g_out: f32 Act [B,1,H,W,256] = gradient of the merged output; parameter gradients accumulate into ``bank`` =
+    (_GradBank, this level's _GradSlot).
     Returns (d_slow, d_fast).  ``fast_stream``: the fast pathway's (and the laterals') backward on that stream, mirroring
     _level_forward: it waits for the slow pathway only where a lateral needs the slow gradient (d_s2 / d_s1)."""
     sp = mod._specs
@@ -542,10 +589,50 @@ def _act_to_ncdhw(act):
     return out.view(act.B, act.T, act.C, act.H, act.W).permute(0, 2, 1, 3, 4)
 
 
+class _FuseFn(torch.autograd.Function):
+    """One lateral connection (Conv3d k x 1 x 1, no bias -> BatchNorm3d -> ReLU) as a differentiable op: fast [B,32,T,H,W]
+    -> [B,64,T-k+1,H,W] (f32, channels-last memory)."""
+
+    @staticmethod
+    @ops.device_guard
+    def forward(ctx, mod, name, grad_enabled, fast, weight, gamma, beta):
+        ops.device_check()
+        spec = mod._specs[name]
+        f = _to_act(fast, mod._act_dtype)
+        out = Act.empty(f.B, f.T - spec.kt + 1, f.H, f.W, spec.cout, torch.float32, fast.device)
+        want_grad = grad_enabled and (fast.requires_grad or weight.requires_grad or gamma.requires_grad or beta.requires_grad)
+        saved = {} if want_grad else None
+        _conv_bn_forward(mod, spec, f, out, mod.training, saved)
+        ctx.mod, ctx.spec, ctx.saved, ctx.x_in = mod, spec, saved, f
+        lateral = out.buf.view(f.B, out.T, f.H, f.W, spec.cout).permute(0, 4, 1, 2, 3)
+        if saved is None:
+            ctx.mark_non_differentiable(lateral)
+        return lateral
+
+    @staticmethod
+    @ops.device_guard
+    def backward(ctx, g):
+        mod, spec, saved, f = ctx.mod, ctx.spec, ctx.saved, ctx.x_in
+        if saved is None:
+            raise RuntimeError("SlowFastLayers.fuse: backward needs a forward with grad enabled")
+        b, c, t, h, w = g.shape
+        gl = g.permute(0, 2, 3, 4, 1)
+        if not (gl.is_contiguous() and g.dtype == torch.float32):
+            gl = gl.float().contiguous()
+        bank = _GradBank(mod, 1, g.device, deterministic=not mod._umma)
+        dx = _layer_backward(mod, spec, Act(gl.reshape(-1), b, t, h, w, c), f, saved, (bank, bank.slot(0)),
+                             need_dx=ctx.needs_input_grad[3])
+        grads = bank.finish(mod)
+        ctx.saved = None
+        return (None, None, None, _act_to_ncdhw(dx) if dx is not None else None, grads[spec.conv + ".weight"],
+                grads[spec.bn + ".weight"], grads[spec.bn + ".bias"])
+
+
 class _SlowFastLevelFn(torch.autograd.Function):
     """forward(slow, fast) of one pyramid level with a hand-written backward over the saved raw conv outputs."""
 
     @staticmethod
+    @ops.device_guard
     def forward(ctx, mod, grad_enabled, slow_list, fast_list, slow5, fast5, *params):
         ops.device_check()
         dt_act = mod._act_dtype
@@ -555,7 +642,7 @@ class _SlowFastLevelFn(torch.autograd.Function):
         else:
             fast_in, slow_in = _lists_to_acts(slow_list, fast_list, dt_act)
         training = mod.training
-        want_grad = training and grad_enabled and (
+        want_grad = grad_enabled and (
             any(p.requires_grad for p in params) or (fast5 is not None and (fast5.requires_grad or slow5.requires_grad)))
         saved = {} if want_grad else None
         scratch = _Scratch(_fwd_scratch_size(mod, 1), fast_in.buf.device) if training else None
@@ -568,12 +655,13 @@ class _SlowFastLevelFn(torch.autograd.Function):
         return merged
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, g):
         mod, saved = ctx.mod, ctx.saved_acts
         if saved is None:
-            raise RuntimeError("SlowFastLayers: backward needs a train-mode forward with grad enabled")
-        bank = _GradBank(mod, 1, g.device)
-        d_slow, d_fast = _level_backward(mod, saved, _grad_to_act(g), ctx.need_input_grad, bank)
+            raise RuntimeError("SlowFastLayers: backward needs a forward with grad enabled")
+        bank = _GradBank(mod, 1, g.device, deterministic=not mod._umma)
+        d_slow, d_fast = _level_backward(mod, saved, _grad_to_act(g), ctx.need_input_grad, (bank, bank.slot(0)))
         grads = bank.finish(mod)
         ctx.saved_acts = None
         g_slow = _act_to_ncdhw(d_slow) if d_slow is not None else None
@@ -654,12 +742,13 @@ class _SlowFastPyramidFn(torch.autograd.Function):
     statistics scratch and accumulate their parameter gradients in-kernel into one buffer (no per-level torch.add)."""
 
     @staticmethod
+    @ops.device_guard
     def forward(ctx, mod, grad_enabled, slow_lists, fast_lists, *params):
         ops.device_check()
         ctx.set_materialize_grads(False)
         dt_act = mod._act_dtype
         training = mod.training
-        want_grad = training and grad_enabled and any(p.requires_grad for p in params)
+        want_grad = grad_enabled and any(p.requires_grad for p in params)
         dev = fast_lists[0][0].device
         scratch = _Scratch(_fwd_scratch_size(mod, len(fast_lists)), dev) if training else None
         outs, saved_all = [], []
@@ -698,19 +787,20 @@ class _SlowFastPyramidFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @ops.device_guard
     def backward(ctx, *gs):
         mod, saved_all = ctx.mod, ctx.saved_all
         if saved_all is None:
-            raise RuntimeError("SlowFastLayers: backward needs a train-mode forward with grad enabled")
+            raise RuntimeError("SlowFastLayers: backward needs a forward with grad enabled")
         live = [i for i, g in enumerate(gs) if g is not None]
         dev = gs[live[0]].device
-        bank = _GradBank(mod, max(1, len(live)), dev)
+        bank = _GradBank(mod, max(1, len(live)), dev, deterministic=not mod._umma)
         main = torch.cuda.current_stream(dev)
         if any(ctx.streams[i] is not None for i in live):
             _prepack(mod, (1,))
         for i in reversed(live):
             with _on_stream(ctx.streams[i], main):
-                _level_backward(mod, saved_all[i], _grad_to_act(gs[i]), False, bank,
+                _level_backward(mod, saved_all[i], _grad_to_act(gs[i]), False, (bank, bank.slot(live.index(i))),
                                 fast_stream=_pathway_stream(dev) if ctx.streams[i] is None and any(st is not None for st in ctx.streams) else None)
             saved_all[i] = None
         for i in live:

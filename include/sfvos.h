@@ -30,6 +30,7 @@ extern "C" {
 
 #define SFVOS_F32 0
 #define SFVOS_BF16 1
+#define SFVOS_F64 2              /* only for the BatchNorm statistics of the fp32 validation mode */
 
 typedef void* sfvos_stream;      /* cudaStream_t */
 
@@ -94,7 +95,9 @@ typedef struct sfvos_conv_params {
 
 /* tcgen05/TMEM/TMA bf16 kernel (the product path). */
 int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream);
-/* fp32 CUDA-core kernel: the "fp32 validation mode" of the north star (<=1e-4), same semantics. */
+/* CUDA-core kernel: the "fp32 validation mode" of the north star (<=1e-4), same semantics.  f32 operands and results,
+ * products accumulated in fp64 and rounded once (a pre-activation's sign is that of the exact sum, so ReLU masks -- and
+ * with them the gradients -- do not depend on summation order); no atomics, bit-reproducible. */
 int sfvos_conv_simt(const sfvos_conv_params* p, sfvos_stream stream);
 
 /* Weight-gradient GEMM: dw[(a,i,j)][c][n] += sum_{b,t,h,w} x[b,t+a-pad_t,h+i-pad_h,w+j-pad_w,c] * dy[b,t,h,w,n].
@@ -107,9 +110,16 @@ typedef struct sfvos_wgrad_params {
     int64_t dy_hstride, dy_tstride, dy_bstride;   /* 0 = dense, as for sfvos_conv_params.x_*stride */
     int64_t kt, kh, kw, pad_t, pad_h, pad_w;
     float* dw;
+    /* sfvos_wgrad_simt only: scratch for the fp64 split-K partial tiles, reduced in split order (no atomics).  NULL or too
+     * small = no split-K (still deterministic, fewer CTAs).  sfvos_wgrad_simt_workspace_bytes() gives the useful size. */
+    void* workspace;
+    int64_t workspace_bytes;
 } sfvos_wgrad_params;
-int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream);   /* x, dy bf16 */
-int sfvos_wgrad_simt(const sfvos_wgrad_params* p, sfvos_stream stream);   /* x, dy f32 */
+int sfvos_wgrad_umma(const sfvos_wgrad_params* p, sfvos_stream stream);   /* x, dy bf16; split-K merged with f32 atomics */
+/* x, dy f32; fp64 accumulation; the CTA that owns a dw tile adds to it without atomics, so concurrent calls must not share
+ * dw (the validation mode gives every pyramid level its own accumulator and sums them in level order). */
+int sfvos_wgrad_simt(const sfvos_wgrad_params* p, sfvos_stream stream);
+int64_t sfvos_wgrad_simt_workspace_bytes(const sfvos_wgrad_params* p);
 
 /* fp32 master weight [Cout,Cin,kt,kh,kw] (the state_dict tensor) -> packed operands.
  *   mode 0 fprop : N=Cout, taps in (a,i,j) order, K=(tap,cin)
@@ -130,13 +140,20 @@ int sfvos_unpack_wgrad(const float* dw, float* grad, int32_t mode, int64_t Cout,
  * BatchNorm3d pieces.  Replace aten::native_batch_norm (+backward) and aten::relu_ reached from
  * nn.BatchNorm3d / nn.ReLU at code/helpers/model.py:69,78,92 (invoked :113-114,121-122,...,148).
  * ------------------------------------------------------------------------------------------------------- */
-/* per-channel sum / sumsq over npix pixels of an f32 channels-last tensor (simt path; umma fuses this). */
-int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride, float* sum, float* sumsq,
-                        sfvos_stream stream);
-/* train: mean/var from (sum,sumsq,count) of the bias-free conv output; writes scale=gamma*rstd,
+/* Bytes of fp64 scratch the deterministic per-channel reductions (sfvos_channel_stats, sfvos_bn_bwd_reduce with a
+ * workspace) need for npix pixels of C channels: one row of 2*C partial sums per CTA. */
+int64_t sfvos_reduce_workspace_bytes(int64_t npix, int64_t C);
+/* per-channel sum / sumsq over npix pixels of an f32 channels-last tensor (validation mode; the umma kernels fuse this
+ * into their epilogue).  stats = fp64 [2*C] (sums, then sums of squares), WRITTEN: fp64 so that |mean| >> std does not
+ * cancel in sumsq/n - mean^2, fixed reduction order (per-CTA rows in the workspace, merged in CTA order) so that two
+ * runs agree bit for bit. */
+int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride, double* stats, void* workspace,
+                        int64_t workspace_bytes, sfvos_stream stream);
+/* train: mean/var from (sum,sumsq,count) of the bias-free conv output (stats_dtype SFVOS_F32: float sums from the umma
+ * epilogues; SFVOS_F64: sfvos_channel_stats); writes scale=gamma*rstd,
  * shift=beta-mean*scale, mean, rstd; updates running stats with PyTorch's rules (momentum, unbiased var,
  * conv bias added back to the mean) and num_batches_tracked += 1 (int64, may be NULL). */
-int sfvos_bn_finalize(const float* sum, const float* sumsq, double count, const float* conv_bias,
+int sfvos_bn_finalize(const void* sum, const void* sumsq, int32_t stats_dtype, double count, const float* conv_bias,
                       const float* gamma, const float* beta, float* running_mean, float* running_var,
                       int64_t* num_batches_tracked, double momentum, double eps, float* scale, float* shift,
                       float* mean, float* rstd, int64_t C, sfvos_stream stream);
@@ -146,10 +163,10 @@ int sfvos_bn_finalize(const float* sum, const float* sumsq, double count, const 
  * running buffers) and keeps the buffers bit-identical to the sequential order.  num_batches_tracked += n_calls. */
 #define SFVOS_BN_MAX_CALLS 8
 typedef struct sfvos_bn_running_params {
-    const float* sum[SFVOS_BN_MAX_CALLS];      /* per call: [C] sums of the bias-free conv output */
-    const float* sumsq[SFVOS_BN_MAX_CALLS];
+    const void* sum[SFVOS_BN_MAX_CALLS];       /* per call: [C] sums of the bias-free conv output (f32 | f64) */
+    const void* sumsq[SFVOS_BN_MAX_CALLS];
     double count[SFVOS_BN_MAX_CALLS];          /* per call: elements per channel */
-    int32_t n_calls, reserved;
+    int32_t n_calls, stats_dtype;              /* SFVOS_F32 | SFVOS_F64 */
     const float* conv_bias;                    /* may be NULL */
     float* running_mean;
     float* running_var;
@@ -158,25 +175,32 @@ typedef struct sfvos_bn_running_params {
     int64_t C;
 } sfvos_bn_running_params;
 int sfvos_bn_running_update(const sfvos_bn_running_params* p, sfvos_stream stream);
-/* eval: scale=gamma/sqrt(rv+eps), shift=beta+(conv_bias-rm)*scale. */
+/* eval: scale=gamma/sqrt(rv+eps), shift=beta+(conv_bias-rm)*scale; optionally (may be NULL) mean = rm - conv_bias and
+ * rstd = 1/sqrt(rv+eps), the constants the eval-mode backward needs in terms of the bias-free conv output. */
 int sfvos_bn_fold_eval(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
-                       const float* running_var, double eps, float* scale, float* shift, int64_t C,
-                       sfvos_stream stream);
+                       const float* running_var, double eps, float* scale, float* shift, float* mean, float* rstd,
+                       int64_t C, sfvos_stream stream);
 /* y = act(x*scale+shift) over a channels-last slice; x f32|bf16, y f32|bf16. */
 int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstride, void* y, int32_t y_dtype,
                      int64_t y_cstride, const float* scale, const float* shift, int32_t relu, int64_t npix,
                      int64_t C, sfvos_stream stream);
 /* BN(+ReLU) backward, pass 1: sums[0][c] += sum dy_m, sums[1][c] += sum dy_m*xhat, with
- * dy_m = dy * (relu ? (x*scale+shift > 0) : 1), xhat = (x-mean)*rstd.  x is the saved raw conv output (f32). */
+ * dy_m = dy * (relu ? (x*scale+shift > 0) : 1), xhat = (x-mean)*rstd.  x is the saved raw conv output (f32).
+ * workspace NULL: per-CTA sums merged with f32 atomics (product path).  workspace given (validation mode, f32 dy,
+ * sfvos_reduce_workspace_bytes bytes): fp64 sums merged in CTA order, ``sums`` written instead of accumulated. */
 int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
                         const float* scale, const float* shift, const float* mean, const float* rstd,
-                        int32_t relu, int64_t npix, int64_t C, float* sums, sfvos_stream stream);
+                        int32_t relu, int64_t npix, int64_t C, float* sums, void* workspace, int64_t workspace_bytes,
+                        sfvos_stream stream);
 /* pass 2: dx = gamma*rstd*(dy_m - sums0/n - xhat*sums1/n) written as bf16|f32; block 0 also does
- * dgamma += sums1, dbeta += sums0 (may be NULL). */
+ * dgamma += sums1, dbeta += sums0 (may be NULL).  fixed_stats != 0 = eval-mode BatchNorm (mean / rstd are the running
+ * statistics, constants): dx = gamma*rstd*dy_m, and dbias (may be NULL) += gamma*rstd*sums0, the gradient of the conv bias
+ * (which train-mode BN cancels exactly). */
 int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
                        const float* scale, const float* shift, const float* mean, const float* rstd,
                        const float* gamma, int32_t relu, int64_t npix, int64_t C, const float* sums, void* dx,
-                       int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, sfvos_stream stream);
+                       int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, int32_t fixed_stats,
+                       float* dbias, sfvos_stream stream);
 /* bias+ReLU layers (mask head): dx = dy * (y > 0) as bf16|f32 and dbias[c] += sum dx. */
 int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const void* y, int32_t y_dtype,
                    int64_t y_cstride, void* dx, int32_t dx_dtype, int64_t dx_cstride, float* dbias, int64_t npix,

@@ -124,6 +124,13 @@ class _RoundBF16(torch.autograd.Function):
 # (relative L2) away from the fp32 reference in ANY bf16 implementation.
 EMULATE_BF16 = False
 
+# Optional recorder: when a list, every ReLU layer appends (conv name, pre-activation tensor) during forward().  Used to
+# measure the ReLU MARGIN of a test input: min |pre-activation| over all ReLU layers.  A gradient comparison through
+# ReLU layers is only meaningful when that margin is well above the arithmetic noise of both sides - an element whose
+# pre-activation sits at 1e-7 has an undetermined mask in fp32, and one flipped mask moves single weight-gradient entries by
+# ~1e-3 of the maximum (tests/golden/make_golden.py picks input seeds by this margin, the GPU tests re-check it).
+PREACT_SINK = None
+
 
 def _conv_bn(sd, conv, bn, x, training, relu, spatial_pad):
     w = sd[conv + ".weight"]
@@ -135,6 +142,8 @@ def _conv_bn(sd, conv, bn, x, training, relu, spatial_pad):
     if training:
         sd[bn + ".num_batches_tracked"] += 1
     y = F.batch_norm(y, rm, rv, sd[bn + ".weight"], sd[bn + ".bias"], training, BN_MOMENTUM, BN_EPS)
+    if relu and PREACT_SINK is not None:
+        PREACT_SINK.append((conv, y.detach()))
     return F.relu(y) if relu else y
 
 
@@ -186,30 +195,59 @@ def synthetic_clip(level_shapes, fp, seed=1234, zero_left=0, scale=1.0):
     return feats
 
 
-def module_loss(merged):
+def module_loss(merged):  # noqa: D401
     """Module-only scalar used to seed gradients in tests/benches: sum_l mean(out_l * r_l) with a fixed seeded
     random projection r_l.  (A plain sum_l mean(out_l^2), as SURVEY 8(d) suggests for benches, is invariant under
     the final BatchNorm -- its true gradient is zero -- so it cannot pin a backward pass.)"""
     total = 0
     for i, v in enumerate(merged.values()):
         g = torch.Generator().manual_seed(777 + i)
-        r = torch.randn(v.shape, generator=g).to(v.device)
+        r = torch.randn(v.shape, generator=g).to(device=v.device, dtype=v.dtype)
         total = total + (v * r).mean()
     return total
 
 
-def grads_of(sd, slow_features, fast_features, loss_fn=module_loss, emulate_bf16=False):
-    """Train-mode forward + backward through the functional graph; returns (merged, loss, {param: grad}, buffers).
-    ``emulate_bf16``: see EMULATE_BF16 above."""
+def cast_inputs(sd, slow_features, fast_features, dtype):
+    """The same state dict / clips in another floating-point dtype (fp64 = the exact-arithmetic version of the oracle)."""
+    sd2 = OrderedDict((k, (v.to(dtype) if v.is_floating_point() else v.clone())) for k, v in sd.items())
+    cast = lambda feats: [OrderedDict((k, v.to(dtype)) for k, v in d.items()) for d in feats]
+    return sd2, cast(slow_features), cast(fast_features)
+
+
+def grads_of(sd, slow_features, fast_features, loss_fn=module_loss, emulate_bf16=False, dtype=None, training=True):
+    """Forward + backward through the functional graph (train mode unless ``training=False``: eval-mode BatchNorm, the
+    running statistics as constants); returns (merged, loss, {param: grad}, buffers).
+    ``emulate_bf16``: see EMULATE_BF16 above.  ``dtype=torch.float64`` runs the same graph in double precision."""
     global EMULATE_BF16
     prev, EMULATE_BF16 = EMULATE_BF16, bool(emulate_bf16)
+    if dtype is not None:
+        sd, slow_features, fast_features = cast_inputs(sd, slow_features, fast_features, dtype)
     try:
-        return _grads_of(sd, slow_features, fast_features, loss_fn)
+        return _grads_of(sd, slow_features, fast_features, loss_fn, training)
     finally:
         EMULATE_BF16 = prev
 
 
-def _grads_of(sd, slow_features, fast_features, loss_fn):
+def relu_preacts(sd, slow_features, fast_features, dtype=torch.float64, training=True):
+    """[(layer, pre-activation tensor)] of every ReLU layer, level by level, in ``dtype``."""
+    global PREACT_SINK
+    sd2, slow, fast = cast_inputs(sd, slow_features, fast_features, dtype)
+    prev, PREACT_SINK = PREACT_SINK, []
+    try:
+        with torch.no_grad():
+            temporally_enhance_features(sd2, slow, fast, training)
+        return PREACT_SINK
+    finally:
+        PREACT_SINK = prev
+
+
+def relu_margin(sd, slow_features, fast_features):
+    """(min |pre-activation| over all ReLU layers in fp64, number of ReLU inputs)."""
+    pre = relu_preacts(sd, slow_features, fast_features)
+    return min(float(y.abs().min()) for _, y in pre), sum(y.numel() for _, y in pre)
+
+
+def _grads_of(sd, slow_features, fast_features, loss_fn, training=True):
     leaves = {}
     work = OrderedDict()
     for k, v in sd.items():
@@ -218,7 +256,7 @@ def _grads_of(sd, slow_features, fast_features, loss_fn):
             work[k] = leaves[k]
         else:
             work[k] = v.clone()
-    merged = temporally_enhance_features(work, slow_features, fast_features, True)
+    merged = temporally_enhance_features(work, slow_features, fast_features, training)
     loss = loss_fn(merged)
     names = list(leaves)
     gs = torch.autograd.grad(loss, [leaves[n] for n in names], allow_unused=True)

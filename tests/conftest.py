@@ -49,3 +49,19 @@ def _exact_fp32_references():
     except Exception:
         pass
     yield
+
+
+def report(test, **values):
+    """Append the MEASURED values behind a tolerance to gpurun_out/parity_report.jsonl (one JSON object per line) when that
+    directory exists: every bound in the GPU suite is documented by the number it was derived from (profiles/ keeps a copy)."""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(out):
+        return
+    def conv(v):
+        try:
+            return float(v)
+        except Exception:
+            return str(v)
+    with open(os.path.join(out, "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps({"test": test, **{k: conv(v) for k, v in values.items()}}) + "\n")

@@ -7,6 +7,15 @@ SlowFast fixtures: reference ``SlowFastLayers`` (code/helpers/model.py:30-165) c
 torch.manual_seed(63) (code/helpers/constants.py:11), fed seeded synthetic FPN features, CPU fp32.
 Stored: train-mode outputs, BN buffers after that step, eval-mode outputs (with those buffers), the scalar
 module loss, and per-parameter gradient summaries (sum, abs-sum, 64 sampled entries).
+
+ReLU margin.  A weight gradient upstream of a ReLU is a discontinuous function of the forward pass: an element whose
+pre-activation sits within arithmetic noise of 0 has an undetermined mask, and one flipped mask moves single gradient
+entries by ~1e-3 of the maximum (round 1's red GPU test: (sp,fp)=(3,7) had a pre-activation at 2.7e-7).  So the input
+seed of every fixture is CHOSEN: the first seed 1234 + 1000*k for which min |pre-activation| over all ReLU layers (fp64
+oracle) is >= RELU_MARGIN = 1e-5 -- ~10x the fp32 summation noise measured on this graph (<= 6e-6 max, ~5e-7 typical) and
+~50x the noise of the GPU validation mode (fp64 accumulation, f32 storage: ~2e-7).  The script also asserts that the
+REFERENCE's own fp32 run has exactly the fp64 masks, and stores the seed and the margin in the fixture; the tests
+re-check the margin on the oracle before they compare gradients.
 ROI/mask fixtures: outputs of the live torchvision ops/modules the reference calls at model.py:346.
 """
 import os
@@ -29,6 +38,7 @@ LEVELS = OrderedDict([("0", (8, 12)), ("pool", (4, 6))])
 CONFIGS = [(1, 8), (3, 7), (2, 16), (4, 32), (1, 1)]
 N_CLIPS = 2
 SAMPLES = 64
+RELU_MARGIN = 1e-5
 
 
 def sample_idx(numel, k=SAMPLES):
@@ -36,13 +46,36 @@ def sample_idx(numel, k=SAMPLES):
     return torch.randint(0, numel, (k,), generator=g)
 
 
-def make_inputs(sp, fp):
+def make_inputs(sp, fp, seed0=1234):
     fast, slow = [], []
     for clip in range(N_CLIPS):
-        f = so.synthetic_clip(LEVELS, fp, seed=1234 + 100 * clip, zero_left=(fp // 2 if clip == 1 else 0))
+        f = so.synthetic_clip(LEVELS, fp, seed=seed0 + 100 * clip, zero_left=(fp // 2 if clip == 1 else 0))
         fast.append(f)
         slow.append(so.slice_window(f, fp // 2, sp))
     return slow, fast
+
+
+def pick_seed(sp, fp):
+    """First input seed whose ReLU margin (fp64 oracle) is >= RELU_MARGIN."""
+    sd = so.init_state_dict(sp, fp, seed=63)
+    for k in range(500):
+        seed0 = 1234 + 1000 * k
+        margin, n = so.relu_margin(sd, *make_inputs(sp, fp, seed0))
+        if margin >= RELU_MARGIN:
+            return seed0, margin, n
+    raise RuntimeError("no seed with the required ReLU margin")
+
+
+def reference_relu_masks(ref, slow, fast):
+    """ReLU masks of the UNMODIFIED reference module's own fp32 forward, via forward hooks on its BatchNorm3d modules (the
+    shared nn.ReLU is in-place, so the pre-activation is captured before it).  Layer-3 BNs feed no ReLU."""
+    masks, hooks = [], []
+    for name in ("bn_s1", "bn_f1", "bn_f2s1", "bn_s2", "bn_f2", "bn_f2s2"):
+        hooks.append(getattr(ref, name).register_forward_hook(lambda m, i, o, name=name: masks.append((name, (o.detach() > 0).clone()))))
+    out = ref.temporally_enhance_features(slow, fast)
+    for h in hooks:
+        h.remove()
+    return out, masks
 
 
 def slowfast_fixture(sp, fp):
@@ -56,12 +89,20 @@ def slowfast_fixture(sp, fp):
         assert torch.equal(ref_sd[k], sd0[k]), k
     n_params = sum(p.numel() for p in ref.parameters())
 
-    slow, fast = make_inputs(sp, fp)
+    seed0, margin, n_relu = pick_seed(sp, fp)
+    slow, fast = make_inputs(sp, fp, seed0)
     ref.train()
-    out_train = ref.temporally_enhance_features(slow, fast)
+    out_train, masks = reference_relu_masks(ref, slow, fast)
+    # the reference's fp32 masks must be the exact (fp64) ones, layer by layer in call order
+    bn_of = dict(so.LAYER_ORDER)
+    exact = so.relu_preacts(sd0, slow, fast)
+    assert len(exact) == len(masks)
+    for (conv, y64), (bn, m32) in zip(exact, masks):
+        assert bn_of[conv] == bn and torch.equal(y64 > 0, m32), f"reference fp32 ReLU mask differs from fp64 at {conv}"
     loss = so.module_loss(out_train)
     loss.backward()
-    rec = {"n_params": np.int64(n_params), "loss": np.float64(loss.item())}
+    rec = {"n_params": np.int64(n_params), "loss": np.float64(loss.item()), "input_seed": np.int64(seed0),
+           "relu_margin": np.float64(margin), "n_relu_inputs": np.int64(n_relu)}
     for k, v in out_train.items():
         rec["train_out_" + k] = v.detach().numpy()
     for name, p in ref.named_parameters():
@@ -78,7 +119,7 @@ def slowfast_fixture(sp, fp):
     for k, v in out_eval.items():
         rec["eval_out_" + k] = v.numpy()
     np.savez_compressed(os.path.join(HERE, f"slowfast_sp{sp}_fp{fp}.npz"), **rec)
-    print(f"sp={sp} fp={fp}: params={n_params} loss={loss.item():.6f}")
+    print(f"sp={sp} fp={fp}: params={n_params} loss={loss.item():.6f} input_seed={seed0} relu_margin={margin:.3e} over {n_relu} ReLU inputs")
 
 
 def roi_mask_fixture():
@@ -137,4 +178,5 @@ def roi_mask_fixture():
 if __name__ == "__main__":
     for sp, fp in CONFIGS:
         slowfast_fixture(sp, fp)
-    roi_mask_fixture()
+    if "--slowfast-only" not in sys.argv:
+        roi_mask_fixture()

@@ -184,7 +184,7 @@ def test_bn_pieces_match_torch_batchnorm():
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     nbt = torch.zeros((), dtype=torch.long, device=DEV)
     xa = _mk_act(ops, x, torch.float32)
-    stats = torch.zeros(2 * C, device=DEV)
+    stats = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
     ops.channel_stats(xa, stats)
     bn4 = torch.empty(4 * C, device=DEV)
     ops.bn_finalize(stats, xa.npix, bias, gamma, beta, rm, rv, nbt, 0.1, 1e-5, bn4)

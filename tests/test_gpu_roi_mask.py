@@ -13,7 +13,7 @@ from torchvision.models.detection.mask_rcnn import MaskRCNNHeads as TVHeads, Mas
 from torchvision.models.detection.roi_heads import maskrcnn_loss as tv_maskrcnn_loss, project_masks_on_boxes as tv_project
 from torchvision.ops import MultiScaleRoIAlign as TVPool
 
-from conftest import GOLDEN
+from conftest import GOLDEN, report
 from oracle import roi_oracle as ro
 
 pytestmark = pytest.mark.gpu
@@ -30,6 +30,7 @@ def _check_grad(name, got, ref, precision):
     moves individual gradient entries by percents of the max while leaving the L2 error tiny.  bf16 adds the
     sqrt(flip fraction) effect described in test_gpu_slowfast._check_grad."""
     rel = (got.float() - ref.float()).norm().item() / (ref.float().norm().item() + 1e-20)
+    report("roi_mask_grad", name=name, precision=precision, rel_l2=rel, max_norm=_nerr(got, ref))
     assert rel < (1e-2 if precision == "fp32" else 0.25), (name, rel)
     if name.startswith(("mask_predictor.mask_fcn_logits", "mask_fcn_logits")):     # downstream of every ReLU
         assert _nerr(got, ref) < (1e-4 if precision == "fp32" else 2e-2), (name, _nerr(got, ref))
@@ -136,6 +137,7 @@ def test_roi_and_mask_golden_fixture():
         head.precision = pred.precision = prec
         x = torch.from_numpy(gold["mh_x"]).cuda()
         logits = pred(head(x))
+        report("mask_logits_golden", precision=prec, max_norm=_nerr(logits, torch.from_numpy(gold["mh_logits"])))
         assert _nerr(logits, torch.from_numpy(gold["mh_logits"])) < tol, prec
         gt = torch.zeros(2, 187, 333, dtype=torch.uint8)
         gt[0, 40:120, 60:200] = 1
@@ -181,6 +183,7 @@ def test_mask_branch_forward_backward_matches_torchvision(precision):
     loss_o = maskrcnn_loss(lo, props, [gt], labels, matched)
     loss_o.backward()
     ftol = 1e-4 if precision == "fp32" else 2e-2
+    report("mask_branch_logits", precision=precision, max_norm=_nerr(lo, lr), loss_rel=abs(loss_o.item() - loss_r.item()) / abs(loss_r.item()))
     assert lo.shape == lr.shape and _nerr(lo, lr) < ftol
     assert abs(loss_o.item() - loss_r.item()) < ftol * abs(loss_r.item())
     for (n1, p1), (n2, p2) in zip(list(head.named_parameters()) + list(pred.named_parameters()),
