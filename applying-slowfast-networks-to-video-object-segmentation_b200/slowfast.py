@@ -142,7 +142,7 @@ class SlowFastLayers(nn.Module):
         (``conv`` / ``bn`` = ``self.conv_f2s{1,2}`` / ``self.bn_f2s{1,2}``).  The fused pipeline (forward /
         temporally_enhance_features) never calls it - there the lateral convolution writes straight into channels 192..255
         of the slow buffer - but it is part of the reference's interface, so it is a differentiable op of its own here."""
-        name = next((n for n in self._specs if getattr(self, n) is conv), None)
+        name = next((n for n in ("conv_f2s1", "conv_f2s2") if getattr(self, n) is conv), None)
         if name is None or getattr(self, self._specs[name].bn) is not bn:
             raise ValueError("fuse: conv / bn must be one of this module's lateral pairs (conv_f2s1, bn_f2s1) / (conv_f2s2, bn_f2s2)")
         lateral = _FuseFn.apply(self, name, torch.is_grad_enabled(), fast, conv.weight, bn.weight, bn.bias)

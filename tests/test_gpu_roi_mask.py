@@ -25,15 +25,21 @@ def _nerr(a, b):
 
 
 def _check_grad(name, got, ref, precision):
-    """Gradients that pass through ReLUs are compared in relative L2: a single ReLU whose pre-activation sits within
-    rounding distance of zero flips between two implementations (measured: ~1 element per 10^6 even fp32-vs-fp32) and
-    moves individual gradient entries by percents of the max while leaving the L2 error tiny.  bf16 adds the
-    sqrt(flip fraction) effect described in test_gpu_slowfast._check_grad."""
-    rel = (got.float() - ref.float()).norm().item() / (ref.float().norm().item() + 1e-20)
+    """Gradients that pass through ReLUs are compared in relative L2: a ReLU whose pre-activation sits within rounding
+    distance of zero flips between two implementations and moves individual gradient entries by percents of the max while
+    leaving the L2 error small.  Unlike the SlowFast fixtures (tests/golden/make_golden.py) the mask branch cannot be given
+    an input with a ReLU margin: 4 conv layers + the ConvTranspose on even 9 ROIs are 3.6 M ReLU inputs with a standard
+    deviation of ~0.1, i.e. an expected minimum |pre-activation| of ~7e-8 (a scan of 400 input seeds found none above
+    4e-6), so a handful of undetermined masks is a property of the test, not of the kernels.  Measured (round 2, B200,
+    gpurun_out/parity_report.jsonl -> profiles/parity_r2.jsonl): fp32 validation mode <= 3.2e-3 (the first head conv, which
+    sees the flips of all layers above it; 5e-5..2e-4 elsewhere; 3e-7 downstream of every ReLU), bf16 <= 0.11 (first
+    conv) / <= 2e-2 (other layers) - the sqrt(flip fraction) effect described in test_gpu_slowfast._check_grad."""
+    rel = (got.double() - ref.double()).norm().item() / (ref.double().norm().item() + 1e-30)
     report("roi_mask_grad", name=name, precision=precision, rel_l2=rel, max_norm=_nerr(got, ref))
     assert rel < (1e-2 if precision == "fp32" else 0.25), (name, rel)
-    if name.startswith(("mask_predictor.mask_fcn_logits", "mask_fcn_logits")):     # downstream of every ReLU
-        assert _nerr(got, ref) < (1e-4 if precision == "fp32" else 2e-2), (name, _nerr(got, ref))
+    if name.startswith(("mask_predictor.mask_fcn_logits", "mask_fcn_logits")):     # downstream of every ReLU: no masks involved
+        # measured 3.9e-7 (fp32 mode) / 2.6e-3 (bf16)
+        assert _nerr(got, ref) < (1e-5 if precision == "fp32" else 1e-2), (name, _nerr(got, ref))
 
 
 def _feats(n=2, c=256, seed=0, shapes=((48, 84), (24, 42), (12, 21), (6, 11))):
@@ -133,7 +139,7 @@ def test_roi_and_mask_golden_fixture():
     torch.manual_seed(11)
     head = MaskRCNNHeads(256, (256, 256, 256, 256), 1).cuda()
     pred = MaskRCNNPredictor(256, 256, 2).cuda()
-    for prec, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+    for prec, tol in (("fp32", 1e-4), ("bf16", 1e-2)):      # north star: <= 1e-4 / <= 1e-2; measured 5.7e-7 / 6.4e-3
         head.precision = pred.precision = prec
         x = torch.from_numpy(gold["mh_x"]).cuda()
         logits = pred(head(x))
@@ -176,13 +182,15 @@ def test_mask_branch_forward_backward_matches_torchvision(precision):
     gt = (torch.rand(2, 96, 160, generator=g) > 0.5).to(torch.uint8).cuda()
     props = [torch.cat(ro.synthetic_rois(1, K, image_hw=(96, 160), seed=3, lo=8.0, hi=150.0)).cuda()]
     labels, matched = [torch.tensor([1, 1]).cuda()], [torch.randint(0, 2, (K,), generator=g).cuda()]
+    if precision == "fp32":              # the exact reference for the validation mode: torchvision's modules in fp64
+        head_ref, pred_ref, xr = head_ref.double(), pred_ref.double(), x.double().clone().requires_grad_(True)
     lr = pred_ref(head_ref(xr))
     loss_r = tv_maskrcnn_loss(lr, props, [gt], labels, matched)
     loss_r.backward()
     lo = pred(head(xo))
     loss_o = maskrcnn_loss(lo, props, [gt], labels, matched)
     loss_o.backward()
-    ftol = 1e-4 if precision == "fp32" else 2e-2
+    ftol = 1e-4 if precision == "fp32" else 1e-2         # north star bounds; measured 7.2e-6 / 6.9e-3
     report("mask_branch_logits", precision=precision, max_norm=_nerr(lo, lr), loss_rel=abs(loss_o.item() - loss_r.item()) / abs(loss_r.item()))
     assert lo.shape == lr.shape and _nerr(lo, lr) < ftol
     assert abs(loss_o.item() - loss_r.item()) < ftol * abs(loss_r.item())
