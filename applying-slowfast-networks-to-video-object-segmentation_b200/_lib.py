@@ -65,7 +65,7 @@ _SIGS = {
     "sfvos_bn_bwd_reduce": [vp, i32, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, vp, vp, i64, vp],
     "sfvos_bn_bwd_apply": [vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, i32, i64, vp, vp, i32, vp, vp],
     "sfvos_relu_bwd": [vp, i32, i64, vp, i32, i64, vp, i32, i64, vp, i64, i64, vp],
-    "sfvos_nchw_to_nhwc": [vp, i64, vp, i32, i64, i64, i64, i64, vp],
+    "sfvos_nchw_to_nhwc": [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp],
     "sfvos_nhwc_to_nchw": [vp, i32, i64, vp, i64, i64, i64, vp],
     "sfvos_roi_levels": [vp, i64, i32, i32, vp, vp],
     "sfvos_roi_align_fwd": [ctypes.POINTER(RoiParams), vp],

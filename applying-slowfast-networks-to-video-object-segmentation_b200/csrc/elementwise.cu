@@ -426,36 +426,52 @@ __global__ void bn_fold_eval_kernel(const float* conv_bias, const float* gamma, 
 }
 
 // ---- layout -----------------------------------------------------------------------------------------------------
-// [F][C][HW] f32 -> [F][HW][cstride]; tile = 64 channels x 128 pixels, 256 threads.
-// Load: 8 independent float4 (16 B) loads per thread along the pixel axis (512 B per warp row).  Store: each thread
-// writes 8 consecutive channels of one pixel (16 B bf16 / 32 B f32), 8 threads cover the tile's 64 channels.
-template <typename OutT>
+// [F][C][HW] (f32 | bf16) -> [F][HW][cstride]; tile = 64 channels x 128 pixels, 256 threads.
+// Load: 8 independent 4-pixel loads per thread along the pixel axis (16 B f32 / 8 B bf16; 512 / 256 B per warp row).  Store:
+// each thread writes 8 consecutive channels of one pixel (16 B bf16 / 32 B f32), 8 threads cover the tile's 64 channels.
+__device__ __forceinline__ float4 load4_px(const float* r, long long p, long long HW, bool vec_ok) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec_ok && p + 3 < HW) return __ldg(reinterpret_cast<const float4*>(r));
+    if (p < HW) v.x = r[0];
+    if (p + 1 < HW) v.y = r[1];
+    if (p + 2 < HW) v.z = r[2];
+    if (p + 3 < HW) v.w = r[3];
+    return v;
+}
+__device__ __forceinline__ float4 load4_px(const __nv_bfloat16* r, long long p, long long HW, bool vec_ok) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec_ok && p + 3 < HW) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(r));
+        v.x = __uint_as_float(u.x << 16); v.y = __uint_as_float(u.x & 0xffff0000u);
+        v.z = __uint_as_float(u.y << 16); v.w = __uint_as_float(u.y & 0xffff0000u);
+        return v;
+    }
+    if (p < HW) v.x = __bfloat162float(r[0]);
+    if (p + 1 < HW) v.y = __bfloat162float(r[1]);
+    if (p + 2 < HW) v.z = __bfloat162float(r[2]);
+    if (p + 3 < HW) v.w = __bfloat162float(r[3]);
+    return v;
+}
+
+template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ src, long long src_fstride, OutT* dst, long long dst_cstride, int C, long long HW) {
+nchw_to_nhwc_kernel(const InT* __restrict__ src, long long src_fstride, OutT* dst, long long dst_cstride, int C, long long HW) {
     __shared__ float tile[64][129];
     const int f = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 128;
     const int c0 = blockIdx.y * 64;
-    const float* s = src + (long long)f * src_fstride;
+    const InT* s = src + (long long)f * src_fstride;
     const int t = threadIdx.x;
     const int lp4 = (t & 31) * 4, lc = t >> 5;
-    const bool vec_ok = (HW % 4 == 0);
+    // 4-pixel vector loads need every channel row to start on a vector boundary
+    const bool vec_ok = (HW % 4 == 0) && (src_fstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & (4 * sizeof(InT) - 1)) == 0);
     float4 buf[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = c0 + lc + 8 * i;
         const long long p = p0 + lp4;
         buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < C) {
-            const float* r = s + (long long)c * HW + p;
-            if (vec_ok && p + 3 < HW) buf[i] = __ldg(reinterpret_cast<const float4*>(r));
-            else {
-                if (p < HW) buf[i].x = r[0];
-                if (p + 1 < HW) buf[i].y = r[1];
-                if (p + 2 < HW) buf[i].z = r[2];
-                if (p + 3 < HW) buf[i].w = r[3];
-            }
-        }
+        if (c < C && p < HW) buf[i] = load4_px(s + (long long)c * HW + p, p, HW, vec_ok);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -746,14 +762,20 @@ extern "C" int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstri
     return SFVOS_OK;
 }
 
-extern "C" int sfvos_nchw_to_nhwc(const float* src, int64_t src_fstride, void* dst, int32_t dst_dtype, int64_t dst_cstride,
-                                  int64_t F, int64_t C, int64_t HW, sfvos_stream stream) {
+extern "C" int sfvos_nchw_to_nhwc(const void* src, int32_t src_dtype, int64_t src_fstride, void* dst, int32_t dst_dtype,
+                                  int64_t dst_cstride, int64_t F, int64_t C, int64_t HW, sfvos_stream stream) {
     SF_CHECK(C % 8 == 0 && dst_cstride % 8 == 0, "nchw_to_nhwc: C and cstride must be multiples of 8");
     SF_CHECK(F <= 65535, "nchw_to_nhwc: too many frames in one call");
+    SF_CHECK(src_dtype == SFVOS_F32 || src_dtype == SFVOS_BF16, "nchw_to_nhwc: source must be f32 or bf16");
     if (F == 0 || HW == 0) return SFVOS_OK;
     dim3 grid((unsigned)((HW + 127) / 128), (unsigned)((C + 63) / 64), (unsigned)F), block(256);
-    if (dst_dtype == SFVOS_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, CS(stream)>>>(src, src_fstride, reinterpret_cast<__nv_bfloat16*>(dst), dst_cstride, (int)C, HW);
-    else nchw_to_nhwc_kernel<float><<<grid, block, 0, CS(stream)>>>(src, src_fstride, reinterpret_cast<float*>(dst), dst_cstride, (int)C, HW);
+    using bf = __nv_bfloat16;
+#define LAUNCH(IT, OT) nchw_to_nhwc_kernel<IT, OT><<<grid, block, 0, CS(stream)>>>(reinterpret_cast<const IT*>(src), src_fstride, reinterpret_cast<OT*>(dst), dst_cstride, (int)C, HW)
+    if (src_dtype == SFVOS_F32 && dst_dtype == SFVOS_BF16) LAUNCH(float, bf);
+    else if (src_dtype == SFVOS_F32) LAUNCH(float, float);
+    else if (dst_dtype == SFVOS_BF16) LAUNCH(bf, bf);
+    else LAUNCH(bf, float);
+#undef LAUNCH
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

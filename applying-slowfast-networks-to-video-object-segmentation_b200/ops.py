@@ -11,6 +11,22 @@ from ._lib import BF16, F32, F64, ConvParams, RoiParams, WgradParams, call
 
 TIMING = None   # bench.py sets this to a list: every conv / wgrad launch then appends (kernel, flops, start, end)
 
+# Optional gradient arena (dp.GradArena): when set, the backward passes write each parameter gradient straight into its slice
+# of ONE flat f32 buffer (and return that slice, which autograd adopts as p.grad without a copy), so the data-parallel step
+# all-reduces contiguous ranges of the arena -- no torch.cat / pack pass over the 73 MB of gradients.
+GRAD_ARENA = None
+
+
+def new_grad(param, shape=None):
+    """Accumulator for ``param``'s gradient: its arena slice (NOT re-zeroed: kernels add to it, the arena is cleared once per
+    optimizer step) or a fresh zero-filled f32 tensor.  ``shape``: view the slice differently (same number of elements)."""
+    if GRAD_ARENA is not None:
+        v = GRAD_ARENA.view(param, shape)
+        if v is not None:
+            return v
+    return torch.zeros(tuple(shape) if shape is not None else param.shape, dtype=torch.float32, device=param.device)
+
+
 
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -183,7 +199,10 @@ def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shi
         p.relu_mask = relu_mask.ptr(); p.relu_mask_cstride = relu_mask.cstride
         if dbias is not None:
             p.sum = _p(dbias)
-    flops = 2.0 * x.B * To * x.H * x.W * N * x.C * k[0] * k[1] * k[2]
+    # algorithmic FLOPs: no zero-padded taps.  fprop: To = T - kt + 1 output frames; a data-gradient launch
+    # (full temporal padding, To = the forward INPUT frames) does the forward layer's work, one product per forward output
+    # frame and tap, so it counts x.T (= the forward output frames) -- min() covers both
+    flops = 2.0 * x.B * min(To, x.T) * x.H * x.W * N * x.C * k[0] * k[1] * k[2]
     _timed_call("conv_umma" if umma else "conv_simt", flops, "sfvos_conv_umma" if umma else "sfvos_conv_simt", p)
 
 
@@ -290,12 +309,12 @@ def relu_bwd(dy, y, dx, dbias):
 
 
 def nchw_to_nhwc(src, dst_act, frame_off=0):
-    """src f32 [F,C,H,W] contiguous -> frames [frame_off, frame_off+F) of dst_act."""
-    assert src.dtype == torch.float32 and src.is_contiguous()
+    """src (f32 | bf16) [F,C,H,W] contiguous -> frames [frame_off, frame_off+F) of dst_act."""
+    assert src.dtype in (torch.float32, torch.bfloat16) and src.is_contiguous()
     F, C, H, W = src.shape
     esz = dst_act.buf.element_size()
     off = (frame_off * H * W * dst_act.cstride + dst_act.ch_off) * esz
-    call("sfvos_nchw_to_nhwc", _p(src), C * H * W, _p(dst_act.buf, off), dt(dst_act.buf), dst_act.cstride, F, C, H * W,
+    call("sfvos_nchw_to_nhwc", _p(src), dt(src), C * H * W, _p(dst_act.buf, off), dt(dst_act.buf), dst_act.cstride, F, C, H * W,
          stream())
 
 

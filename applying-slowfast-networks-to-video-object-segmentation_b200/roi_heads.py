@@ -274,10 +274,10 @@ class _MaskHeadFn(torch.autograd.Function):
         for i in range(n - 1, -1, -1):
             w, b = wb[2 * i], wb[2 * i + 1]
             x_in, y = acts[i], acts[i + 1]
-            gw = torch.zeros_like(w, dtype=torch.float32)
+            gw = ops.new_grad(w)
             if dconv is None:
                 dconv = Act.empty(K, 1, H, W, y.C, dt_act, g.device)
-                db = torch.zeros_like(b, dtype=torch.float32)
+                db = ops.new_grad(b)
                 if K:
                     ops.relu_bwd(dy, y, dconv, db)
             if K:
@@ -290,7 +290,7 @@ class _MaskHeadFn(torch.autograd.Function):
                 # pre-activation gradient (bf16) and its bias gradient - no f32 round trip, no separate relu_bwd pass
                 wd, cpd = _pack(w, 1, umma, w.shape[0])
                 nxt = Act.empty(K, 1, H, W, x_in.C, dt_act, g.device)
-                db = torch.zeros_like(wb[2 * i - 1], dtype=torch.float32)
+                db = ops.new_grad(wb[2 * i - 1])
                 ops.conv(dconv, wd, cpd, x_in.C, (1, 3, 3), (0, 1, 1), 1, nxt, umma=True, relu_mask=x_in, dbias=db)
                 dconv = nxt
             elif i > 0 or ctx.needs_input_grad[0]:
@@ -379,10 +379,10 @@ class _MaskPredictorFn(torch.autograd.Function):
         xin, up = ctx.acts
         umma, dt_act, x_dtype, K, C, H, W, co, n_cls = ctx.meta
         dev = glogits.device
-        gwl = torch.zeros(n_cls, co, dtype=torch.float32, device=dev)
-        gbl = torch.zeros(n_cls, dtype=torch.float32, device=dev)
-        gwt = torch.zeros_like(wt, dtype=torch.float32)
-        gbt = torch.zeros(co, dtype=torch.float32, device=dev)
+        gwl = ops.new_grad(wl, (n_cls, co))
+        gbl = ops.new_grad(bl)
+        gwt = ops.new_grad(wt)
+        gbt = ops.new_grad(bt)
         gx = None
         if K:
             gl = glogits.float().contiguous()
@@ -507,7 +507,7 @@ def _linear_bwd(x, dy, w, umma, dx_dtype, need_dx=True):
     """dy = gradient of the PRE-activation output [M,N] (Act); returns (gw [N,K] f32, dx Act [M,K] or None)."""
     N, K = w.shape
     dev = dy.buf.device
-    gw = torch.zeros(N, K, dtype=torch.float32, device=dev)
+    gw = ops.new_grad(w)
     dx = None
     if x.W:
         dwp = torch.zeros(K * N, dtype=torch.float32, device=dev)
@@ -551,8 +551,7 @@ class _BoxHeadFn(torch.autograd.Function):
         xin, y6, y7 = ctx.acts
         umma, dt_act, x_dtype, x_shape = ctx.meta
         M, dev = xin.W, g.device
-        gb6 = torch.zeros(w6.shape[0], dtype=torch.float32, device=dev)
-        gb7 = torch.zeros(w7.shape[0], dtype=torch.float32, device=dev)
+        gb6, gb7 = ops.new_grad(b6), ops.new_grad(b7)
         dy7 = _as_rows(g, dt_act)
         dc7 = Act.empty(1, 1, 1, M, y7.C, dt_act, dev)
         if M:
@@ -628,8 +627,13 @@ class _BoxPredictorFn(torch.autograd.Function):
         gw, dx = _linear_bwd(xin, dy, w, umma, dt_act, need_dx=ctx.needs_input_grad[0])
         gx = dx.buf.view(x_shape).to(x_dtype) if dx is not None else None
         ctx.acts = None
-        return (gx, None, gw[:nc].to(wc.dtype), stats[0, :nc].to(bc.dtype), gw[nc:nc + nb].to(wb.dtype),
-                stats[0, nc:nc + nb].to(bb.dtype))
+        # the four parameter gradients are row ranges of the stacked GEMM's: added into their own accumulators
+        outs = []
+        for prm, val in ((wc, gw[:nc]), (bc, stats[0, :nc]), (wb, gw[nc:nc + nb]), (bb, stats[0, nc:nc + nb])):
+            acc = ops.new_grad(prm)
+            acc.add_(val.to(torch.float32))
+            outs.append(acc.to(prm.dtype))
+        return (gx, None) + tuple(outs)
 
 
 class FastRCNNPredictor(tv_faster_rcnn.FastRCNNPredictor):

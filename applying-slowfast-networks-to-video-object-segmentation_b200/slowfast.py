@@ -235,9 +235,7 @@ class SlowFastLayers(nn.Module):
                         fast_in.buf[:left * per].zero_()
                     if right:
                         fast_in.buf[(t_in - right) * per:].zero_()
-                    src = x[f0 + hl:f1 + hl].to(dev)
-                    if src.dtype != torch.float32 or not src.is_contiguous():
-                        src = src.float().contiguous()
+                    src = _as_source(x[f0 + hl:f1 + hl].to(dev))
                     ops.nchw_to_nhwc(src, fast_in, frame_off=left)
                     slow_in = fast_in.frames(s_off, s_off + (c1 - c0) + sp - 1)
                     chunk_outs[key] = _level_forward(self, slow_in, fast_in, False, None).as_nchw()
@@ -252,13 +250,17 @@ class SlowFastLayers(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------------
 # engine
 # ----------------------------------------------------------------------------------------------------------------------
+def _as_source(x):
+    """Contiguous f32 or bf16 tensor (the layout kernel reads both; anything else is converted to f32 first)."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return x if x.is_contiguous() else x.contiguous()
+
+
 def _to_act(x5, dtype):
     """[B,C,T,H,W] tensor (any strides) -> dense channels-last Act."""
     b, c, t, h, w = x5.shape
-    frames = x5.permute(0, 2, 1, 3, 4)
-    if frames.dtype != torch.float32:
-        frames = frames.float()
-    frames = frames.contiguous().view(b * t, c, h, w)
+    frames = _as_source(x5.permute(0, 2, 1, 3, 4)).view(b * t, c, h, w)
     act = Act.empty(b, t, h, w, c, dtype, x5.device)
     ops.nchw_to_nhwc(frames, act)
     return act
@@ -269,9 +271,7 @@ def _clips_to_act(clips, dtype):
     t, c, h, w = clips[0].shape
     act = Act.empty(len(clips), t, h, w, c, dtype, clips[0].device)
     for b, clip in enumerate(clips):
-        if clip.dtype != torch.float32 or not clip.is_contiguous():
-            clip = clip.float().contiguous()
-        ops.nchw_to_nhwc(clip, act, frame_off=b * t)
+        ops.nchw_to_nhwc(_as_source(clip), act, frame_off=b * t)
     return act
 
 
@@ -290,11 +290,11 @@ def _alias_offset(slow_list, fast_list):
     model.py:242-248, yields exactly such views) return the common first-frame offset, else None."""
     off = None
     for s, f in zip(slow_list, fast_list):
-        if not (s.is_contiguous() and f.is_contiguous() and s.dtype == f.dtype == torch.float32):
+        if not (s.is_contiguous() and f.is_contiguous() and s.dtype == f.dtype and f.dtype in (torch.float32, torch.bfloat16)):
             return None
         if s.untyped_storage().data_ptr() != f.untyped_storage().data_ptr() or s.shape[1:] != f.shape[1:]:
             return None
-        frame_bytes = f[0].numel() * 4
+        frame_bytes = f[0].numel() * f.element_size()
         delta = s.data_ptr() - f.data_ptr()
         if delta < 0 or delta % frame_bytes:
             return None
@@ -470,19 +470,26 @@ class _GradBank:
         self.scratch = _Scratch(n_slots * per_slot + sums, device)
         self.per_slot, self.deterministic = per_slot, deterministic
         self.slots = []
+        # product path with a gradient arena (ops.GRAD_ARENA, data-parallel step): the parameter gradients live in the arena
+        # (accumulated into, cleared once per optimizer step by its owner); only the packed accumulators stay in the scratch
+        arena = None if deterministic else ops.GRAD_ARENA
+
+        def grad_view(param):
+            v = arena.view(param) if arena is not None else None
+            return v if v is not None else self.scratch.take(param.numel()).view(param.shape)
         for i in range(n_slots):
             assert self.scratch.off == i * per_slot
             slot = _GradSlot(deterministic)
             for s in specs:
                 conv, bn = getattr(mod, s.conv), getattr(mod, s.bn)
                 if conv.weight.requires_grad:
-                    slot.grads[s.conv + ".weight"] = self.scratch.take(conv.weight.numel()).view(conv.weight.shape)
+                    slot.grads[s.conv + ".weight"] = grad_view(conv.weight)
                     slot.dwp[s.conv] = self.scratch.take(s.kt * s.khw * s.khw * s.cin * s.cout)
                 if conv.bias is not None:
                     # a per-channel constant added before train-mode BN has exactly zero gradient
-                    slot.grads[s.conv + ".bias"] = self.scratch.take(s.cout)
-                slot.grads[s.bn + ".weight"] = self.scratch.take(s.cout)
-                slot.grads[s.bn + ".bias"] = self.scratch.take(s.cout)
+                    slot.grads[s.conv + ".bias"] = grad_view(conv.bias)
+                slot.grads[s.bn + ".weight"] = grad_view(bn.weight)
+                slot.grads[s.bn + ".bias"] = grad_view(bn.bias)
             self.scratch.off = (i + 1) * per_slot
             self.slots.append(slot)
 

@@ -189,6 +189,29 @@ class HotPathStep:
                 p.grad = None
         return loss
 
+    # ---- data-parallel step pieces ----------------------------------------------------------------------------------------
+    def groups(self):
+        """Parameter groups in the order the backward pass COMPLETES them: every roi_heads gradient (87 % of the bytes) is final
+        once the ROI pooling's backward has run, before the SlowFast module's backward starts."""
+        roi = [p for name, m in self.modules() if name != "slow_fast" for p in m.parameters()]
+        return [("roi_heads", roi), ("slow_fast", list(self.slow_fast.parameters()))]
+
+    def backward_split(self, loss, merged, on_roi_done=None):
+        """``loss.backward()`` in two phases with a callback in between: (1) the box / mask branches and the ROI pooling --
+        afterwards every roi_heads gradient is complete (``on_roi_done()`` may launch their all-reduce) -- (2) the SlowFast
+        module.  Gradients ACCUMULATE into p.grad like backward() does; with a gradient arena (ops.GRAD_ARENA) set p.grad = None
+        first so the arena slices are adopted instead of added to themselves."""
+        roi = [p for p in self.groups()[0][1] if p.requires_grad]
+        outs = [v for v in merged.values() if v.requires_grad]
+        grads = torch.autograd.grad(loss, roi + outs, allow_unused=True)
+        for p, g in zip(roi, grads):
+            if g is not None:
+                p.grad = g if p.grad is None else p.grad.add_(g)
+        if on_roi_done is not None:
+            on_roi_done()
+        live = [(o, g) for o, g in zip(outs, grads[len(roi):]) if g is not None]
+        torch.autograd.backward([o for o, _ in live], [g for _, g in live])
+
     def capture(self, features, warmup=2, pool=None):
         """Capture one forward+backward on ``features`` (static device buffers) into a CUDA graph: ~430 kernel launches
         become one graph launch, which removes the launch gaps between the (many short) kernels of the small pyramid
@@ -213,6 +236,50 @@ class HotPathStep:
             loss.backward()
         return graph, loss
 
+    def capture_split(self, features, zero_arena=False, warmup=1, pool=None):
+        """The same step as TWO graphs split where ``backward_split`` calls back: (forward + roi_heads backward, SlowFast
+        backward).  A data-parallel trainer replays the first, launches the all-reduce of the roi_heads gradient range, and
+        replays the second underneath it.  Needs ``ops.GRAD_ARENA`` (the gradients are static arena slices that successive
+        micro-batch graphs accumulate into; ``zero_arena`` puts the arena's clear at the head of the first graph).
+        Returns (graph1, graph2, loss)."""
+        from . import ops
+        arena = ops.GRAD_ARENA
+        assert arena is not None, "capture_split needs a gradient arena"
+        params = self.parameters()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                for p in params:
+                    p.grad = None
+                loss, merged = self.forward(features)
+                self.backward_split(loss, merged)
+        torch.cuda.current_stream().wait_stream(side)
+        try:
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
+        for p in params:
+            p.grad = None
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = pool if pool is not None else torch.cuda.graph_pool_handle()
+        box = {}
+        with torch.cuda.graph(g1, pool=pool):
+            if zero_arena:
+                arena.zero()
+            loss, merged = self.forward(features)
+            roi = [p for p in self.groups()[0][1] if p.requires_grad]
+            outs = [v for v in merged.values() if v.requires_grad]
+            grads = torch.autograd.grad(loss, roi + outs, allow_unused=True)
+            for p, g in zip(roi, grads):
+                if g is not None:
+                    p.grad = g
+            box["live"] = [(o, g) for o, g in zip(outs, grads[len(roi):]) if g is not None]
+        with torch.cuda.graph(g2, pool=pool):
+            torch.autograd.backward([o for o, _ in box["live"]], [g for _, g in box["live"]])
+        assert arena.adopted(), "autograd did not adopt the arena slices as .grad"
+        return g1, g2, loss
+
     def flops_per_step(self):
         conv = conv_flops(self.sp, self.fp, self.levels) * self.B
         mask = 3.0 * MASK_HEAD_FLOPS_PER_ROI * self.k_mask * self.B
@@ -221,6 +288,31 @@ class HotPathStep:
 
 
 def flat_grads(params):
-    """One contiguous f32 bucket holding every parameter gradient (what the DP step all-reduces)."""
+    """One contiguous f32 bucket holding every parameter gradient (a COPY; the data-parallel step uses dp.GradArena, where the
+    gradients are written into the flat buffer in the first place)."""
     gs = [p.grad for p in params if p.grad is not None]
     return torch.cat([g.reshape(-1) for g in gs]) if gs else None
+
+
+def synthetic_sequence(n_frames, levels=LEVELS, seed=1234, device="cpu", dtype=torch.float32, pin=False):
+    """OrderedDict {level: [n_frames,256,H,W]} of seeded unit-variance features: the backbone output of ONE sequence."""
+    d = OrderedDict()
+    for i, (k, (h, w)) in enumerate(levels.items()):
+        if device == "cpu":
+            g = torch.Generator().manual_seed(seed + i)
+            t = torch.randn(n_frames, 256, h, w, generator=g).to(dtype)
+            if pin:
+                t = t.pin_memory()
+        else:
+            g = torch.Generator(device=device).manual_seed(seed + i)
+            t = torch.randn(n_frames, 256, h, w, generator=g, device=device).to(dtype)
+        d[k] = t
+    return d
+
+
+def sequence_windows(seq, fp, first=0, count=None):
+    """The reference's clips (code/helpers/model.py:318-337): window w = frames [w, w+fp) of the sequence's features, as VIEWS
+    (consecutive windows share fp-1 frames; nothing is copied)."""
+    n = next(iter(seq.values())).shape[0] - fp + 1
+    count = n - first if count is None else count
+    return [OrderedDict((k, v[w:w + fp]) for k, v in seq.items()) for w in range(first, first + count)]

@@ -18,6 +18,7 @@ sample, timed on this box's host cores.  `--impl reference` times only that CPU 
 """
 import argparse
 import json
+from collections import OrderedDict
 import math
 import os
 import subprocess
@@ -134,8 +135,12 @@ def build_cpu_state():
             [torch.zeros(K_MASK, dtype=torch.int64)], [wl.IMAGE_HW], box_head, box_pred, box_lab, box_tgt)
 
 
-def time_cpu_reference(steps, warmup):
+def time_cpu_reference(steps, warmup, threads=None):
+    """-> (clip-frames/s, seconds per step): MEDIAN of ``steps`` timed repetitions after ``warmup`` (SURVEY 8(d) protocol)."""
+    import torch
     state = build_cpu_state()
+    if threads:
+        torch.set_num_threads(threads)
     for _ in range(warmup):
         cpu_reference_step(state)
     times = []
@@ -143,7 +148,7 @@ def time_cpu_reference(steps, warmup):
         t0 = time.perf_counter()
         cpu_reference_step(state)
         times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
+    sec = sorted(times)[len(times) // 2]
     return FP / sec, sec
 
 
@@ -151,10 +156,10 @@ def run_reference(args, rank):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    steps, warmup = min(steps, 5), min(warmup, 2)           # each step is seconds of CPU work
+    steps, warmup = max(3, min(steps, 5)), max(1, min(warmup, 2))     # each step is seconds of CPU work; >= 3 timed, median
     value, sec = time_cpu_reference(steps, warmup)
     cores = os.cpu_count() or 1
-    sample = f"1 clip (B=1, sp={SP}, fp={FP}, 5 levels, {K_BOX} box + {K_MASK} mask ROIs) fwd+bwd per step; {steps} timed steps after {warmup} warm-up"
+    sample = f"1 clip (B=1, sp={SP}, fp={FP}, 5 levels, {K_BOX} box + {K_MASK} mask ROIs) fwd+bwd per step; median of {steps} timed steps after {warmup} warm-up"
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -170,7 +175,7 @@ def run_reference(args, rank):
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from sfvos_b200 import ops, workload as wl
+    from sfvos_b200 import dp, ops, workload as wl
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -178,24 +183,45 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = _peaks()
-    step = wl.HotPathStep(SP, FP, B_PER_GPU, K_BOX, K_MASK, device=dev, precision="bf16")
+    micro = max(1, min(args.micro, B_PER_GPU))
+    n_micro = (B_PER_GPU + micro - 1) // micro
+    assert n_micro * micro == B_PER_GPU, "clips per GPU must be a multiple of --micro"
+    feat_dtype = torch.bfloat16 if args.feat_dtype == "bf16" else torch.float32
+    step = wl.HotPathStep(SP, FP, micro, K_BOX, K_MASK, device=dev, precision="bf16")
     params = step.parameters()
-    feats = wl.synthetic_features(B_PER_GPU, FP, device=dev, seed=1234 + 1000 * rank)
+    # The rank's clips are the B consecutive windows of ONE synthetic sequence of B + fp - 1 frames -- how the reference forms
+    # its clips (code/helpers/model.py:318-337: window w = frames [w, w+fp) of the cached backbone features) -- kept as ONE
+    # [frames,256,H,W] tensor per level; the clips are views of it.
+    n_frames = B_PER_GPU + FP - 1
+    seq = wl.synthetic_sequence(n_frames, seed=1234 + 1000 * rank, device=dev, dtype=feat_dtype)
+    chunks = lambda sq: [wl.sequence_windows(sq, FP, j * micro, micro) for j in range(n_micro)]
+    # gradients live in one flat arena: [roi_heads | slow_fast]; each range is all-reduced as soon as it is complete
+    arena = dp.GradArena(step.groups(), dev)
+    ops.GRAD_ARENA = arena
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4, foreach=True)       # code/train.py:80
 
-    def finish_step(loss, zero):
-        if world > 1:                                   # the one collective of the DP step: gradient all-reduce
-            bucket = wl.flat_grads(params)
-            dist.all_reduce(bucket)
-            ops.axpby(bucket, bucket, 1.0 / world, 0.0)
-        if zero:
+    def reduce_and_step(roi_work):
+        """Tail of the step: the (small) SlowFast range joins the roi_heads range already in flight, 1/world, SGD."""
+        if world > 1:
+            sf_work = dist.all_reduce(arena.range("slow_fast"), async_op=True)
+            roi_work.wait(); sf_work.wait()
+            ops.axpby(arena.flat, arena.flat, 1.0 / world, 0.0)
+        opt.step()
+
+    def launch_roi_allreduce():
+        return dist.all_reduce(arena.range("roi_heads"), async_op=True) if world > 1 else None
+
+    def eager_step(sq):
+        arena.zero()
+        work = [None]
+        for j, clips in enumerate(chunks(sq)):
             for p in params:
                 p.grad = None
+            loss, merged = step.forward(clips)
+            last = j == n_micro - 1
+            step.backward_split(loss, merged, (lambda: work.__setitem__(0, launch_roi_allreduce())) if last else None)
+        reduce_and_step(work[0])
         return loss
-
-    def one_step(features):
-        loss, _ = step.forward(features)
-        loss.backward()
-        return finish_step(loss, True)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -217,17 +243,18 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     for _ in range(max(3, args.warmup)):
-        one_step(feats)
+        eager_step(seq)
+    assert arena.adopted(), "gradient arena slices were not adopted as .grad"
     # ---- eager pass: K steps with CUDA events around every tensor-core / ROIAlign launch (per-kernel rooflines) ----
     # (single stream for this pass: with the pyramid levels on concurrent streams an event pair around a small level's launch
     # brackets the time it waits for SMs behind level 0's persistent kernels, not the kernel.  The timed region below runs the
     # levels concurrently.)
     prev_streams = os.environ.get("SFVOS_LEVEL_STREAMS")
     os.environ["SFVOS_LEVEL_STREAMS"] = "0"
-    one_step(feats)
+    eager_step(seq)
     ops.TIMING = []
     l0 = ops.launches()
-    ms_eager = timed(lambda: one_step(feats), args.steps)
+    ms_eager = timed(lambda: eager_step(seq), args.steps)
     launches = ops.launches() - l0
     timing, ops.TIMING = ops.TIMING, None
     if prev_streams is None:
@@ -235,38 +262,55 @@ def run_ours(args, rank, local_rank, world):
     else:
         os.environ["SFVOS_LEVEL_STREAMS"] = prev_streams
     step_peak = torch.cuda.max_memory_allocated(dev)           # features + one eager step
-    torch.cuda.empty_cache()                                    # the graph below captures into its own pool
+    torch.cuda.empty_cache()
 
-    # ---- timed region: K steps, inputs resident in HBM.  The step is replayed from a CUDA graph (same kernels, same
-    # order, one graph launch per step); SFVOS_GRAPH=0 or a failed capture falls back to the eager launches above ----
-    graph, mode = None, "eager"
+    # ---- timed region: K steps, inputs resident in HBM.  Every micro-batch is replayed from TWO CUDA graphs (forward +
+    # roi_heads backward | SlowFast backward) so that the all-reduce of the roi_heads gradient range can be launched in
+    # between and run under the second graph; SFVOS_GRAPH=0 or a failed capture falls back to the eager launches above ----
+    # Two input slots (device copies of the sequence) so that the e2e leg can fill one while the other is consumed.
+    h2d = sum(v.numel() * v.element_size() for v in seq.values())
+    slots = [seq]
+    free_now = torch.cuda.mem_get_info(dev)[0]
+    if free_now > (step_peak - h2d) + 2 * h2d + (6 << 30):
+        slots.append(OrderedDict((k, torch.empty_like(v)) for k, v in seq.items()))
+    graphs, mode = None, "eager"
     if os.environ.get("SFVOS_GRAPH", "1") != "0":
         try:
-            graph, g_loss = step.capture(feats)
+            pool = torch.cuda.graph_pool_handle()
+            graphs = [[step.capture_split(clips, zero_arena=(j == 0), pool=pool) for j, clips in enumerate(chunks(sq))] for sq in slots]
             mode = "cuda_graph"
         except Exception as exc:                        # keep the run valid: report the eager number
             print(f"bench: CUDA-graph capture failed ({exc.__class__.__name__}: {exc}); timing eager launches", file=sys.stderr)
-            graph = None
+            graphs = None
             for p in params:
                 p.grad = None
+
+    def graph_step(slot=0):
+        work = None
+        for j, (g1, g2, _) in enumerate(graphs[slot]):
+            g1.replay()
+            if j == n_micro - 1:
+                work = launch_roi_allreduce()
+            g2.replay()
+        reduce_and_step(work)
+        return graphs[slot][-1][2]
+
+    run_step = (lambda slot=0: graph_step(slot)) if graphs is not None else (lambda slot=0: eager_step(slots[slot]))
+    if graphs is not None:
+        # the replayed step must be the step: same loss as an eager forward on the same inputs and parameters
+        graphs[0][-1][0].replay()
+        g_loss = float(graphs[0][-1][2].detach())
+        ref_loss = float(step.forward(chunks(seq)[-1])[0].detach())
+        assert abs(g_loss - ref_loss) <= 1e-3 * max(1.0, abs(ref_loss)), (g_loss, ref_loss)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    if graph is not None:
-        def graph_step():
-            graph.replay()
-            return finish_step(g_loss, False)
-        for _ in range(2):
-            graph_step()
-        ms = timed(graph_step, args.steps)
-        # the replayed step must be the step: same loss as an eager forward on the same inputs and parameters
-        ref_loss = float(step.forward(feats)[0].detach())
-        assert abs(float(g_loss.detach()) - ref_loss) <= 1e-3 * max(1.0, abs(ref_loss)), (float(g_loss), ref_loss)
-    else:
-        ms = timed(lambda: one_step(feats), args.steps)
+    for _ in range(2):
+        run_step()
+    ms = timed(run_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- rooflines from the per-launch CUDA events of the timed region ----
+    # ---- rooflines from the per-launch CUDA events of the eager pass ----
     # tensor-core GEMM kernels: work = algorithmic FLOPs of the launch (no padding / halo / zero-tap FLOPs);
     # ROIAlign: work = algorithmic bytes of the launch (workload.roi_align_bytes).
     roi_bytes = {"roi_align_fwd_p7": wl.roi_align_bytes(step.box_props, 7, 4, 2),
@@ -286,16 +330,19 @@ def run_ours(args, rank, local_rank, world):
     dom = max(tensor, key=lambda k: tensor[k][1]) if tensor else None          # the kernel with the largest share of the step
     dom_f, dom_ms, dom_n = tensor[dom] if dom else (0.0, 0.0, 0)
     achieved = dom_f / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
-    traffic = None
+    traffic, traffic_src, dram = None, None, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"{dom}_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"{dom}_dram_bytes_per_launch")
+            traffic_src = tj.get("source")
+            dram = tj.get("roi_align_dram", {})
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "kernel": f"{dom}_kernel ({dom_n // max(1, args.steps)} launches/step: the dominant kernel by time)",
                 "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": traffic,
+                "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + ", sustained bf16",
                 "flops_per_launch": dom_f / max(1, dom_n), "us_per_launch": round(dom_ms * 1e3 / max(1, dom_n), 1),
                 "all_tensor_kernels": {"achieved": round(achieved_all, 1), "frac": round(achieved_all / peaks["bf16_sustained"], 4),
@@ -308,7 +355,16 @@ def run_ours(args, rank, local_rank, world):
         if t:
             roi["roi_align_" + tag] = {"bound": "hbm", "achieved": round(by / (t * 1e-3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
                                        "frac": round(by / (t * 1e-3) / 1e9 / peaks["hbm"], 4), "bytes_per_step": by / args.steps,
-                                       "ms_per_step": round(t / args.steps, 3)}
+                                       "ms_per_step": round(t / args.steps, 3), "basis": "algorithmic bytes (SURVEY 8(d) unique-footprint model)"}
+    for k, v in fam.items():                               # per launch kind, with the DRAM bytes ncu counted for it (if captured)
+        if k.startswith("roi_align_") and v[1]:
+            us = v[1] * 1e3 / v[2]
+            rec = {"us_per_launch": round(us, 1), "algorithmic_gbs": round(v[0] / v[2] / us / 1e3, 1)}
+            if k in dram:
+                rec["ncu_dram_bytes_per_launch"] = dram[k]
+                rec["dram_gbs"] = round(dram[k] / us / 1e3, 1)
+                rec["dram_frac_of_hbm_peak"] = round(dram[k] / us / 1e3 / peaks["hbm"], 4)
+            roi[k] = rec
     by_all = sum(v[0] for k, v in fam.items() if k.startswith("roi_align_"))
     t_all = sum(v[1] for k, v in fam.items() if k.startswith("roi_align_"))
     if t_all:                                               # all four ROIAlign launches of the step together
@@ -318,18 +374,12 @@ def run_ours(args, rank, local_rank, world):
     roofline["roi_align"] = roi
 
     # ---- end to end through the public API from pinned host buffers ----
-    # Every step's inputs come from pinned HOST memory and every step's loss goes back to the host, all inside the
-    # timed region.  The copies are software-pipelined like a data loader: step i+1's features cross PCIe on a copy
-    # stream into the second of two device buffers while step i computes, and each loss is read back asynchronously.
-    e2e_steps = max(2, min(args.steps, 4))
-    host = wl.synthetic_features(B_PER_GPU, FP, device="cpu", pin=True, seed=1234 + 1000 * rank)
-    h2d = sum(v.numel() * 4 for f in host for v in f.values())
-    graph = g_loss = None                                       # release the graph's private pool before the e2e buffers
-    torch.cuda.empty_cache()
-    # slot 0 reuses the device feature buffers of the timed region; a second slot (double buffering) if it fits next to a step
-    slots = [feats]
-    if torch.cuda.mem_get_info(dev)[0] > (step_peak - h2d) + h2d + (4 << 30):
-        slots.append([{k: torch.empty_like(v, device=dev) for k, v in f.items()} for f in host])
+    # Every step's inputs come from pinned HOST memory and every step's loss goes back to the host, all inside the timed
+    # region.  What crosses PCIe is the sequence's features, every frame ONCE (the windows are views; the reference's
+    # features_cache does the same on its side, model.py:191-227), in the feature dtype.  The copies are software-pipelined
+    # like a data loader: step i+1's sequence goes into the other device slot on a copy stream while step i computes.
+    e2e_steps = max(2, min(args.steps, 6))
+    host = wl.synthetic_sequence(n_frames, seed=1234 + 1000 * rank, device="cpu", dtype=feat_dtype, pin=True)
     ns = len(slots)
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(ns)]
@@ -339,9 +389,8 @@ def run_ours(args, rank, local_rank, world):
     def issue_copy(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[slot])
-            for fh, fd in zip(host, slots[slot]):
-                for k, v in fh.items():
-                    fd[k].copy_(v, non_blocking=True)
+            for k, v in host.items():
+                slots[slot][k].copy_(v, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def e2e_run(n):
@@ -353,7 +402,7 @@ def run_ours(args, rank, local_rank, world):
             if ns > 1 and i + 1 < n:
                 issue_copy((i + 1) % ns)
             cur.wait_event(ready[i % ns])
-            loss = one_step(slots[i % ns])
+            loss = run_step(i % ns)
             freed[i % ns].record(cur)
             if ns == 1 and i + 1 < n:
                 issue_copy(0)
@@ -374,31 +423,51 @@ def run_ours(args, rank, local_rank, world):
     e2e = {"value": round(world * B_PER_GPU * FP / (e2e_ms * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": 4 * world, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
            "h2d_gbs_per_gpu": round(h2d / (e2e_ms * 1e-3) / 1e9, 1),
-           "note": ("fp32 FPN features copied from pinned host memory every step, double-buffered on a copy stream so step "
-                    "i+1's H2D overlaps step i's compute; PCIe-bound (see h2d_gbs_per_gpu)") if ns > 1 else
-                   "fp32 FPN features copied from pinned host memory every step; single device buffer (a second one does not fit next "
-                   "to this configuration's step), so H2D and compute alternate"}
-    del slots
+           "note": (f"{args.feat_dtype} FPN features of the rank's {n_frames}-frame sequence copied from pinned host memory every step (each "
+                    f"frame once; the {B_PER_GPU} clips are windows = views of it), " +
+                    ("double-buffered on a copy stream so step i+1's H2D overlaps step i's compute" if ns > 1 else
+                     "single device buffer (a second one does not fit next to this configuration's step), so H2D and compute alternate"))}
+
+    vs_library = None
+    if rank == 0 and world == 1 and not args.no_lib:
+        graphs = None                                           # release the graphs' private pool first
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_library
+            vs_library = bench_library.run(SP, FP, min(B_PER_GPU, 8), K_BOX, K_MASK, dev="cuda")
+        except Exception as exc:
+            vs_library = {"error": f"{exc.__class__.__name__}: {exc}"}
+    roofline["vs_library"] = vs_library
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, sec = time_cpu_reference(1, 1)
+            v, sec = time_cpu_reference(3, 1)
             cpu = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"1 clip of the same workload (B=1) fwd+bwd on the host CPU, 1 warm-up + 1 timed step ({sec:.1f} s)"}
+                   "sample": f"1 clip of the same workload (B=1) fwd+bwd on the host CPU, 1 warm-up + 3 timed steps, median ({sec:.1f} s/step)"}
+            if not args.no_cpu_1t:
+                v1, sec1 = time_cpu_reference(1, 0, threads=1)
+                cpu["one_thread"] = {"value": round(v1, 4), "unit": UNIT, "cores": 1, "sample": f"the same clip on ONE thread, 1 timed step ({sec1:.1f} s)"}
         conv_f, mask_f = step.flops_per_step()
+        conv_f, mask_f = conv_f * n_micro, mask_f * n_micro
         line = {"metric": METRIC, "value": round(world * B_PER_GPU * FP / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"{CONFIG_NAME}: SlowFast temporal module (sp={SP}, fp={FP}) + multi-level ROIAlign + box head (fc6/fc7/predictor/fastrcnn_loss) + mask head/predictor/loss, fwd+bwd",
+                "config": {"workload": f"{CONFIG_NAME}: SlowFast temporal module (sp={SP}, fp={FP}) + multi-level ROIAlign + box head (fc6/fc7/predictor/fastrcnn_loss) + mask head/predictor/loss, fwd+bwd, gradient all-reduce (N>1), SGD step",
                            "clips_per_gpu": B_PER_GPU, "frames_per_clip": FP, "levels": "192x336,96x168,48x84,24x42,12x21 x256ch",
-                           "rois_per_clip": {"box": K_BOX, "mask": K_MASK}, "parallelism": f"dp{world} by clip, 1 NCCL grad all-reduce/step",
-                           "l2": f"inputs ({h2d / 1e9:.1f} GB of features per step) far exceed the 126 MB L2; no explicit flush",
+                           "clips": f"the {B_PER_GPU} windows of one synthetic {n_frames}-frame sequence per GPU (views; code/helpers/model.py:318-337), features {args.feat_dtype} [frames,256,H,W]",
+                           "micro_batches": n_micro, "clips_per_micro_batch": micro,
+                           "rois_per_clip": {"box": K_BOX, "mask": K_MASK},
+                           "parallelism": f"dp{world} by clip; gradients in one flat arena, roi_heads range all-reduced under the SlowFast backward, SlowFast range at the end",
+                           "optimizer": "torch.optim.SGD(lr 1e-3, momentum 0.9, weight_decay 1e-4, foreach) inside the timed region",
+                           "l2": f"inputs ({h2d / 1e9:.2f} GB of features) and activations (> 10 GB per step) far exceed the 126 MB L2; no explicit flush",
                            "launch": mode, "eager_ms_per_step": round(ms_eager, 3),
-                           "streams": "timed region: pyramid levels 1..4 on side streams inside the graph; per-kernel event pass: eager, one stream"},
+                           "streams": "timed region: pyramid levels 1..4 on side streams inside the graphs; per-kernel event pass: eager, one stream"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "model_tflops": round((conv_f + mask_f) * world / (ms * 1e-3) / 1e12, 1)}
         print(json.dumps(line), flush=True)
+    ops.GRAD_ARENA = None
     if world > 1:
         dist.destroy_process_group()
 
@@ -410,6 +479,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu-1t", action="store_true", help="skip the single-thread figure of the cpu_baseline leg")
+    ap.add_argument("--no-lib", action="store_true", help="skip the same-box library baselines (cuDNN / torchvision, roofline.vs_library)")
+    ap.add_argument("--feat-dtype", default="bf16", choices=["bf16", "fp32"], help="dtype of the FPN features handed to the module (host and device)")
+    ap.add_argument("--micro", type=int, default=8, help="clips per micro-batch (forward+backward call); a rank's clips run as ceil(clips/micro) calls whose gradients accumulate")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
                     help="BASELINE.json workload: c2 (default, the configuration the metric is quoted on), c3 long context, c5 DP training")
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: the config's)")
@@ -417,7 +490,7 @@ def main():
     global SP, FP, B_PER_GPU, CONFIG_NAME
     SP, FP, B_PER_GPU, CONFIG_NAME = CONFIGS[args.config]
     if args.config == "c5":
-        B_PER_GPU = max(1, 64 // max(1, args.gpus)) if args.gpus > 1 else 8      # global batch 64; one GPU cannot hold 64 clips
+        B_PER_GPU = max(8, 64 // max(1, args.gpus))      # global batch 64 over the ranks, 8 clips per micro-batch (one GPU alone: 8)
     if args.clips:
         B_PER_GPU = args.clips
     rank = int(os.environ.get("RANK", "0"))
@@ -431,8 +504,8 @@ def main():
         port = 29500 + (os.getpid() % 2000)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--config", args.config] + (["--no-cpu"] if args.no_cpu else []) + (
-                   ["--clips", str(args.clips)] if args.clips else [])
+               "--warmup", str(args.warmup), "--config", args.config, "--micro", str(args.micro), "--feat-dtype", args.feat_dtype] + (
+                   ["--no-cpu"] if args.no_cpu else []) + (["--clips", str(args.clips)] if args.clips else [])
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, local_rank, world)
 

@@ -210,9 +210,10 @@ int sfvos_relu_bwd(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const v
  * Layout.  Replaces torch.stack(...).transpose(1,2) at code/helpers/model.py:157-158 and
  * torch.cat(...).squeeze at :162 (the latter by writing both pathways into one channels-last buffer).
  * ------------------------------------------------------------------------------------------------------- */
-/* src f32 [F, C, HW] (frame stride src_fstride elements) -> dst (f32|bf16) [F, HW, cstride]. */
-int sfvos_nchw_to_nhwc(const float* src, int64_t src_fstride, void* dst, int32_t dst_dtype, int64_t dst_cstride,
-                       int64_t F, int64_t C, int64_t HW, sfvos_stream stream);
+/* src (f32|bf16) [F, C, HW] (frame stride src_fstride elements) -> dst (f32|bf16) [F, HW, cstride].  bf16 sources are what
+ * a feature cache kept in half the bytes hands over (host-resident windows cross PCIe at half the size). */
+int sfvos_nchw_to_nhwc(const void* src, int32_t src_dtype, int64_t src_fstride, void* dst, int32_t dst_dtype,
+                       int64_t dst_cstride, int64_t F, int64_t C, int64_t HW, sfvos_stream stream);
 /* src (f32|bf16) [F, HW, cstride] -> dst f32 [F, C, HW]. */
 int sfvos_nhwc_to_nchw(const void* src, int32_t src_dtype, int64_t src_cstride, float* dst, int64_t F, int64_t C,
                        int64_t HW, sfvos_stream stream);
