@@ -185,3 +185,60 @@ def test_sequence_sweep_full_size_level_is_bit_identical_to_windows():
         with torch.no_grad():
             win = mod.temporally_enhance_features([slow], [fast])["1"]
         assert torch.equal(seq[t:t + 1], win), t
+
+
+# ---- the ORACLE itself at BASELINE sizes: its torch graph runs on the GPU in IEEE fp32 (conftest.force_ieee_fp32) -------------
+@pytest.mark.parametrize("cfg,sp,fp,hw,B", [("C2 level 0", 1, 8, (192, 336), 2), ("C5 level 1", 2, 16, (96, 168), 2),
+                                            ("C3 level 1", 4, 32, (96, 168), 1)])
+def test_module_matches_the_oracle_at_baseline_sizes(cfg, sp, fp, hw, B):
+    """tcgen05 path and validation mode against oracle.slowfast_oracle.grads_of evaluated on CUDA tensors (the same functional
+    graph the CPU tests pin to the reference, cuDNN IEEE fp32 instead of oneDNN), at sizes where every kernel runs many waves
+    of full and partial tiles: outputs <= 1e-2 (bf16) / <= 1e-4 (validation mode) max-normalised; bf16 gradients against the
+    bf16-EMULATED oracle (the reference graph with conv operands rounded to bf16) in relative L2.  At these sizes (10^7..10^8
+    ReLU inputs) no input has a ReLU margin, so the validation mode's gradients upstream of a ReLU are held in relative L2 as
+    well: a handful of elements with |pre-activation| < 1e-6 have masks that cuDNN's fp32 summation order decides."""
+    from conftest import report
+    from oracle import slowfast_oracle as so
+    from sfvos_b200 import SlowFastLayers
+    g = torch.Generator(device=DEV).manual_seed(11)
+    fast = [OrderedDict([("0", torch.randn(fp, 256, hw[0], hw[1], device=DEV, generator=g))]) for _ in range(B)]
+    if B > 1:
+        fast[1]["0"][:fp // 2] = 0                                  # sequence start: zero-padded frames
+    slow = [so.slice_window(f, fp // 2, sp) for f in fast]
+    sd = OrderedDict((k, v.to(DEV)) for k, v in so.init_state_dict(sp, fp, seed=63).items())
+    ref_out, _, ref_grads, _ = so.grads_of(sd, slow, fast)
+    ref_out = {k: v.detach() for k, v in ref_out.items()}
+    emu_out, _, emu_grads, _ = so.grads_of(sd, slow, fast, emulate_bf16=True)
+    emu_out = {k: v.detach() for k, v in emu_out.items()}
+    torch.cuda.empty_cache()
+    skip = ("conv1.bias", "conv2.bias", "conv3.bias")
+    for prec in ("bf16", "fp32"):
+        torch.manual_seed(63)
+        m = SlowFastLayers(256, torch.device(DEV), sp, fp).to(DEV).train()
+        m.precision = prec
+        out = m.temporally_enhance_features(slow, fast)
+        so.module_loss(out).backward()
+        torch.cuda.synchronize()
+        e_out = _nerr(out["0"], ref_out["0"])
+        assert e_out <= (1e-2 if prec == "bf16" else 1e-4), (cfg, prec, e_out)
+        rec = {"out_vs_fp32_oracle": e_out}
+        if prec == "bf16":
+            rec["out_vs_bf16_emulated"] = _nerr(out["0"], emu_out["0"])
+            assert rec["out_vs_bf16_emulated"] <= 4e-3, (cfg, rec)
+        worst3, worst = 0.0, 0.0
+        for n, p in m.named_parameters():
+            if n.endswith(skip):
+                continue
+            ref = (emu_grads if prec == "bf16" else ref_grads)[n]
+            rel = (p.grad.double() - ref.double()).norm().item() / (ref.double().norm().item() + 1e-30)
+            if n.startswith(("fast_conv3", "slow_conv3", "bn_f3", "bn_s3")):
+                worst3 = max(worst3, _nerr(p.grad, ref))            # downstream of every ReLU: no masks involved
+            else:
+                worst = max(worst, rel)
+        rec["layer3_grad_max_norm"], rec["other_grads_rel_l2"] = worst3, worst
+        report("fullsize_oracle", cfg=cfg, precision=prec, **rec)
+        # measured (round 2, B200): see profiles/parity_r2.jsonl; bounds = ~3x the measured values
+        assert worst3 <= (2e-2 if prec == "bf16" else 1e-4), (cfg, prec, rec)
+        assert worst <= (5e-2 if prec == "bf16" else 1e-2), (cfg, prec, rec)
+        del m, out
+        torch.cuda.empty_cache()
