@@ -51,6 +51,7 @@ class BnRunningParams(ctypes.Structure):
 _SIGS = {
     "sfvos_version": [],
     "sfvos_device_check": [],
+    "sfvos_tma_overlap_supported": [vp],
     "sfvos_conv_umma": [ctypes.POINTER(ConvParams), vp],
     "sfvos_conv_simt": [ctypes.POINTER(ConvParams), vp],
     "sfvos_wgrad_umma": [ctypes.POINTER(WgradParams), vp],

@@ -101,3 +101,20 @@ int sfvos_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t
     }
     return SFVOS_OK;
 }
+
+// Can a tensor map describe OVERLAPPING windows, i.e. a batch stride smaller than the extent of the dimensions below it
+// (window b = frames [b, b+T) of one sequence buffer: stride_B = one frame)?  The TMA unit only forms base + sum(coord * stride),
+// but the driver validates the descriptor, so ask it once: encode a 5-D map {C, W, H, T, B} with stride_B = stride_T on the
+// caller's (16-byte aligned, never dereferenced) device pointer.
+extern "C" int sfvos_tma_overlap_supported(const void* dev_ptr) {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    if (sfvos_device_check() != SFVOS_OK || dev_ptr == nullptr) return 0;
+    CUtensorMap m;
+    const uint64_t C = 64, W = 16, H = 8, T = 4, B = 3;
+    const uint64_t dims[5] = {C, W, H, T, B};
+    const uint64_t strides[4] = {C * 2, W * C * 2, H * W * C * 2, H * W * C * 2};      // stride_B == stride_T: windows overlap
+    const uint32_t box[5] = {64, 16, 8, 1, 1};
+    cached = sfvos_make_tmap(&m, dev_ptr, 5, dims, strides, box, 128) == SFVOS_OK ? 1 : 0;
+    return cached;
+}

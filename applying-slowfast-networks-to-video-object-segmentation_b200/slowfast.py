@@ -16,7 +16,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 from ._lib import BF16, F32
 from .ops import Act
 
@@ -277,12 +277,45 @@ def _clips_to_act(clips, dtype):
 
 def _lists_to_acts(slow_list, fast_list, dt_act):
     """Per-clip [T,256,H,W] tensors -> (fast Act, slow Act); the slow window aliases the fast buffer when it is a frame
-    range of it (what the reference's _slice_features yields)."""
-    fast_in = _clips_to_act(fast_list, dt_act)
+    range of it (what the reference's _slice_features yields).  When the fast clips themselves are consecutive windows of one
+    sequence tensor (clip b = frames [b, b+T): how the reference forms its clips, model.py:318-337) every frame is converted
+    ONCE into a channels-last sequence buffer and the clips are overlapping views of it (batch stride = one frame)."""
     off = _alias_offset(slow_list, fast_list)
+    seq = _window_sequence(fast_list)
+    if seq is not None:
+        b, (t, c, h, w) = len(fast_list), fast_list[0].shape
+        buf = Act.empty(1, b + t - 1, h, w, c, dt_act, seq.device)
+        # tcgen05 path: the kernels address clips through a 5-D tensor map whose batch stride becomes one frame -- ask the
+        # driver once whether it encodes such a map; the CUDA-core validation mode uses plain pointer arithmetic
+        if dt_act == torch.float32 or _lib.load().sfvos_tma_overlap_supported(ops._p(buf.buf)) == 1:
+            ops.nchw_to_nhwc(seq, buf)
+            fast_in = Act(buf.buf, b, t, h, w, c, c, 0, bstride=h * w * c)
+            slow_in = fast_in.frames(off, off + slow_list[0].shape[0]) if off is not None else _clips_to_act(slow_list, dt_act)
+            return fast_in, slow_in
+    fast_in = _clips_to_act(fast_list, dt_act)
     if off is not None:
         return fast_in, fast_in.frames(off, off + slow_list[0].shape[0])
     return fast_in, _clips_to_act(slow_list, dt_act)
+
+
+def _window_sequence(fast_list):
+    """If clip b is frames [b, b+T) of ONE contiguous [F,C,H,W] tensor (same storage, consecutive start frames) return that
+    tensor's frames [0, B+T-1) as a view, else None.  SFVOS_WINDOW_DEDUP=0 disables the detection."""
+    if len(fast_list) < 2 or os.environ.get("SFVOS_WINDOW_DEDUP", "1") == "0":
+        return None
+    f0 = fast_list[0]
+    if f0.dtype not in (torch.float32, torch.bfloat16) or not f0.is_contiguous() or f0.dim() != 4:
+        return None
+    frame = f0[0].numel()
+    base = f0.untyped_storage().data_ptr()
+    for b, f in enumerate(fast_list):
+        if (f.shape != f0.shape or f.dtype != f0.dtype or not f.is_contiguous() or f.untyped_storage().data_ptr() != base
+                or f.storage_offset() != f0.storage_offset() + b * frame):
+            return None
+    n = len(fast_list) + f0.shape[0] - 1
+    if (f0.storage_offset() + n * frame) * f0.element_size() > f0.untyped_storage().nbytes():
+        return None
+    return torch.as_strided(f0, (n,) + tuple(f0.shape[1:]), f0.stride(), f0.storage_offset())
 
 
 def _alias_offset(slow_list, fast_list):

@@ -43,6 +43,12 @@ int sfvos_device_check(void);
  * measured launch times to kernels. */
 const char* sfvos_last_kernel(void);
 
+/* 1 iff the driver accepts tensor maps whose batch stride is smaller than a clip's extent, i.e. x_bstride = one frame:
+ * clip b = frames [b, b+T) of ONE channels-last sequence buffer.  That is how the reference's clips relate (consecutive
+ * windows of the cached per-frame features, code/helpers/model.py:318-337), and it lets the layout pass convert every frame
+ * once instead of once per window.  dev_ptr: any 16-byte aligned device pointer (not dereferenced). */
+int sfvos_tma_overlap_supported(const void* dev_ptr);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution (fprop and dgrad share one kernel).
  * Replaces aten::conv3d / cudnn_convolution reached from nn.Conv3d at code/helpers/model.py:72-76,83-90

@@ -452,3 +452,39 @@ def test_module_on_a_non_current_device():
     for a_list, b_list in zip(outs[0], outs[1]):
         for a, b in zip(a_list, b_list):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("sp,fp,dtype", [(1, 8, torch.float32), (3, 7, torch.bfloat16)])
+def test_consecutive_windows_of_a_sequence_are_converted_once(precision, sp, fp, dtype, monkeypatch):
+    """Clips that are consecutive windows of ONE sequence tensor (clip b = frames [b, b+fp): the reference's own clips,
+    model.py:318-337) take the de-duplicated input path: every frame is laid out channels-last once and the clips are
+    overlapping views (batch stride = one frame).  Same results as converting every window separately (SFVOS_WINDOW_DEDUP=0),
+    bit for bit in the validation mode; f32 and bf16 feature tensors."""
+    from sfvos_b200 import ops
+    n_win = 5
+    levels = OrderedDict([("0", (13, 21)), ("1", (8, 12)), ("pool", (4, 6))])
+    g = torch.Generator().manual_seed(31)
+    seq = OrderedDict((k, torch.randn(n_win + fp - 1, 256, h, w, generator=g).to(dtype).cuda()) for k, (h, w) in levels.items())
+    fast_c = [OrderedDict((k, v[b:b + fp]) for k, v in seq.items()) for b in range(n_win)]
+    slow_c = [so.slice_window(f, fp // 2, sp) for f in fast_c]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SFVOS_WINDOW_DEDUP", flag)
+        m = _module(sp, fp, precision).train()
+        before = ops.launches()
+        out = _train_step(m, slow_c, fast_c)
+        res[flag] = ([v.detach().clone() for v in out.values()], [p.grad.detach().clone() for p in m.parameters()], ops.launches() - before)
+    assert res["1"][2] < res["0"][2]                          # fewer layout launches: one per level instead of one per clip
+    for a_list, b_list in zip(res["1"][:2], res["0"][:2]):
+        for a, b in zip(a_list, b_list):
+            if precision == "fp32":
+                assert torch.equal(a, b)
+            else:
+                assert _rel_l2(a, b) <= 5e-2 or float(b.abs().max()) == 0
+    # and against the oracle on the same windows
+    slow = [OrderedDict((k, v.float().cpu()) for k, v in d.items()) for d in slow_c]
+    fast = [OrderedDict((k, v.float().cpu()) for k, v in d.items()) for d in fast_c]
+    ref_out, _, _, _ = so.grads_of(so.init_state_dict(sp, fp, seed=63), slow, fast)
+    for v, r in zip(res["1"][0], ref_out.values()):
+        assert _nerr(v, r) <= TOL[precision]
