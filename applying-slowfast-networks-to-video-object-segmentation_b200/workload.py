@@ -241,7 +241,8 @@ class HotPathStep:
         backward).  A data-parallel trainer replays the first, launches the all-reduce of the roi_heads gradient range, and
         replays the second underneath it.  Needs ``ops.GRAD_ARENA`` (the gradients are static arena slices that successive
         micro-batch graphs accumulate into; ``zero_arena`` puts the arena's clear at the head of the first graph).
-        Returns (graph1, graph2, loss)."""
+        Returns (graph1, graph2, loss).  Drop every reference to earlier losses / outputs of this step first: a live autograd
+        graph keeps the parameters' AccumulateGrad nodes of the stream it ran on, and a capture cannot wait on the legacy stream."""
         from . import ops
         arena = ops.GRAD_ARENA
         assert arena is not None, "capture_split needs a gradient arena"
