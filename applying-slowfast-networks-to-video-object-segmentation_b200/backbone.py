@@ -1,0 +1,167 @@
+"""The step BEFORE the hot path: the feature-pyramid half of the frozen backbone and the RPN head on
+libsfvos.so, behind torchvision's own module interfaces, producing the channels-last bf16 features the temporal module
+consumes without a layout pass.
+
+  FeaturePyramidNetwork <- torchvision.ops.FeaturePyramidNetwork        (TV/ops/feature_pyramid_network.py)
+                           lateral 1x1 convs C_l -> 256, top-down nearest-upsample + add, 3x3 output convs, LastLevelMaxPool
+  RPNHead               <- torchvision...rpn.RPNHead                    (TV/models/detection/rpn.py)
+                           3x3 conv + ReLU, then cls_logits (A) and bbox_pred (4A) as ONE 1x1 GEMM
+  AnchorGenerator       <- torchvision...anchor_utils.AnchorGenerator   (anchors stay f32 whatever the feature dtype)
+  install_backbone(maskrcnn_model)   swaps them in IN PLACE (same parameters / state_dict keys), like roi_heads.install
+
+Reference call sites: code/helpers/model.py:204 (``self.maskrcnn_model.backbone(batch_imgs)``) and :236-240
+(``self.maskrcnn_model.rpn(...)``); both are frozen (model.py:176-179), so there is no backward here and the packed weights
+are cached until a parameter changes.
+
+Per 480x854 frame this is 219 of the ~390 GFLOP of backbone + RPN (FPN output convs 101, RPN conv 101, laterals 16, heads
+0.7); the ResNet-50 body (stride-2 convolutions, 7x7 stem, max-pool) stays torchvision.  Anchor generation, box decoding
+and NMS stay torchvision."""
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+from torchvision.models.detection import anchor_utils as tv_anchor_utils
+from torchvision.models.detection import rpn as tv_rpn
+from torchvision.ops import feature_pyramid_network as tv_fpn
+
+from . import ops
+from ._lib import BF16, F32, call
+from .ops import Act, _p, stream
+from .roi_heads import _act_dtype, _default_precision, _nchw_view, _to_cl_act
+
+_PACKED = {}      # (data_ptr, mode, umma) -> (version, device, packed operand, Cp): the backbone / RPN weights are frozen
+
+
+def _packed(w, umma):
+    """[Cout,Cin,kh,kw] parameter -> fprop GEMM operand, cached until the parameter is written to."""
+    cin = w.shape[1]
+    cp = (cin + 63) // 64 * 64 if umma else cin
+    key = (w.data_ptr(), umma)
+    tag = (w._version, str(w.device), tuple(w.shape))
+    hit = _PACKED.get(key)
+    if hit is None or hit[0] != tag or torch.cuda.is_current_stream_capturing():
+        hit = (tag, ops.pack_weights(w, 0, BF16 if umma else F32, cp), cp)
+        if not torch.cuda.is_current_stream_capturing():
+            _PACKED[key] = hit
+    return hit[1], hit[2]
+
+
+def _conv(x, w, b, umma, out_dtype, relu=False):
+    """x: channels-last Act [N,1,H,W,Cin]; w [Cout,Cin,k,k] (k = 1 or 3, stride 1, 'same' padding), b [Cout] -> Act."""
+    cout, _, kh, kw = w.shape
+    assert kh == kw and kh in (1, 3), "1x1 and 3x3 convolutions only"
+    wp, cp = _packed(w, umma)
+    y = Act.empty(x.B, 1, x.H, x.W, cout, out_dtype, x.buf.device)
+    if x.npix:
+        ops.conv(x, wp, cp, cout, (1, kh, kw), (0, kh // 2, kw // 2), 1, y, umma=umma, relu=relu,
+                 shift=None if b is None else b.detach().float())
+    return y
+
+
+class FeaturePyramidNetwork(tv_fpn.FeaturePyramidNetwork):
+    """Same ctor / parameters / state_dict keys (``inner_blocks.{i}.0.*``, ``layer_blocks.{i}.0.*``) as torchvision's; forward
+    on libsfvos.  Returns ``{name: [N,256,H,W]}`` with channels_last strides, bf16 on the product path (f32 with
+    ``precision == "fp32"``): exactly what SlowFastLayers lays out as its input, so no conversion pass follows."""
+
+    precision = None
+
+    @ops.device_guard
+    def forward(self, x: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        ops.device_check()
+        precision = self.precision or _default_precision()
+        umma, dt_act = precision != "fp32", _act_dtype(precision)
+        names, feats = list(x.keys()), list(x.values())
+        n = len(feats)
+        for blk in list(self.inner_blocks) + list(self.layer_blocks):
+            assert len(blk) == 1, "norm / activation layers inside the FPN blocks are not supported"
+        # lateral 1x1 convolutions, f32 results (the top-down chain adds up to n of them)
+        inner = [_conv(_to_cl_act(f, dt_act), self.inner_blocks[i][0].weight, self.inner_blocks[i][0].bias, umma, torch.float32)
+                 for i, f in enumerate(feats)]
+        results = [None] * n
+        for i in range(n - 1, -1, -1):
+            a = inner[i]
+            top = inner[i + 1] if i + 1 < n else None
+            merged = a if not umma else Act.empty(a.B, 1, a.H, a.W, a.C, torch.bfloat16, a.buf.device)
+            if a.npix and (top is not None or umma):
+                call("sfvos_upsample_add", top.ptr() if top is not None else None, top.H if top is not None else 0,
+                     top.W if top is not None else 0, a.ptr(), merged.ptr() if umma else None, a.B, a.H, a.W, a.C, stream())
+            out = _conv(merged, self.layer_blocks[i][0].weight, self.layer_blocks[i][0].bias, umma, dt_act)
+            results[i] = _nchw_view(out.buf, out.B, out.H, out.W, out.C)
+        if self.extra_blocks is not None:
+            if isinstance(self.extra_blocks, tv_fpn.LastLevelMaxPool):
+                # max_pool2d(kernel 1, stride 2) = every second row / column of the coarsest map
+                results.append(results[-1][:, :, ::2, ::2].contiguous(memory_format=torch.channels_last))
+                names = names + ["pool"]
+            else:
+                results, names = self.extra_blocks(results, feats, names)
+        return OrderedDict(zip(names, results))
+
+
+class RPNHead(tv_rpn.RPNHead):
+    """Same ctor / parameters / state_dict keys (``conv.{i}.0.*``, ``cls_logits.*``, ``bbox_pred.*``) as torchvision's.
+    Returns (objectness [N,A,H,W], box deltas [N,4A,H,W]) per level, f32."""
+
+    precision = None
+
+    @ops.device_guard
+    def forward(self, x: List[Tensor]) -> Tuple[List[Tensor], List[Tensor]]:
+        ops.device_check()
+        precision = self.precision or _default_precision()
+        umma, dt_act = precision != "fp32", _act_dtype(precision)
+        a_cls, a_box = self.cls_logits.out_channels, self.bbox_pred.out_channels
+        n_pad = (a_cls + a_box + 31) // 32 * 32
+        dev = self.cls_logits.weight.device
+        # cls_logits and bbox_pred as one GEMM over the stacked (zero-padded) weight
+        key = ("rpn_pred", self.cls_logits.weight.data_ptr(), self.cls_logits.weight._version, self.bbox_pred.weight._version,
+               self.cls_logits.bias._version, self.bbox_pred.bias._version, str(dev))
+        hit = _PACKED.get("rpn_pred")
+        if hit is None or hit[0] != key or torch.cuda.is_current_stream_capturing():
+            w = torch.zeros(n_pad, self.cls_logits.in_channels, 1, 1, dtype=torch.float32, device=dev)
+            b = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+            w[:a_cls] = self.cls_logits.weight.detach(); w[a_cls:a_cls + a_box] = self.bbox_pred.weight.detach()
+            b[:a_cls] = self.cls_logits.bias.detach(); b[a_cls:a_cls + a_box] = self.bbox_pred.bias.detach()
+            hit = (key, w, b)
+            if not torch.cuda.is_current_stream_capturing():
+                _PACKED["rpn_pred"] = hit
+        _, w_pred, b_pred = hit
+        logits, bbox_reg = [], []
+        for feature in x:
+            t = _to_cl_act(feature, dt_act)
+            for blk in self.conv:
+                t = _conv(t, blk[0].weight, blk[0].bias, umma, dt_act, relu=True)
+            pred = _conv(t, w_pred, b_pred, umma, torch.float32)
+            out = torch.empty(t.B, n_pad, t.H, t.W, dtype=torch.float32, device=dev)
+            if t.npix:
+                ops.nhwc_to_nchw(pred, out)
+            logits.append(out[:, :a_cls].contiguous())
+            bbox_reg.append(out[:, a_cls:a_cls + a_box].contiguous())
+        return logits, bbox_reg
+
+
+class AnchorGenerator(tv_anchor_utils.AnchorGenerator):
+    """torchvision's generator takes the anchors' dtype from the feature maps; with bf16 features that would quantise box
+    coordinates to 8 px.  Only the maps' spatial sizes are needed, so hand it f32 stand-ins of the same shape."""
+
+    def forward(self, image_list, feature_maps: List[Tensor]) -> List[Tensor]:
+        proxies = [torch.empty((1, 1) + tuple(f.shape[-2:]), dtype=torch.float32, device=f.device) for f in feature_maps]
+        return super().forward(image_list, proxies)
+
+
+def install_backbone(maskrcnn_model, precision: Optional[str] = None):
+    """Swap the libsfvos FPN / RPN head into a torchvision Mask R-CNN IN PLACE (same parameters, same state_dict keys).
+    Returns the model."""
+    precision = precision or _default_precision()
+    fpn = getattr(maskrcnn_model.backbone, "fpn", None)
+    if fpn is not None and type(fpn) in (tv_fpn.FeaturePyramidNetwork, FeaturePyramidNetwork) and \
+            all(len(b) == 1 for b in list(fpn.inner_blocks) + list(fpn.layer_blocks)):
+        fpn.__class__ = FeaturePyramidNetwork
+        fpn.precision = precision
+    head = maskrcnn_model.rpn.head
+    if type(head) in (tv_rpn.RPNHead, RPNHead) and all(len(b) == 2 for b in head.conv):
+        head.__class__ = RPNHead
+        head.precision = precision
+    gen = maskrcnn_model.rpn.anchor_generator
+    if type(gen) in (tv_anchor_utils.AnchorGenerator, AnchorGenerator):
+        gen.__class__ = AnchorGenerator
+    return maskrcnn_model

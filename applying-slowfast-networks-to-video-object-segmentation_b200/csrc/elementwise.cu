@@ -528,6 +528,35 @@ nhwc_to_nchw_kernel(const InT* __restrict__ src, long long src_cstride, float* d
     }
 }
 
+// FPN top-down merge (TV/ops/feature_pyramid_network.py: F.interpolate(last_inner, size, mode="nearest") + inner_lateral):
+// inner[n,h,w,:] += top[n, floor(h*Ht/H), floor(w*Wt/W), :] in place on the f32 lateral output, plus the bf16 copy the 3x3
+// output convolution reads.  top == nullptr (coarsest level): only the bf16 copy.  8 channels per thread.
+__global__ void __launch_bounds__(256)
+upsample_add_kernel(const float* __restrict__ top, int Ht, int Wt, float* inner, __nv_bfloat16* out, int H, int W, int C, long long total8) {
+    const int C8 = C / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long long pix = i / C8;
+        const int w = (int)(pix % W); pix /= W;
+        const int h = (int)(pix % H);
+        const long long n = pix / H;
+        float v[8];
+        float* ip = inner + (((n * H + h) * W + w) * (long long)C) + cg * 8;
+        load8(ip, v);
+        if (top != nullptr) {
+            // torch 'nearest': src = min(floor(dst * in / out), in - 1), computed in float like ATen (scale = in / out)
+            const int hs = min((int)floorf(h * ((float)Ht / (float)H)), Ht - 1);
+            const int ws = min((int)floorf(w * ((float)Wt / (float)W)), Wt - 1);
+            float t[8];
+            load8(top + (((n * Ht + hs) * Wt + ws) * (long long)C) + cg * 8, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j];
+            store8(ip, v);
+        }
+        if (out != nullptr) store8(out + (((n * H + h) * W + w) * (long long)C) + cg * 8, v);
+    }
+}
+
 __global__ void axpby_kernel(const float* __restrict__ x, float* y, float a, float b, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
@@ -788,6 +817,18 @@ extern "C" int sfvos_nhwc_to_nchw(const void* src, int32_t src_dtype, int64_t sr
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)F), block(32, 8);
     if (src_dtype == SFVOS_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_cstride, dst, (int)C, HW);
     else nhwc_to_nchw_kernel<float><<<grid, block, 0, CS(stream)>>>(reinterpret_cast<const float*>(src), src_cstride, dst, (int)C, HW);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_upsample_add(const float* top, int64_t Ht, int64_t Wt, float* inner, void* out_bf16, int64_t N, int64_t H,
+                                  int64_t W, int64_t C, sfvos_stream stream) {
+    SF_CHECK(C % 8 == 0 && inner != nullptr, "upsample_add: C must be a multiple of 8 and inner non-null");
+    SF_CHECK(top == nullptr || (Ht >= 1 && Wt >= 1 && Ht <= H && Wt <= W), "upsample_add: the coarser map must not be larger");
+    const long long total8 = N * H * W * (C / 8);
+    if (total8 == 0) return SFVOS_OK;
+    upsample_add_kernel<<<grid_for(total8, 256), 256, 0, CS(stream)>>>(top, (int)Ht, (int)Wt, inner, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                                     (int)H, (int)W, (int)C, total8);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

@@ -317,6 +317,16 @@ int sfvos_paste_masks(const float* masks, const float* boxes, int64_t K, int32_t
                       int64_t im_w, float* out, sfvos_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * FPN top-down merge.  Replaces F.interpolate(last_inner, size=..., mode="nearest") + the addition at
+ * TV/ops/feature_pyramid_network.py (FeaturePyramidNetwork.forward), reached from code/helpers/model.py:204 through
+ * maskrcnn_model.backbone.  inner f32 [N,H,W,C] (the lateral 1x1 convolution's output) += top f32 [N,Ht,Wt,C] at the
+ * nearest coarser pixel (ATen's floor(dst * in / out) rule), in place; out_bf16 (may be NULL) receives the bf16 copy that
+ * the 3x3 output convolution reads.  top == NULL: only the copy (coarsest level).
+ * ------------------------------------------------------------------------------------------------------- */
+int sfvos_upsample_add(const float* top, int64_t Ht, int64_t Wt, float* inner, void* out_bf16, int64_t N, int64_t H,
+                       int64_t W, int64_t C, sfvos_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Optimiser-side helpers for the data-parallel step (the one collective is NCCL all-reduce, called from Python).
  * ------------------------------------------------------------------------------------------------------- */
 /* y[i] = a*x[i] + b*y[i]  (flat f32), used to fold 1/world_size into the reduced gradient bucket. */

@@ -237,8 +237,11 @@ def test_module_matches_the_oracle_at_baseline_sizes(cfg, sp, fp, hw, B):
                 worst = max(worst, rel)
         rec["layer3_grad_max_norm"], rec["other_grads_rel_l2"] = worst3, worst
         report("fullsize_oracle", cfg=cfg, precision=prec, **rec)
-        # measured (round 2, B200): see profiles/parity_r2.jsonl; bounds = ~3x the measured values
-        assert worst3 <= (2e-2 if prec == "bf16" else 1e-4), (cfg, prec, rec)
-        assert worst <= (5e-2 if prec == "bf16" else 1e-2), (cfg, prec, rec)
+        # measured (round 2, B200, profiles/parity_r2.jsonl): bf16 outputs 5.4-6.7e-3 vs the fp32 oracle and 1.9-2.0e-3 vs the
+        # emulation, layer-3 gradients 2.4-3.2e-3, other gradients 2.1-3.1e-2 (relative L2 vs the emulation); validation mode
+        # outputs 2.7-4.3e-6, layer-3 gradients 3.1-5.1e-6, other gradients 2.2-3.5e-3 (mask flips against cuDNN's fp32 sums).
+        # Bounds = 2-3x the measured values.
+        assert worst3 <= (1e-2 if prec == "bf16" else 2e-5), (cfg, prec, rec)
+        assert worst <= (6e-2 if prec == "bf16" else 1e-2), (cfg, prec, rec)
         del m, out
         torch.cuda.empty_cache()
