@@ -68,6 +68,10 @@ class FeaturePyramidNetwork(tv_fpn.FeaturePyramidNetwork):
 
     @ops.device_guard
     def forward(self, x: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(v.requires_grad for v in x.values())):
+            # the reference freezes backbone and RPN (code/helpers/model.py:176-179) and calls them under no_grad (:324-333);
+            # someone fine-tuning the FPN gets torchvision's differentiable forward -- this module has no backward
+            return super().forward(x)
         ops.device_check()
         precision = self.precision or _default_precision()
         umma, dt_act = precision != "fp32", _act_dtype(precision)
@@ -106,6 +110,8 @@ class RPNHead(tv_rpn.RPNHead):
 
     @ops.device_guard
     def forward(self, x: List[Tensor]) -> Tuple[List[Tensor], List[Tensor]]:
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(v.requires_grad for v in x)):
+            return super().forward([v.float() for v in x])         # trainable RPN head: torchvision's differentiable forward
         ops.device_check()
         precision = self.precision or _default_precision()
         umma, dt_act = precision != "fp32", _act_dtype(precision)

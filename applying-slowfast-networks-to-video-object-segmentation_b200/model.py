@@ -15,6 +15,7 @@ from torch import nn
 from torchvision.models.detection.faster_rcnn import FastRCNNPredictor
 from torchvision.models.detection.image_list import ImageList
 
+from . import backbone as sf_backbone
 from . import roi_heads as sf_roi_heads
 from .roi_heads import MaskRCNNPredictor
 from .slowfast import SlowFastLayers
@@ -64,6 +65,9 @@ class SegmentationModel(nn.Module):
                                         fast_pathway_size=fast_pathway_size)
         self.maskrcnn_model.roi_heads.detections_per_img = 10
         sf_roi_heads.install(self.maskrcnn_model.roi_heads)      # same parameters, libsfvos kernels
+        if os.environ.get("SFVOS_NATIVE_BACKBONE", "1") != "0":
+            # FPN + RPN head on libsfvos as well: channels-last bf16 features, no layout pass afterwards
+            sf_backbone.install_backbone(self.maskrcnn_model)
         self.features_cache = {}
         self.use_caching = True
         # eval only: one temporal sweep per sequence chunk instead of one window per frame (same outputs, see
@@ -97,9 +101,13 @@ class SegmentationModel(nn.Module):
         for key in per_frame[0].keys():
             stacked = torch.cat([f[key] for f in per_frame])
             if left or right:        # out-of-sequence frames are all-zero feature maps (model.py:215-225)
-                pad_l = stacked.new_zeros((left,) + stacked.shape[1:])
-                pad_r = stacked.new_zeros((right,) + stacked.shape[1:])
-                stacked = torch.cat([pad_l, stacked, pad_r])
+                fmt = torch.channels_last if stacked.is_contiguous(memory_format=torch.channels_last) else torch.contiguous_format
+                parts = [stacked]
+                if left:
+                    parts.insert(0, torch.zeros((left,) + stacked.shape[1:], dtype=stacked.dtype, device=stacked.device).contiguous(memory_format=fmt))
+                if right:
+                    parts.append(torch.zeros((right,) + stacked.shape[1:], dtype=stacked.dtype, device=stacked.device).contiguous(memory_format=fmt))
+                stacked = torch.cat(parts)
             out[key] = stacked
         return out
 

@@ -235,8 +235,7 @@ class SlowFastLayers(nn.Module):
                         fast_in.buf[:left * per].zero_()
                     if right:
                         fast_in.buf[(t_in - right) * per:].zero_()
-                    src = _as_source(x[f0 + hl:f1 + hl].to(dev))
-                    ops.nchw_to_nhwc(src, fast_in, frame_off=left)
+                    _fill_frames(fast_in, left, x[f0 + hl:f1 + hl].to(dev))
                     slow_in = fast_in.frames(s_off, s_off + (c1 - c0) + sp - 1)
                     chunk_outs[key] = _level_forward(self, slow_in, fast_in, False, None).as_nchw()
             for st in streams:
@@ -250,6 +249,31 @@ class SlowFastLayers(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------------
 # engine
 # ----------------------------------------------------------------------------------------------------------------------
+def _frame_layout(t):
+    """"nchw" / "nhwc": how the frames of a [F,C,H,W] tensor are laid out when each frame is dense and frames are
+    consecutive (a frame range of such a tensor is again one); None otherwise.  "nhwc" = torch.channels_last, what the
+    libsfvos FPN (backbone.py) emits."""
+    if t.dim() != 4:
+        return None
+    if t.is_contiguous():
+        return "nchw"
+    if t.permute(0, 2, 3, 1).is_contiguous():
+        return "nhwc"
+    return None
+
+
+def _fill_frames(dst, frame_off, src):
+    """Frames [frame_off, frame_off+F) of the dense channels-last Act ``dst`` <- src [F,C,H,W] of any layout / float dtype:
+    one layout-conversion launch, or a plain copy when the source already is channels-last in the activation dtype."""
+    f, c, h, w = src.shape
+    if (src.dtype == dst.buf.dtype and dst.cstride == c and _frame_layout(src) == "nhwc" and src.device == dst.buf.device):
+        per = h * w * c
+        o = dst.ch_off + frame_off * per
+        dst.buf[o:o + f * per].view(f, h, w, c).copy_(src.permute(0, 2, 3, 1))
+    else:
+        ops.nchw_to_nhwc(_as_source(src), dst, frame_off=frame_off)
+
+
 def _as_source(x):
     """Contiguous f32 or bf16 tensor (the layout kernel reads both; anything else is converted to f32 first)."""
     if x.dtype not in (torch.float32, torch.bfloat16):
@@ -271,7 +295,7 @@ def _clips_to_act(clips, dtype):
     t, c, h, w = clips[0].shape
     act = Act.empty(len(clips), t, h, w, c, dtype, clips[0].device)
     for b, clip in enumerate(clips):
-        ops.nchw_to_nhwc(_as_source(clip), act, frame_off=b * t)
+        _fill_frames(act, b * t, clip)
     return act
 
 
@@ -284,12 +308,16 @@ def _lists_to_acts(slow_list, fast_list, dt_act):
     seq = _window_sequence(fast_list)
     if seq is not None:
         b, (t, c, h, w) = len(fast_list), fast_list[0].shape
-        buf = Act.empty(1, b + t - 1, h, w, c, dt_act, seq.device)
         # tcgen05 path: the kernels address clips through a 5-D tensor map whose batch stride becomes one frame -- ask the
         # driver once whether it encodes such a map; the CUDA-core validation mode uses plain pointer arithmetic
-        if dt_act == torch.float32 or _lib.load().sfvos_tma_overlap_supported(ops._p(buf.buf)) == 1:
-            ops.nchw_to_nhwc(seq, buf)
-            fast_in = Act(buf.buf, b, t, h, w, c, c, 0, bstride=h * w * c)
+        if dt_act == torch.float32 or _lib.load().sfvos_tma_overlap_supported(ops._p(seq)) == 1:
+            if _frame_layout(seq) == "nhwc" and seq.dtype == dt_act and seq.data_ptr() % 16 == 0:
+                flat = seq.permute(0, 2, 3, 1).reshape(-1)            # already channels-last in the activation dtype: no copy
+            else:
+                buf = Act.empty(1, b + t - 1, h, w, c, dt_act, seq.device)
+                _fill_frames(buf, 0, seq)
+                flat = buf.buf
+            fast_in = Act(flat, b, t, h, w, c, c, 0, bstride=h * w * c)
             slow_in = fast_in.frames(off, off + slow_list[0].shape[0]) if off is not None else _clips_to_act(slow_list, dt_act)
             return fast_in, slow_in
     fast_in = _clips_to_act(fast_list, dt_act)
@@ -304,12 +332,13 @@ def _window_sequence(fast_list):
     if len(fast_list) < 2 or os.environ.get("SFVOS_WINDOW_DEDUP", "1") == "0":
         return None
     f0 = fast_list[0]
-    if f0.dtype not in (torch.float32, torch.bfloat16) or not f0.is_contiguous() or f0.dim() != 4:
+    layout = _frame_layout(f0)
+    if f0.dtype not in (torch.float32, torch.bfloat16) or layout is None:
         return None
     frame = f0[0].numel()
     base = f0.untyped_storage().data_ptr()
     for b, f in enumerate(fast_list):
-        if (f.shape != f0.shape or f.dtype != f0.dtype or not f.is_contiguous() or f.untyped_storage().data_ptr() != base
+        if (f.shape != f0.shape or f.dtype != f0.dtype or _frame_layout(f) != layout or f.untyped_storage().data_ptr() != base
                 or f.storage_offset() != f0.storage_offset() + b * frame):
             return None
     n = len(fast_list) + f0.shape[0] - 1
@@ -323,7 +352,8 @@ def _alias_offset(slow_list, fast_list):
     model.py:242-248, yields exactly such views) return the common first-frame offset, else None."""
     off = None
     for s, f in zip(slow_list, fast_list):
-        if not (s.is_contiguous() and f.is_contiguous() and s.dtype == f.dtype and f.dtype in (torch.float32, torch.bfloat16)):
+        if not (_frame_layout(f) is not None and _frame_layout(s) == _frame_layout(f) and s.dtype == f.dtype
+                and f.dtype in (torch.float32, torch.bfloat16)):
             return None
         if s.untyped_storage().data_ptr() != f.untyped_storage().data_ptr() or s.shape[1:] != f.shape[1:]:
             return None

@@ -1,0 +1,116 @@
+"""GPU parity of the step BEFORE the hot path: the libsfvos FeaturePyramidNetwork and RPNHead against the
+torchvision modules they replace (reached from code/helpers/model.py:204,236-240), same parameters, same state_dict keys;
+<= 1e-4 in the fp32 validation mode, <= 1e-2 in bf16 (max-normalised)."""
+import copy
+from collections import OrderedDict
+
+import pytest
+import torch
+import torchvision
+from torchvision.models.detection.image_list import ImageList
+from torchvision.models.detection.rpn import RPNHead as TVRPNHead
+from torchvision.ops import FeaturePyramidNetwork as TVFPN
+from torchvision.ops.feature_pyramid_network import LastLevelMaxPool
+
+from conftest import report
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+def _nerr(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("hw", [(48, 84), (45, 83)])
+def test_fpn_matches_torchvision(precision, hw):
+    from sfvos_b200 import FeaturePyramidNetwork
+    torch.manual_seed(3)
+    chans = [256, 512, 1024, 2048]
+    ref = TVFPN(chans, 256, extra_blocks=LastLevelMaxPool()).cuda()
+    ours = copy.deepcopy(ref)
+    ours.__class__ = FeaturePyramidNetwork
+    ours.precision = precision
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    g = torch.Generator().manual_seed(4)
+    x = OrderedDict()
+    h, w = hw
+    for i, c in enumerate(chans):
+        x[str(i)] = torch.randn(2, c, h, w, generator=g).cuda()
+        h, w = (h + 1) // 2, (w + 1) // 2
+    with torch.no_grad():
+        want = ref(x)
+        got = ours(x)
+    assert list(got.keys()) == list(want.keys()) == ["0", "1", "2", "3", "pool"]
+    for k in want:
+        assert got[k].shape == want[k].shape
+        assert got[k].dtype == (torch.float32 if precision == "fp32" else torch.bfloat16)
+        assert got[k].permute(0, 2, 3, 1).is_contiguous()              # channels-last: what SlowFastLayers lays out itself
+        e = _nerr(got[k], want[k])
+        report("fpn", precision=precision, hw=str(hw), level=k, max_norm=e)
+        assert e <= TOL[precision], (k, e)
+    # channels-last bf16 inputs (a bf16 body) are consumed in place
+    if precision == "bf16":
+        xb = OrderedDict((k, v.bfloat16().contiguous(memory_format=torch.channels_last)) for k, v in x.items())
+        with torch.no_grad():
+            got2 = ours(xb)
+        for k in want:
+            assert _nerr(got2[k], want[k]) <= 1.5e-2, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_rpn_head_matches_torchvision(precision):
+    from sfvos_b200 import RPNHead
+    torch.manual_seed(5)
+    ref = TVRPNHead(256, 3).cuda()
+    for p in ref.parameters():                                           # torchvision's init (std 0.01, zero bias) is nearly degenerate
+        torch.nn.init.normal_(p, std=0.05)
+    ours = copy.deepcopy(ref)
+    ours.__class__ = RPNHead
+    ours.precision = precision
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    g = torch.Generator().manual_seed(6)
+    feats = [torch.randn(2, 256, h, w, generator=g).cuda() for h, w in ((48, 84), (23, 41), (12, 21), (6, 11), (3, 6))]
+    with torch.no_grad():
+        want_l, want_b = ref(feats)
+        got_l, got_b = ours(feats)
+    for a, b in zip(got_l + got_b, want_l + want_b):
+        assert a.shape == b.shape and a.dtype == torch.float32 and a.is_contiguous()
+        e = _nerr(a, b)
+        report("rpn_head", precision=precision, shape=str(tuple(b.shape)), max_norm=e)
+        assert e <= TOL[precision], e
+
+
+def test_install_backbone_keeps_parameters_and_proposals():
+    """install_backbone on a torchvision Mask R-CNN: same state_dict, and in the validation mode the same backbone features and
+    the same RPN proposals as the untouched model (anchors stay f32 whatever the feature dtype)."""
+    from sfvos_b200 import install_backbone
+    torch.manual_seed(7)
+    ref = torchvision.models.detection.maskrcnn_resnet50_fpn(weights=None, weights_backbone=None, num_classes=2).cuda().eval()
+    ours = install_backbone(copy.deepcopy(ref), precision="fp32")
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    for (k1, v1), (k2, v2) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(v1, v2), k1
+    g = torch.Generator().manual_seed(8)
+    img = torch.rand(2, 3, 192, 256, generator=g).cuda()
+    with torch.no_grad():
+        f_ref, f_our = ref.backbone(img), ours.backbone(img)
+        for k in f_ref:
+            assert _nerr(f_our[k], f_ref[k]) <= 1e-4, k
+        images = ImageList(img, [(192, 256)] * 2)
+        p_ref, _ = ref.rpn(images, f_ref)
+        p_our, _ = ours.rpn(images, f_our)
+    for a, b in zip(p_our, p_ref):
+        assert a.shape == b.shape and a.dtype == torch.float32
+        assert (a - b).abs().max().item() <= 0.05                       # pixels
+    # bf16 product path: features within 1e-2, proposals are f32 boxes inside the image
+    fast = install_backbone(copy.deepcopy(ref), precision="bf16")
+    with torch.no_grad():
+        f_bf = fast.backbone(img)
+        for k in f_ref:
+            assert f_bf[k].dtype == torch.bfloat16 and _nerr(f_bf[k], f_ref[k]) <= 1e-2, k
+        p_bf, _ = fast.rpn(images, f_bf)
+    for a in p_bf:
+        assert a.dtype == torch.float32 and a.shape[1] == 4 and float(a.min()) >= 0 and float(a[:, 2].max()) <= 256
