@@ -30,28 +30,28 @@ from ._lib import BF16, F32, call
 from .ops import Act, _p, stream
 from .roi_heads import _act_dtype, _default_precision, _nchw_view, _to_cl_act
 
-_PACKED = {}      # (data_ptr, mode, umma) -> (version, device, packed operand, Cp): the backbone / RPN weights are frozen
-
-
-def _packed(w, umma):
-    """[Cout,Cin,kh,kw] parameter -> fprop GEMM operand, cached until the parameter is written to."""
+def _packed(owner, name, w, umma):
+    """[Cout,Cin,kh,kw] parameter -> fprop GEMM operand, cached ON THE OWNING MODULE until the parameter is written to or
+    replaced (backbone and RPN are frozen, code/helpers/model.py:176-179).  The cache lives and dies with the module: a
+    process-wide cache keyed by address would hand a new model the operands of a freed one."""
     cin = w.shape[1]
     cp = (cin + 63) // 64 * 64 if umma else cin
-    key = (w.data_ptr(), umma)
-    tag = (w._version, str(w.device), tuple(w.shape))
-    hit = _PACKED.get(key)
-    if hit is None or hit[0] != tag or torch.cuda.is_current_stream_capturing():
+    capturing = torch.cuda.is_current_stream_capturing()
+    cache = owner.__dict__.setdefault("_sfvos_packed", {})
+    tag = (w.data_ptr(), w._version, str(w.device), tuple(w.shape), umma)
+    hit = cache.get(name)
+    if hit is None or hit[0] != tag or capturing:
         hit = (tag, ops.pack_weights(w, 0, BF16 if umma else F32, cp), cp)
-        if not torch.cuda.is_current_stream_capturing():
-            _PACKED[key] = hit
+        if not capturing:
+            cache[name] = hit
     return hit[1], hit[2]
 
 
-def _conv(x, w, b, umma, out_dtype, relu=False):
+def _conv(owner, name, x, w, b, umma, out_dtype, relu=False):
     """x: channels-last Act [N,1,H,W,Cin]; w [Cout,Cin,k,k] (k = 1 or 3, stride 1, 'same' padding), b [Cout] -> Act."""
     cout, _, kh, kw = w.shape
     assert kh == kw and kh in (1, 3), "1x1 and 3x3 convolutions only"
-    wp, cp = _packed(w, umma)
+    wp, cp = _packed(owner, name, w, umma)
     y = Act.empty(x.B, 1, x.H, x.W, cout, out_dtype, x.buf.device)
     if x.npix:
         ops.conv(x, wp, cp, cout, (1, kh, kw), (0, kh // 2, kw // 2), 1, y, umma=umma, relu=relu,
@@ -80,8 +80,8 @@ class FeaturePyramidNetwork(tv_fpn.FeaturePyramidNetwork):
         for blk in list(self.inner_blocks) + list(self.layer_blocks):
             assert len(blk) == 1, "norm / activation layers inside the FPN blocks are not supported"
         # lateral 1x1 convolutions, f32 results (the top-down chain adds up to n of them)
-        inner = [_conv(_to_cl_act(f, dt_act), self.inner_blocks[i][0].weight, self.inner_blocks[i][0].bias, umma, torch.float32)
-                 for i, f in enumerate(feats)]
+        inner = [_conv(self, f"inner{i}", _to_cl_act(f, dt_act), self.inner_blocks[i][0].weight, self.inner_blocks[i][0].bias, umma,
+                       torch.float32) for i, f in enumerate(feats)]
         results = [None] * n
         for i in range(n - 1, -1, -1):
             a = inner[i]
@@ -90,7 +90,7 @@ class FeaturePyramidNetwork(tv_fpn.FeaturePyramidNetwork):
             if a.npix and (top is not None or umma):
                 call("sfvos_upsample_add", top.ptr() if top is not None else None, top.H if top is not None else 0,
                      top.W if top is not None else 0, a.ptr(), merged.ptr() if umma else None, a.B, a.H, a.W, a.C, stream())
-            out = _conv(merged, self.layer_blocks[i][0].weight, self.layer_blocks[i][0].bias, umma, dt_act)
+            out = _conv(self, f"layer{i}", merged, self.layer_blocks[i][0].weight, self.layer_blocks[i][0].bias, umma, dt_act)
             results[i] = _nchw_view(out.buf, out.B, out.H, out.W, out.C)
         if self.extra_blocks is not None:
             if isinstance(self.extra_blocks, tv_fpn.LastLevelMaxPool):
@@ -119,24 +119,25 @@ class RPNHead(tv_rpn.RPNHead):
         n_pad = (a_cls + a_box + 31) // 32 * 32
         dev = self.cls_logits.weight.device
         # cls_logits and bbox_pred as one GEMM over the stacked (zero-padded) weight
-        key = ("rpn_pred", self.cls_logits.weight.data_ptr(), self.cls_logits.weight._version, self.bbox_pred.weight._version,
-               self.cls_logits.bias._version, self.bbox_pred.bias._version, str(dev))
-        hit = _PACKED.get("rpn_pred")
-        if hit is None or hit[0] != key or torch.cuda.is_current_stream_capturing():
+        capturing = torch.cuda.is_current_stream_capturing()
+        prm = (self.cls_logits.weight, self.bbox_pred.weight, self.cls_logits.bias, self.bbox_pred.bias)
+        key = tuple((t.data_ptr(), t._version) for t in prm) + (str(dev),)
+        hit = self.__dict__.get("_sfvos_pred")
+        if hit is None or hit[0] != key or capturing:
             w = torch.zeros(n_pad, self.cls_logits.in_channels, 1, 1, dtype=torch.float32, device=dev)
             b = torch.zeros(n_pad, dtype=torch.float32, device=dev)
             w[:a_cls] = self.cls_logits.weight.detach(); w[a_cls:a_cls + a_box] = self.bbox_pred.weight.detach()
             b[:a_cls] = self.cls_logits.bias.detach(); b[a_cls:a_cls + a_box] = self.bbox_pred.bias.detach()
             hit = (key, w, b)
-            if not torch.cuda.is_current_stream_capturing():
-                _PACKED["rpn_pred"] = hit
+            if not capturing:
+                self.__dict__["_sfvos_pred"] = hit
         _, w_pred, b_pred = hit
         logits, bbox_reg = [], []
         for feature in x:
             t = _to_cl_act(feature, dt_act)
-            for blk in self.conv:
-                t = _conv(t, blk[0].weight, blk[0].bias, umma, dt_act, relu=True)
-            pred = _conv(t, w_pred, b_pred, umma, torch.float32)
+            for j, blk in enumerate(self.conv):
+                t = _conv(self, f"conv{j}", t, blk[0].weight, blk[0].bias, umma, dt_act, relu=True)
+            pred = _conv(self, "pred", t, w_pred, b_pred, umma, torch.float32)
             out = torch.empty(t.B, n_pad, t.H, t.W, dtype=torch.float32, device=dev)
             if t.npix:
                 ops.nhwc_to_nchw(pred, out)

@@ -100,11 +100,19 @@ def test_install_backbone_keeps_parameters_and_proposals():
         for k in f_ref:
             assert _nerr(f_our[k], f_ref[k]) <= 1e-4, k
         images = ImageList(img, [(192, 256)] * 2)
-        p_ref, _ = ref.rpn(images, f_ref)
+        # anchors are identical (f32 whatever the feature dtype), objectness / deltas within the validation tolerance: together
+        # they determine the proposals up to the order of near-ties (random-init scores are all ~equal, so the top-k / NMS
+        # selection itself is not comparable between two implementations)
+        a_ref = ref.rpn.anchor_generator(images, list(f_ref.values()))
+        a_our = ours.rpn.anchor_generator(images, list(f_our.values()))
+        for a, b in zip(a_our, a_ref):
+            assert a.dtype == torch.float32 and torch.equal(a, b)
+        (l_ref, d_ref), (l_our, d_our) = ref.rpn.head(list(f_ref.values())), ours.rpn.head(list(f_our.values()))
+        for a, b in zip(l_our + d_our, l_ref + d_ref):
+            assert a.shape == b.shape and _nerr(a, b) <= 1e-4
         p_our, _ = ours.rpn(images, f_our)
-    for a, b in zip(p_our, p_ref):
-        assert a.shape == b.shape and a.dtype == torch.float32
-        assert (a - b).abs().max().item() <= 0.05                       # pixels
+    for a in p_our:
+        assert a.dtype == torch.float32 and a.shape[1] == 4 and float(a.min()) >= 0 and float(a[:, 2].max()) <= 256
     # bf16 product path: features within 1e-2, proposals are f32 boxes inside the image
     fast = install_backbone(copy.deepcopy(ref), precision="bf16")
     with torch.no_grad():
