@@ -59,12 +59,12 @@ _SIGS = {
     "sfvos_pack_weights": [vp, vp, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, vp],
     "sfvos_unpack_wgrad": [vp, vp, i32, i64, i64, i64, i64, i64, i64, i64, vp],
     "sfvos_channel_stats": [vp, i64, i64, i64, vp, vp, i64, vp],
-    "sfvos_bn_finalize": [vp, vp, i32, f64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp, vp, vp, i64, vp],
+    "sfvos_bn_finalize": [vp, vp, i32, f64, vp, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp, vp, i64, vp],
     "sfvos_bn_running_update": [ctypes.POINTER(BnRunningParams), vp],
     "sfvos_bn_fold_eval": [vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, i64, vp],
     "sfvos_affine_act": [vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, i64, vp],
-    "sfvos_bn_bwd_reduce": [vp, i32, i64, vp, i32, i64, vp, vp, vp, vp, i32, i64, i64, vp, vp, i64, vp],
-    "sfvos_bn_bwd_apply": [vp, i32, i64, vp, i32, i64, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, i32, i64, vp, vp, i32, vp, vp],
+    "sfvos_bn_bwd_reduce": [vp, i32, i64, vp, i64, vp, vp, vp, vp, i32, i64, i64, vp, vp, i64, vp],
+    "sfvos_bn_bwd_apply": [vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, i32, i64, vp, vp, i32, vp, vp],
     "sfvos_relu_bwd": [vp, i32, i64, vp, i32, i64, vp, i32, i64, vp, i64, i64, vp],
     "sfvos_nchw_to_nhwc": [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp],
     "sfvos_nhwc_to_nchw": [vp, i32, i64, vp, i64, i64, i64, vp],

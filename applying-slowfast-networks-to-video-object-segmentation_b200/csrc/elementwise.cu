@@ -204,13 +204,9 @@ channel_stats_kernel(const float* __restrict__ x, long long npix, int C, long lo
 
 // AccT = float: per-CTA sums merged into ``sums`` with atomics (product path).  AccT = double: fp64 sums written to
 // ``partial`` for the fixed-order merge (validation mode).
-// XT: type of ``x`` -- the saved raw conv output (f32) or, in the from-output mode of the product path, the layer's
-// post-activation output y (bf16 / f32) with the per-channel constants re-expressed for it (sfvos_bn_finalize's ymode block):
-// scale' = 1, shift' = 0 (mask: y <= 0), mean' = beta, rstd' = 1 / gamma, so that xhat = (y - beta) / gamma falls out of the
-// same (x - mean) * rstd expression.
-template <typename DyT, typename AccT, typename XT>
+template <typename DyT, typename AccT>
 __global__ void __launch_bounds__(RED_THREADS)
-bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const XT* __restrict__ x, long long x_cstride,
+bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ rstd, int relu, long long npix, int C, float* sums, double* partial, int ppc) {
     extern __shared__ double red_smem_d[];
@@ -257,9 +253,9 @@ bn_bwd_reduce_kernel(const DyT* __restrict__ dy, long long dy_cstride, const XT*
 
 // dx = k1*dm - k2 - k3*(x - mean) with k1 = gamma*rstd, k2 = k1*sum(dm)/n, k3 = k1*rstd*sum(dm*xhat)/n.
 // Thread -> (pixel lane, fixed 8-channel group): the per-channel constants live in registers for the whole pixel loop.
-template <typename DyT, typename DxT, typename XT>
+template <typename DyT, typename DxT>
 __global__ void __launch_bounds__(RED_THREADS)
-bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const XT* __restrict__ x, long long x_cstride,
+bn_bwd_apply_kernel(const DyT* __restrict__ dy, long long dy_cstride, const float* __restrict__ x, long long x_cstride,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, int relu, long long npix, int C,
                     const float* __restrict__ sums, DxT* dx, long long dx_cstride, float* dgamma, float* dbeta,
@@ -371,7 +367,7 @@ __device__ __forceinline__ double stat_at(const void* p, int f64, int c) {
 __global__ void bn_finalize_kernel(const void* sum, const void* sumsq, int stats_f64, double count, const float* conv_bias,
                                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                                    long long* nbt, double momentum, double eps, float* scale, float* shift, float* mean,
-                                   float* rstd, float* ymode, int C) {
+                                   float* rstd, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt != nullptr) *nbt += 1;
     if (c >= C) return;
@@ -384,16 +380,6 @@ __global__ void bn_finalize_kernel(const void* sum, const void* sumsq, int stats
     shift[c] = (float)((double)beta[c] - m * g * rs);
     mean[c] = (float)m;
     rstd[c] = (float)rs;
-    if (ymode != nullptr) {
-        // constants of the backward pass expressed in the layer's OUTPUT y = gamma * xhat + beta (see bn_bwd_reduce_kernel):
-        // [scale' = 1 | shift' = 0 | mean' = beta | rstd' = 1/gamma | gamma' = gamma^2 * rstd  (gamma' * rstd' = gamma * rstd)]
-        const double ig = g != 0.0 ? 1.0 / g : 0.0;
-        ymode[c] = 1.0f;
-        ymode[C + c] = 0.0f;
-        ymode[2 * C + c] = beta[c];
-        ymode[3 * C + c] = (float)ig;
-        ymode[4 * C + c] = (float)(g * g * rs);
-    }
     if (running_mean != nullptr) {
         const double mb = m + (conv_bias ? (double)conv_bias[c] : 0.0);
         const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -685,11 +671,11 @@ extern "C" int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int6
 extern "C" int sfvos_bn_finalize(const void* sum, const void* sumsq, int32_t stats_dtype, double count, const float* conv_bias,
                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
                                  int64_t* num_batches_tracked, double momentum, double eps, float* scale, float* shift,
-                                 float* mean, float* rstd, float* ymode, int64_t C, sfvos_stream stream) {
+                                 float* mean, float* rstd, int64_t C, sfvos_stream stream) {
     SF_CHECK(count > 0, "bn_finalize: empty batch");
     SF_CHECK(stats_dtype == SFVOS_F32 || stats_dtype == SFVOS_F64, "bn_finalize: statistics are f32 or f64");
     bn_finalize_kernel<<<(int)((C + 127) / 128), 128, 0, CS(stream)>>>(sum, sumsq, stats_dtype == SFVOS_F64, count, conv_bias, gamma, beta,
-        running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, mean, rstd, ymode, (int)C);
+        running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, mean, rstd, (int)C);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
@@ -731,43 +717,39 @@ extern "C" int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstrid
     return SFVOS_OK;
 }
 
-extern "C" int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const void* x, int32_t x_dtype,
-                                   int64_t x_cstride, const float* scale, const float* shift, const float* mean, const float* rstd,
+extern "C" int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
+                                   const float* scale, const float* shift, const float* mean, const float* rstd,
                                    int32_t relu, int64_t npix, int64_t C, float* sums, void* workspace,
                                    int64_t workspace_bytes, sfvos_stream stream) {
     CHECK_C8(C);
     SF_CHECK(dy_cstride % 8 == 0 && x_cstride % 8 == 0, "bn_bwd_reduce: strides must be multiples of 8");
-    SF_CHECK(x_dtype == SFVOS_F32 || x_dtype == SFVOS_BF16, "bn_bwd_reduce: x is f32 or bf16");
     if (npix == 0) return SFVOS_OK;
     int ppc;
     const int grid = red_grid(npix, (int)C, &ppc);
-    using bf = __nv_bfloat16;
     if (workspace != nullptr) {
         // validation mode: fp64 partial rows + fixed-order merge; ``sums`` is overwritten (not accumulated into)
-        SF_CHECK(dy_dtype == SFVOS_F32 && x_dtype == SFVOS_F32 && C <= 512, "bn_bwd_reduce: the deterministic mode takes f32 tensors, <= 512 channels");
+        SF_CHECK(dy_dtype == SFVOS_F32 && C <= 512, "bn_bwd_reduce: the deterministic mode takes f32 gradients, <= 512 channels");
         SF_CHECK(workspace_bytes >= sfvos_reduce_workspace_bytes(npix, C) && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
                  "bn_bwd_reduce: workspace needs sfvos_reduce_workspace_bytes(npix, C) = %lld bytes, 8-byte aligned",
                  (long long)sfvos_reduce_workspace_bytes(npix, C));
         double* partial = reinterpret_cast<double*>(workspace);
-        bn_bwd_reduce_kernel<float, double, float><<<grid, RED_THREADS, red_smem_bytes(2, (int)C, sizeof(double)), CS(stream)>>>(
-            reinterpret_cast<const float*>(dy), dy_cstride, reinterpret_cast<const float*>(x), x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, partial, ppc);
+        bn_bwd_reduce_kernel<float, double><<<grid, RED_THREADS, red_smem_bytes(2, (int)C, sizeof(double)), CS(stream)>>>(
+            reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, partial, ppc);
         SF_LAUNCH_CHECK();
         reduce_partials_kernel<float><<<(int)((2 * C + 127) / 128), 128, 0, CS(stream)>>>(partial, grid, (int)(2 * C), sums);
         SF_LAUNCH_CHECK();
         return SFVOS_OK;
     }
     const size_t sm = red_smem_bytes(2, (int)C);
-#define LAUNCH(DT, XT) bn_bwd_reduce_kernel<DT, float, XT><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, reinterpret_cast<const XT*>(x), x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, nullptr, ppc)
-    if (dy_dtype == SFVOS_F32 && x_dtype == SFVOS_F32) LAUNCH(float, float);
-    else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf);
-    else if (x_dtype == SFVOS_F32) LAUNCH(bf, float);
-    else LAUNCH(bf, bf);
-#undef LAUNCH
+    if (dy_dtype == SFVOS_F32)
+        bn_bwd_reduce_kernel<float, float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const float*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, nullptr, ppc);
+    else
+        bn_bwd_reduce_kernel<__nv_bfloat16, float><<<grid, RED_THREADS, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, relu, npix, (int)C, sums, nullptr, ppc);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }
 
-extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const void* x, int32_t x_dtype, int64_t x_cstride,
+extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
                                   const float* scale, const float* shift, const float* mean, const float* rstd,
                                   const float* gamma, int32_t relu, int64_t npix, int64_t C, const float* sums, void* dx,
                                   int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, int32_t fixed_stats,
@@ -779,19 +761,11 @@ extern "C" int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_c
     const int ppc = pick_ppc(npix, 512);
     const int grid = (int)((npix + ppc - 1) / ppc);
     using bf = __nv_bfloat16;
-#define LAUNCH(DT, OT, XT) bn_bwd_apply_kernel<DT, OT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, reinterpret_cast<const XT*>(x), x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<OT*>(dx), dx_cstride, dgamma, dbeta, fixed_stats, dbias, ppc)
-    SF_CHECK(x_dtype == SFVOS_F32 || x_dtype == SFVOS_BF16, "bn_bwd_apply: x is f32 or bf16");
-    if (x_dtype == SFVOS_F32) {
-        if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float, float);
-        else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf, float);
-        else if (dx_dtype == SFVOS_F32) LAUNCH(bf, float, float);
-        else LAUNCH(bf, bf, float);
-    } else {
-        if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float, bf);
-        else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf, bf);
-        else if (dx_dtype == SFVOS_F32) LAUNCH(bf, float, bf);
-        else LAUNCH(bf, bf, bf);
-    }
+#define LAUNCH(DT, XT) bn_bwd_apply_kernel<DT, XT><<<grid, RED_THREADS, 0, CS(stream)>>>(reinterpret_cast<const DT*>(dy), dy_cstride, x, x_cstride, scale, shift, mean, rstd, gamma, relu, npix, (int)C, sums, reinterpret_cast<XT*>(dx), dx_cstride, dgamma, dbeta, fixed_stats, dbias, ppc)
+    if (dy_dtype == SFVOS_F32 && dx_dtype == SFVOS_F32) LAUNCH(float, float);
+    else if (dy_dtype == SFVOS_F32) LAUNCH(float, bf);
+    else if (dx_dtype == SFVOS_F32) LAUNCH(bf, float);
+    else LAUNCH(bf, bf);
 #undef LAUNCH
     SF_LAUNCH_CHECK();
     return SFVOS_OK;

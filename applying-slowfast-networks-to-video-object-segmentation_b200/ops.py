@@ -246,14 +246,13 @@ def _stats_dtype(stats):
     return (F64, 8) if stats.dtype == torch.float64 else (F32, 4)
 
 
-def bn_finalize(stats, count, conv_bias, gamma, beta, running_mean, running_var, nbt, momentum, eps, out4, ymode=None):
-    """stats: [2C] (sum, sumsq), f32 (umma epilogues) or f64 (channel_stats); out4: f32 [4,C] = (scale, shift, mean, rstd);
-    ymode: optional f32 [5,C], the backward constants in terms of the layer's output (see sfvos_bn_finalize)."""
+def bn_finalize(stats, count, conv_bias, gamma, beta, running_mean, running_var, nbt, momentum, eps, out4):
+    """stats: [2C] (sum, sumsq), f32 (umma epilogues) or f64 (channel_stats); out4: f32 [4,C] = (scale, shift, mean, rstd)."""
     C = gamma.numel()
     code, esz = _stats_dtype(stats)
     call("sfvos_bn_finalize", _p(stats), _p(stats, C * esz), code, float(count), _p(conv_bias), _p(gamma), _p(beta),
          _p(running_mean), _p(running_var), _p(nbt), float(momentum), float(eps),
-         _p(out4), _p(out4, C * 4), _p(out4, 2 * C * 4), _p(out4, 3 * C * 4), _p(ymode), C, stream())
+         _p(out4), _p(out4, C * 4), _p(out4, 2 * C * 4), _p(out4, 3 * C * 4), C, stream())
 
 
 def bn_running_update(calls, conv_bias, running_mean, running_var, nbt, momentum):
@@ -288,21 +287,18 @@ def affine_act(x, y, scale, shift, relu):
 
 
 def bn_bwd(dy, raw, bn4, gamma, relu, dx, dgamma, dbeta, sums=None, deterministic=False, fixed_stats=False, dbias=None):
-    """dy, raw, dx: Acts over the same pixels; bn4 = (scale, shift, mean, rstd) [4,C]; ``sums``: optional zero-filled f32 [2C]
-    scratch.  ``raw`` is the saved raw conv output (f32) -- or the layer's OUTPUT y (bf16 | f32) when ``bn4`` is the
-    [5,C] ymode block of bn_finalize, whose 5th row then replaces ``gamma`` (the product path: the f32 raw output is neither
-    kept nor re-read).  ``deterministic`` (validation mode, f32 dy): the two per-channel sums are formed in
+    """dy, raw (f32), dx: Acts over the same pixels; bn4 = (scale, shift, mean, rstd) [4,C]; ``sums``: optional
+    zero-filled f32 [2C] scratch.  ``deterministic`` (validation mode, f32 dy): the two per-channel sums are formed in
     fp64 in a fixed order instead of with float atomics.  ``fixed_stats``: eval-mode BatchNorm (bn4 from bn_fold_eval): the
     statistics are constants, dx = gamma*rstd*dy_m, and ``dbias`` receives the conv-bias gradient."""
     C = raw.C
     if sums is None:
         sums = torch.zeros(2 * C, dtype=torch.float32, device=raw.buf.device)
     sc, sh, mu, rs = _p(bn4), _p(bn4, C * 4), _p(bn4, 2 * C * 4), _p(bn4, 3 * C * 4)
-    g = _p(bn4, 4 * C * 4) if bn4.numel() >= 5 * C else _p(gamma)
     ws, nbytes = _reduce_workspace(raw.npix, C, raw.buf.device) if deterministic and raw.npix else (None, 0)
-    call("sfvos_bn_bwd_reduce", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), dt(raw.buf), raw.cstride, sc, sh, mu, rs, int(relu),
+    call("sfvos_bn_bwd_reduce", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), raw.cstride, sc, sh, mu, rs, int(relu),
          raw.npix, C, _p(sums), _p(ws), nbytes, stream())
-    call("sfvos_bn_bwd_apply", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), dt(raw.buf), raw.cstride, sc, sh, mu, rs, g,
+    call("sfvos_bn_bwd_apply", dy.ptr(), dt(dy.buf), dy.cstride, raw.ptr(), raw.cstride, sc, sh, mu, rs, _p(gamma),
          int(relu), raw.npix, C, _p(sums), dx.ptr(), dt(dx.buf), dx.cstride, _p(dgamma), _p(dbeta), int(fixed_stats),
          _p(dbias), stream())
 

@@ -420,10 +420,6 @@ def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
             ops.conv(x, wp, cp, spec.cout, spec.k, pad, to, raw, umma=False)
             ops.channel_stats(raw, stats)
         bn4 = scratch.take(4 * spec.cout) if scratch is not None else torch.empty(4 * spec.cout, dtype=torch.float32, device=dev)
-        # product path, ReLU layers: the backward pass works from the layer's bf16 OUTPUT instead of the f32 raw conv output
-        # (half the bytes in both BatchNorm-backward passes, and the raw buffer dies right after the normalisation below)
-        from_y = umma and spec.relu and saved is not None and os.environ.get("SFVOS_BN_FROM_Y", "1") != "0"
-        ymode = torch.empty(5 * spec.cout, dtype=torch.float32, device=dev) if from_y else None
         track = bn.track_running_stats and bn.running_mean is not None
         deferred = getattr(scratch, "deferred", None) if scratch is not None else None
         if track and deferred is not None:
@@ -431,10 +427,10 @@ def _conv_bn_forward(mod, spec, x, out, training, saved, scratch=None):
             track = False
         ops.bn_finalize(stats, raw.npix, conv.bias, bn.weight, bn.bias, bn.running_mean if track else None,
                         bn.running_var if track else None, bn.num_batches_tracked if track else None,
-                        BN_MOMENTUM if bn.momentum is None else bn.momentum, bn.eps, bn4, ymode)
+                        BN_MOMENTUM if bn.momentum is None else bn.momentum, bn.eps, bn4)
         ops.affine_act(raw, out, bn4[:spec.cout], bn4[spec.cout:2 * spec.cout], spec.relu)
         if saved is not None:
-            saved[spec.conv] = (out, ymode, False) if from_y else (raw, bn4, False)
+            saved[spec.conv] = (raw, bn4, False)
     elif saved is not None:
         # eval mode WITH autograd (fine-tuning against frozen BatchNorm statistics; the reference module backpropagates
         # through eval-mode BN like any nn.Module): keep the raw conv output like the train path does; BatchNorm is the fixed

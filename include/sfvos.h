@@ -162,12 +162,7 @@ int sfvos_channel_stats(const float* x, int64_t npix, int64_t C, int64_t cstride
 int sfvos_bn_finalize(const void* sum, const void* sumsq, int32_t stats_dtype, double count, const float* conv_bias,
                       const float* gamma, const float* beta, float* running_mean, float* running_var,
                       int64_t* num_batches_tracked, double momentum, double eps, float* scale, float* shift,
-                      float* mean, float* rstd, float* ymode, int64_t C, sfvos_stream stream);
-/* ymode (may be NULL): f32 [5*C] = the backward pass's per-channel constants re-expressed for the layer's OUTPUT
- * y = gamma*xhat + beta instead of the raw conv output x: (scale' = 1, shift' = 0, mean' = beta, rstd' = 1/gamma,
- * gamma' = gamma^2*rstd).  Passing y (bf16 on the product path) with these to sfvos_bn_bwd_reduce / _apply gives the same
- * sums and dx -- xhat = (y - beta)/gamma, mask = (y <= 0), gamma'*rstd' = gamma*rstd -- so the f32 raw conv output need not be
- * kept for (or re-read by) the backward pass: 2 instead of 4 bytes per element in both passes. */
+                      float* mean, float* rstd, int64_t C, sfvos_stream stream);
 /* Running-statistics update of ONE BatchNorm for n_calls consecutive train-mode forward calls (the pyramid levels of one
  * temporally_enhance_features call, code/helpers/model.py:155-162), applied in call order: the same sequence of EMA steps
  * as n_calls sfvos_bn_finalize calls with running buffers.  Lets the calls themselves run concurrently (finalize with NULL
@@ -196,19 +191,18 @@ int sfvos_affine_act(const void* x, int32_t x_dtype, int64_t x_cstride, void* y,
                      int64_t y_cstride, const float* scale, const float* shift, int32_t relu, int64_t npix,
                      int64_t C, sfvos_stream stream);
 /* BN(+ReLU) backward, pass 1: sums[0][c] += sum dy_m, sums[1][c] += sum dy_m*xhat, with
- * dy_m = dy * (relu ? (x*scale+shift > 0) : 1), xhat = (x-mean)*rstd.  x is the saved raw conv output (f32), or the layer's
- * output y (f32|bf16) together with the ymode constants of sfvos_bn_finalize.
+ * dy_m = dy * (relu ? (x*scale+shift > 0) : 1), xhat = (x-mean)*rstd.  x is the saved raw conv output (f32).
  * workspace NULL: per-CTA sums merged with f32 atomics (product path).  workspace given (validation mode, f32 dy,
  * sfvos_reduce_workspace_bytes bytes): fp64 sums merged in CTA order, ``sums`` written instead of accumulated. */
-int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const void* x, int32_t x_dtype,
-                        int64_t x_cstride, const float* scale, const float* shift, const float* mean, const float* rstd,
+int sfvos_bn_bwd_reduce(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
+                        const float* scale, const float* shift, const float* mean, const float* rstd,
                         int32_t relu, int64_t npix, int64_t C, float* sums, void* workspace, int64_t workspace_bytes,
                         sfvos_stream stream);
 /* pass 2: dx = gamma*rstd*(dy_m - sums0/n - xhat*sums1/n) written as bf16|f32; block 0 also does
  * dgamma += sums1, dbeta += sums0 (may be NULL).  fixed_stats != 0 = eval-mode BatchNorm (mean / rstd are the running
  * statistics, constants): dx = gamma*rstd*dy_m, and dbias (may be NULL) += gamma*rstd*sums0, the gradient of the conv bias
  * (which train-mode BN cancels exactly). */
-int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const void* x, int32_t x_dtype, int64_t x_cstride,
+int sfvos_bn_bwd_apply(const void* dy, int32_t dy_dtype, int64_t dy_cstride, const float* x, int64_t x_cstride,
                        const float* scale, const float* shift, const float* mean, const float* rstd,
                        const float* gamma, int32_t relu, int64_t npix, int64_t C, const float* sums, void* dx,
                        int32_t dx_dtype, int64_t dx_cstride, float* dgamma, float* dbeta, int32_t fixed_stats,
