@@ -82,6 +82,9 @@ _SIGS = {
     "sfvos_fastrcnn_loss_bwd": [vp, i64, vp, i64, vp, vp, vp, i64, i32, f32, vp, i64, vp, i64, vp],
     "sfvos_paste_masks": [vp, vp, i64, i32, i32, i64, i64, vp, vp],
     "sfvos_upsample_add": [vp, i64, i64, vp, vp, i64, i64, i64, i64, vp],
+    "sfvos_im2col": [vp, vp, i32, i64, i64, i64, i64, i64, i64, i64, i64, i64, vp],
+    "sfvos_maxpool3x3s2": [vp, vp, i32, i64, i64, i64, i64, vp],
+    "sfvos_add_relu": [vp, vp, vp, vp, i64, vp],
     "sfvos_axpby": [vp, vp, f32, f32, i64, vp],
 }
 

@@ -23,6 +23,7 @@ import torch
 from torch import Tensor
 from torchvision.models.detection import anchor_utils as tv_anchor_utils
 from torchvision.models.detection import rpn as tv_rpn
+from torchvision.models import _utils as tv_utils
 from torchvision.ops import feature_pyramid_network as tv_fpn
 
 from . import ops
@@ -57,6 +58,150 @@ def _conv(owner, name, x, w, b, umma, out_dtype, relu=False):
         ops.conv(x, wp, cp, cout, (1, kh, kw), (0, kh // 2, kw // 2), 1, y, umma=umma, relu=relu,
                  shift=None if b is None else b.detach().float())
     return y
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ResNet-50 body: stem + 16 bottleneck blocks, frozen BatchNorm folded into the convolution epilogues
+# ----------------------------------------------------------------------------------------------------------------------
+def _fold_bn(owner, name, bn):
+    """Frozen / eval-mode BatchNorm2d -> (scale, shift) f32 [C]: y = x * scale + shift.  Cached on ``owner``."""
+    cache = owner.__dict__.setdefault("_sfvos_folded", {})
+    ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    tag = tuple((t.data_ptr(), t._version) for t in ts)
+    hit = cache.get(name)
+    if hit is None or hit[0] != tag:
+        eps = float(getattr(bn, "eps", 1e-5))
+        scale = (bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + eps))
+        shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+        hit = (tag, scale.float().contiguous(), shift.float().contiguous())
+        cache[name] = hit
+    return hit[1], hit[2]
+
+
+def _derived(owner, name, w, fn):
+    """A re-arranged copy of a frozen weight (stem patch order, stride-2 phase sub-kernels), cached on ``owner``."""
+    cache = owner.__dict__.setdefault("_sfvos_derived", {})
+    tag = (w.data_ptr(), w._version)
+    hit = cache.get(name)
+    if hit is None or hit[0] != tag:
+        hit = (tag, fn(w.detach().float()).contiguous())
+        cache[name] = hit
+    return hit[1]
+
+
+def _conv_bn(owner, name, x, w, scale, shift, umma, out_dtype, relu, stride=1):
+    """Conv2d (1x1 or 3x3, 'same' padding, stride 1 or 2, no bias) + folded BatchNorm (+ ReLU) on a channels-last Act."""
+    cout, cin, kh, kw = w.shape
+    dev = x.buf.device
+    if stride == 1:
+        wp, cp = _packed(owner, name, w, umma)
+        y = Act.empty(x.B, 1, x.H, x.W, cout, out_dtype, dev)
+        ops.conv(x, wp, cp, cout, (1, kh, kw), (0, kh // 2, kw // 2), 1, y, umma=umma, relu=relu, scale=scale, shift=shift)
+        return y
+    assert stride == 2 and x.H % 2 == 0 and x.W % 2 == 0 and x.cstride == x.C and x.bstride == 0
+    ho, wo = x.H // 2, x.W // 2
+    frame = x.H * x.W * x.C
+
+    def phase(pi, pj):      # x[:, pi::2, pj::2, :] as a strided Act: pixel stride 2C, row stride 2WC
+        v = Act(x.buf, x.B, 1, ho, wo, x.C, 2 * x.C, x.ch_off + (pi * x.W + pj) * x.C)
+        return v, (2 * x.W * x.C, frame, frame)
+    if kh == 1:             # 1x1 stride 2 (the downsample branch): every second pixel of every second row
+        v, strides = phase(0, 0)
+        wp, cp = _packed(owner, name, w, umma)
+        y = Act.empty(x.B, 1, ho, wo, cout, out_dtype, dev)
+        ops.conv(v, wp, cp, cout, (1, 1, 1), (0, 0, 0), 1, y, umma=umma, relu=relu, scale=scale, shift=shift, x_strides=strides)
+        return y
+    # 3x3 stride 2, padding 1: out[y,x] = sum_ij in[2y+i-1, 2x+j-1] w[i,j].  Rows 2y-1 / 2y+1 are rows y-1 / y of the odd
+    # row phase (taps i = 0, 2), row 2y is row y of the even phase (tap i = 1); the same for columns: four stride-1
+    # convolutions (1x1, 1x2, 2x1, 2x2 taps) over the four phase images, accumulated in f32, then scale / shift / ReLU
+    acc = Act.empty(x.B, 1, ho, wo, cout, torch.float32, dev)
+    first = True
+    for pi, rows in ((0, [1]), (1, [0, 2])):
+        for pj, cols in ((0, [1]), (1, [0, 2])):
+            sub = _derived(owner, f"{name}.p{pi}{pj}", w, lambda t, r=rows, c=cols: t[:, :, r][:, :, :, c])
+            wp, cp = _packed(owner, f"{name}.p{pi}{pj}", sub, umma)
+            v, strides = phase(pi, pj)
+            ops.conv(v, wp, cp, cout, (1, len(rows), len(cols)), (0, len(rows) - 1, len(cols) - 1), 1, acc, umma=umma,
+                     accumulate=not first, x_strides=strides)
+            first = False
+    y = Act.empty(x.B, 1, ho, wo, cout, out_dtype, dev)
+    ops.affine_act(acc, y, scale, shift, relu)
+    return y
+
+
+class ResNetBody(tv_utils.IntermediateLayerGetter):
+    """torchvision's ``backbone.body`` (IntermediateLayerGetter over ResNet-50: conv1 / bn1 / relu / maxpool / layer1..4) with
+    the forward on libsfvos: same modules, same parameters, same state_dict keys.  The 7x7 stride-2 stem is a patch GEMM
+    (sfvos_im2col + a 1x1 convolution), every other convolution runs on sfvos_conv_umma with the frozen BatchNorm folded into
+    its scale / shift epilogue, stride-2 3x3 convolutions as four phase convolutions; the residual stream stays f32.
+    Returns ``{name: [N,C,H,W]}`` channels-last in the activation dtype -- the FPN below consumes them in place.
+    Anything it cannot express (trainable or train-mode BatchNorm, autograd, basic blocks, odd sizes) goes to torchvision's
+    forward."""
+
+    precision = None
+
+    def _native_ok(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[-2] % 32 or x.shape[-1] % 32 or not x.is_cuda:
+            return False
+        mods = dict(self.items())
+        if not all(k in mods for k in ("conv1", "bn1", "maxpool", "layer1", "layer2", "layer3", "layer4")):
+            return False
+        for m in self.modules():
+            if isinstance(m, torch.nn.BatchNorm2d) and m.training:
+                return False
+        c1 = mods["conv1"]
+        if c1.kernel_size != (7, 7) or c1.stride != (2, 2) or c1.padding != (3, 3) or c1.bias is not None:
+            return False
+        return all(type(b).__name__ == "Bottleneck" and b.conv2.groups == 1 and b.conv2.dilation == (1, 1)
+                   for k in ("layer1", "layer2", "layer3", "layer4") for b in mods[k])
+
+    @ops.device_guard
+    def forward(self, x):
+        if not self._native_ok(x):
+            return super().forward(x)
+        ops.device_check()
+        precision = self.precision or _default_precision()
+        umma, dt_act = precision != "fp32", _act_dtype(precision)
+        mods = dict(self.items())
+        n, _, h, w = x.shape
+        dev = x.device
+        # ---- stem: 7x7 stride-2 conv on 3 channels as a [pixels, 192] x [192, 64] GEMM, then 3x3 stride-2 max-pool
+        conv1 = mods["conv1"]
+        kp = 192
+        ho, wo = h // 2, w // 2
+        rows = Act.empty(n, 1, ho, wo, kp, dt_act, dev)
+        call("sfvos_im2col", _p(x.float().contiguous()), rows.ptr(), ops.dt(rows.buf), n, 3, h, w, 7, 7, 2, 3, kp, stream())
+        w_stem = _derived(self, "stem", conv1.weight, lambda t: torch.nn.functional.pad(
+            t.permute(0, 2, 3, 1).reshape(t.shape[0], -1), (0, kp - 147)).reshape(t.shape[0], kp, 1, 1))
+        sc, sh = _fold_bn(self, "bn1", mods["bn1"])
+        stem = _conv_bn(self, "stem", rows, w_stem, sc, sh, umma, dt_act, relu=True)
+        cur = Act.empty(n, 1, ho // 2, wo // 2, 64, dt_act, dev)
+        call("sfvos_maxpool3x3s2", stem.ptr(), cur.ptr(), ops.dt(cur.buf), n, ho, wo, 64, stream())
+        cur32 = None                                           # f32 residual stream (None before the first block: it downsamples)
+        out = OrderedDict()
+        for lname in ("layer1", "layer2", "layer3", "layer4"):
+            for bi, blk in enumerate(mods[lname]):
+                tag = f"{lname}.{bi}"
+                s = blk.conv2.stride[0]
+                o = _conv_bn(self, tag + ".conv1", cur, blk.conv1.weight, *_fold_bn(self, tag + ".bn1", blk.bn1), umma, dt_act, True,
+                             stride=blk.conv1.stride[0])
+                o = _conv_bn(self, tag + ".conv2", o, blk.conv2.weight, *_fold_bn(self, tag + ".bn2", blk.bn2), umma, dt_act, True, stride=s)
+                o = _conv_bn(self, tag + ".conv3", o, blk.conv3.weight, *_fold_bn(self, tag + ".bn3", blk.bn3), umma, torch.float32, False)
+                if blk.downsample is not None:
+                    ds_conv, ds_bn = blk.downsample[0], blk.downsample[1]
+                    idt = _conv_bn(self, tag + ".down", cur, ds_conv.weight, *_fold_bn(self, tag + ".dbn", ds_bn), umma, torch.float32,
+                                   False, stride=ds_conv.stride[0])
+                else:
+                    idt = cur32
+                nxt32 = Act.empty(o.B, 1, o.H, o.W, o.C, torch.float32, dev)
+                nxt = nxt32 if not umma else Act.empty(o.B, 1, o.H, o.W, o.C, torch.bfloat16, dev)
+                call("sfvos_add_relu", o.ptr(), idt.ptr(), nxt32.ptr(), nxt.ptr() if umma else None, o.npix * o.C, stream())
+                cur, cur32 = nxt, nxt32
+            if lname in self.return_layers:
+                out[self.return_layers[lname]] = _nchw_view(cur.buf, cur.B, cur.H, cur.W, cur.C)
+        return out
 
 
 class FeaturePyramidNetwork(tv_fpn.FeaturePyramidNetwork):
@@ -159,6 +304,10 @@ def install_backbone(maskrcnn_model, precision: Optional[str] = None):
     """Swap the libsfvos FPN / RPN head into a torchvision Mask R-CNN IN PLACE (same parameters, same state_dict keys).
     Returns the model."""
     precision = precision or _default_precision()
+    body = getattr(maskrcnn_model.backbone, "body", None)
+    if body is not None and type(body) in (tv_utils.IntermediateLayerGetter, ResNetBody):
+        body.__class__ = ResNetBody
+        body.precision = precision
     fpn = getattr(maskrcnn_model.backbone, "fpn", None)
     if fpn is not None and type(fpn) in (tv_fpn.FeaturePyramidNetwork, FeaturePyramidNetwork) and \
             all(len(b) == 1 for b in list(fpn.inner_blocks) + list(fpn.layer_blocks)):

@@ -528,6 +528,85 @@ nhwc_to_nchw_kernel(const InT* __restrict__ src, long long src_cstride, float* d
     }
 }
 
+// ---- ResNet body helpers ---------------------------------------------------------------------
+// Stem patches: f32 NCHW image [N,Cin,H,W] -> rows [N*Ho*Wo, Kp] (bf16 | f32) with row[(i*kw + j)*Cin + c] =
+// x[n, c, oy*stride + i - pad, ox*stride + j - pad] (0 outside the image, 0 in the Kp - kh*kw*Cin padding columns): the 7x7
+// stride-2 stem convolution of 3 input channels becomes a [pixels, 192] x [192, 64] GEMM on the tensor cores.
+// One thread per (output pixel, 8 consecutive K columns).
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ x, OutT* rows, int Cin, int H, int W, int Ho, int Wo, int kh, int kw, int stride, int pad,
+              int Kp, long long total) {
+    const int K8 = Kp / 8;
+    const int K = kh * kw * Cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kg = (int)(i % K8);
+        long long pix = i / K8;
+        const int ox = (int)(pix % Wo); pix /= Wo;
+        const int oy = (int)(pix % Ho);
+        const long long n = pix / Ho;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = kg * 8 + e;
+            float val = 0.f;
+            if (k < K) {
+                const int c = k % Cin, t = k / Cin;
+                const int tj = t % kw, ti = t / kw;
+                const int iy = oy * stride + ti - pad, ix = ox * stride + tj - pad;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(x + ((n * Cin + c) * H + iy) * (long long)W + ix);
+            }
+            v[e] = val;
+        }
+        store8(rows + (((n * Ho + oy) * Wo + ox) * (long long)Kp) + kg * 8, v);
+    }
+}
+
+// max_pool2d(kernel 3, stride 2, padding 1) on a channels-last tensor; 8 channels per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const T* __restrict__ x, T* y, int H, int W, int Ho, int Wo, int C, long long total8) {
+    const int C8 = C / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long long pix = i / C8;
+        const int ox = (int)(pix % Wo); pix /= Wo;
+        const int oy = (int)(pix % Ho);
+        const long long n = pix / Ho;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int di = 0; di < 3; ++di) {
+            const int iy = 2 * oy + di - 1;
+            if (iy < 0 || iy >= H) continue;
+            for (int dj = 0; dj < 3; ++dj) {
+                const int ix = 2 * ox + dj - 1;
+                if (ix < 0 || ix >= W) continue;
+                float v[8];
+                load8(x + (((n * H + iy) * W + ix) * (long long)C) + cg * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+            }
+        }
+        store8(y + (((n * Ho + oy) * Wo + ox) * (long long)C) + cg * 8, m);
+    }
+}
+
+// residual join of a bottleneck block: out = relu(a + b) on f32 (the residual stream stays f32), plus the bf16 copy the next
+// block's convolutions read
+__global__ void __launch_bounds__(256)
+add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* out, __nv_bfloat16* out_bf16, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float u[8], v[8];
+        load8(a + i * 8, u);
+        load8(b + i * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = fmaxf(u[j] + v[j], 0.f);
+        if (out != nullptr) store8(out + i * 8, u);
+        if (out_bf16 != nullptr) store8(out_bf16 + i * 8, u);
+    }
+}
+
 // FPN top-down merge (TV/ops/feature_pyramid_network.py: F.interpolate(last_inner, size, mode="nearest") + inner_lateral):
 // inner[n,h,w,:] += top[n, floor(h*Ht/H), floor(w*Wt/W), :] in place on the f32 lateral output, plus the bf16 copy the 3x3
 // output convolution reads.  top == nullptr (coarsest level): only the bf16 copy.  8 channels per thread.
@@ -817,6 +896,40 @@ extern "C" int sfvos_nhwc_to_nchw(const void* src, int32_t src_dtype, int64_t sr
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)F), block(32, 8);
     if (src_dtype == SFVOS_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_cstride, dst, (int)C, HW);
     else nhwc_to_nchw_kernel<float><<<grid, block, 0, CS(stream)>>>(reinterpret_cast<const float*>(src), src_cstride, dst, (int)C, HW);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_im2col(const float* x, void* rows, int32_t rows_dtype, int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t kh,
+                            int64_t kw, int64_t stride, int64_t pad, int64_t Kp, sfvos_stream stream) {
+    SF_CHECK(Kp % 8 == 0 && Kp >= kh * kw * Cin, "im2col: Kp=%lld must be a multiple of 8 and >= kh*kw*Cin", (long long)Kp);
+    SF_CHECK(stride >= 1 && kh >= 1 && kw >= 1, "im2col: bad geometry");
+    const long long Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    const long long total = N * Ho * Wo * (Kp / 8);
+    if (total <= 0) return SFVOS_OK;
+#define LAUNCH(T) im2col_kernel<T><<<grid_for(total, 256), 256, 0, CS(stream)>>>(x, reinterpret_cast<T*>(rows), (int)Cin, (int)H, (int)W, (int)Ho, (int)Wo, (int)kh, (int)kw, (int)stride, (int)pad, (int)Kp, total)
+    if (rows_dtype == SFVOS_BF16) LAUNCH(__nv_bfloat16); else LAUNCH(float);
+#undef LAUNCH
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_maxpool3x3s2(const void* x, void* y, int32_t dtype, int64_t N, int64_t H, int64_t W, int64_t C, sfvos_stream stream) {
+    SF_CHECK(C % 8 == 0, "maxpool3x3s2: C must be a multiple of 8");
+    const long long Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total8 = N * Ho * Wo * (C / 8);
+    if (total8 <= 0) return SFVOS_OK;
+#define LAUNCH(T) maxpool3x3s2_kernel<T><<<grid_for(total8, 256), 256, 0, CS(stream)>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), (int)H, (int)W, (int)Ho, (int)Wo, (int)C, total8)
+    if (dtype == SFVOS_BF16) LAUNCH(__nv_bfloat16); else LAUNCH(float);
+#undef LAUNCH
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}
+
+extern "C" int sfvos_add_relu(const float* a, const float* b, float* out, void* out_bf16, int64_t n, sfvos_stream stream) {
+    SF_CHECK(n % 8 == 0, "add_relu: n must be a multiple of 8");
+    if (n == 0) return SFVOS_OK;
+    add_relu_kernel<<<grid_for(n / 8, 256), 256, 0, CS(stream)>>>(a, b, out, reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 8);
     SF_LAUNCH_CHECK();
     return SFVOS_OK;
 }

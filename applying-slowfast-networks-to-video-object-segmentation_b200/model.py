@@ -21,6 +21,22 @@ from .roi_heads import MaskRCNNPredictor
 from .slowfast import SlowFastLayers
 
 
+def _freeze_batchnorm(module):
+    """nn.BatchNorm2d -> torchvision FrozenBatchNorm2d (same statistics / affine values, as buffers), recursively.  The
+    pretrained Mask R-CNN the reference starts from has a frozen-BN ResNet (torchvision builds the backbone that way whenever
+    it carries trained weights); ``weights=None`` builds trainable BatchNorm2d layers instead, which would change the
+    parameter count (+53,120) and, in train mode, the arithmetic."""
+    from torchvision.ops.misc import FrozenBatchNorm2d
+    for name, child in list(module.named_children()):
+        if isinstance(child, torch.nn.BatchNorm2d):
+            frozen = FrozenBatchNorm2d(child.num_features, eps=child.eps)
+            frozen.weight.copy_(child.weight.detach()); frozen.bias.copy_(child.bias.detach())
+            frozen.running_mean.copy_(child.running_mean); frozen.running_var.copy_(child.running_var)
+            setattr(module, name, frozen)
+        else:
+            _freeze_batchnorm(child)
+
+
 def get_model_instance_segmentation(num_classes, pretrained=True):
     """code/helpers/model.py:12-27.  ``pretrained`` weights need the torchvision hub cache; offline we fall back to
     random init with FrozenBatchNorm2d so the parameter count matches the reference's report."""
@@ -38,6 +54,8 @@ def get_model_instance_segmentation(num_classes, pretrained=True):
         except TypeError:
             kwargs.pop("norm_layer")
             model = torchvision.models.detection.maskrcnn_resnet50_fpn(**kwargs)
+    if not pretrained:
+        _freeze_batchnorm(model.backbone.body)      # what the pretrained model the reference loads has (model.py:13)
     in_features = model.roi_heads.box_predictor.cls_score.in_features
     model.roi_heads.box_predictor = FastRCNNPredictor(in_features, num_classes)
     in_features_mask = model.roi_heads.mask_predictor.conv5_mask.in_channels

@@ -325,6 +325,17 @@ int sfvos_paste_masks(const float* masks, const float* boxes, int64_t K, int32_t
  * ------------------------------------------------------------------------------------------------------- */
 int sfvos_upsample_add(const float* top, int64_t Ht, int64_t Wt, float* inner, void* out_bf16, int64_t N, int64_t H,
                        int64_t W, int64_t C, sfvos_stream stream);
+/* ResNet-50 body helpers (the frozen backbone's convolution stack, TV/models/resnet.py reached through
+ * torchvision...backbone_utils.BackboneWithFPN at code/helpers/model.py:204; the convolutions themselves run on
+ * sfvos_conv_umma with the frozen BatchNorm folded into scale / shift):
+ *   sfvos_im2col       f32 NCHW image [N,Cin,H,W] -> patch rows [N*Ho*Wo, Kp] (bf16|f32), column (i*kw + j)*Cin + c, zeros
+ *                      outside the image and in the padding columns: the 7x7 stride-2 stem on 3 channels as ONE GEMM
+ *   sfvos_maxpool3x3s2 F.max_pool2d(kernel 3, stride 2, padding 1) on a channels-last (bf16|f32) tensor
+ *   sfvos_add_relu     out = relu(a + b) over f32 (the residual stream), plus an optional bf16 copy for the next block's convs */
+int sfvos_im2col(const float* x, void* rows, int32_t rows_dtype, int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t kh,
+                 int64_t kw, int64_t stride, int64_t pad, int64_t Kp, sfvos_stream stream);
+int sfvos_maxpool3x3s2(const void* x, void* y, int32_t dtype, int64_t N, int64_t H, int64_t W, int64_t C, sfvos_stream stream);
+int sfvos_add_relu(const float* a, const float* b, float* out, void* out_bf16, int64_t n, sfvos_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Optimiser-side helpers for the data-parallel step (the one collective is NCCL all-reduce, called from Python).
