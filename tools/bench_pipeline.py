@@ -4,8 +4,9 @@
     python tools/bench_pipeline.py [--sp 1 --fp 8 --sequences 4 --frames 24]              # one GPU
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_pipeline.py ...
 
-Prints one JSON line per mode (sequence sweep on / off): frames/s over all ranks (max-over-ranks time).  The backbone and RPN
-are torchvision modules (not rebuilt); random-init weights, synthetic frames (no network for DAVIS)."""
+Prints one JSON line per mode (sequence sweep on / off): frames/s over all ranks (max-over-ranks time).  Backbone (ResNet-50
+body + FPN) and RPN head run on libsfvos (SFVOS_NATIVE_BACKBONE=0 = torchvision fp32); anchors, box decoding
+and NMS are torchvision.  Random-init weights, synthetic frames (no network for DAVIS)."""
 import argparse
 import json
 import os
@@ -39,6 +40,7 @@ def main():
     ap.add_argument("--sp", type=int, default=1); ap.add_argument("--fp", type=int, default=8)
     ap.add_argument("--sequences", type=int, default=4); ap.add_argument("--frames", type=int, default=24)
     ap.add_argument("--chunk", type=int, default=32)
+    ap.add_argument("--sweep-only", action="store_true", help="skip the reference-faithful per-frame loop (4-5x slower)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -67,7 +69,7 @@ def main():
             n += len(dets)
         return n
 
-    for mode in (True, False):
+    for mode in ((True,) if a.sweep_only else (True, False)):
         run(mode)                                              # warm-up (cuDNN autotune, allocator)
         torch.cuda.synchronize()
         if world > 1:
@@ -84,7 +86,8 @@ def main():
                               "n_gpus": world, "sequences": lengths, "frames_total": sum(lengths), "seconds": round(sec.item(), 3),
                               "frames_per_s": round(sum(lengths) / sec.item(), 2),
                               "phase_seconds_rank0": {k: round(v, 3) for k, v in model.phase_times.items()},
-                              "note": "wall clock incl. the torchvision fp32 backbone/RPN, per-frame D2H of the pasted masks (as the reference does)"}),
+                              "backbone": "libsfvos ResNet-50 body + FPN + RPN head (bf16 NHWC)" if os.environ.get("SFVOS_NATIVE_BACKBONE", "1") != "0" else "torchvision fp32",
+                              "note": "wall clock incl. backbone, RPN (torchvision anchors / NMS), SlowFast sweep, roi_heads, paste-back and the D2H of the pasted masks (as the reference does)"}),
                   flush=True)
     if world > 1:
         dist.destroy_process_group()
