@@ -23,9 +23,9 @@ namespace {
 constexpr int BM = 128;                     // rows per CTA (the MMA is 256 x N)
 constexpr int BK = 64;
 constexpr uint32_t ROW = BK * 2;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;             // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;             // TWO warps per TMEM lane quarter, each draining half of the accumulator's columns
 constexpr int TW = 8, TH = 16;
 
 struct PairArgs {
@@ -131,7 +131,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < a.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < a.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }      // 4 epilogue warps x 2 CTAs
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16); }     // 8 epilogue warps x 2 CTAs
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc_pair(tmem_slot, a.tmem_cols);
@@ -223,7 +223,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     } else if (warp >= EPI_WARP0) {
         // ------------------------------ epilogue (both CTAs, own tile) ------------------------------
-        const int q = warp - EPI_WARP0;
+        // Two warps share every TMEM lane quarter (a warp reads lanes 32 * (warp % 4) ..): the first drains the lower half of
+        // the accumulator's column blocks, the second the upper half.  With one warp per scheduler the epilogue ran its
+        // dependent shuffle / select chains (fused BN statistics: ~310 instructions per 32-column block) at ~0.15 IPC and a
+        // statistics-carrying fprop tile took about as long to drain as to compute (ncu, round 2: 67 % tensor-pipe-active with
+        // statistics against 79 % without); two warps per scheduler halve the drain and hide each other's latencies.
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3;
+        const int c_split = ((a.N / 32 + 1) / 2) * 32;
+        const int c_begin = (ew >> 2) ? c_split : 0, c_end = (ew >> 2) ? a.N : c_split;
         const int r = q * 32 + lane;
         const int hl = r / TW, wl = r - hl * TW;
         const bool do_stats = (a.sum != nullptr) && (a.relu_mask == nullptr);
@@ -241,7 +249,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * a.N;
-            for (int c0 = 0; c0 < a.N; c0 += 32) {
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + c0, v);
                 tmem_ld_wait();

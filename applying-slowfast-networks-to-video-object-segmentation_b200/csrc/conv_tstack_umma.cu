@@ -253,6 +253,14 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const bool affine = (a.scale != nullptr) || (a.shift != nullptr);
         int acc = 0;
         uint32_t acc_phase = 0;
+        // BatchNorm statistics: this thread's row sums of x and x^2 per output channel stay in REGISTERS across every frame
+        // of every work item of the CTA; the cross-lane reduction (31 shuffles + selects per quantity) runs ONCE at the end
+        // instead of once per (item, frame).  ncu (round 2): the per-frame reductions were 314 of the epilogue's 407
+        // instructions per frame and its dependent shuffle chains kept the single epilogue warp of each scheduler at 0.15 IPC,
+        // which -- not the tensor pipe (34 % active) -- set the pace of the 32-channel layers.
+        float st_sum[32], st_sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { st_sum[j] = 0.0f; st_sq[j] = 0.0f; }
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
             const Item it = decode_item(a, item);
             const int h = it.h0 + hl, w = it.w0 + wl;
@@ -265,16 +273,13 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + (it.t1 - 1 - t) * NC, v);
                 tmem_ld_wait();
-                if (do_stats) {
-                    float f[32];
+                if (do_stats && valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.0f;
-                    float s = warp_transpose_reduce32(f, lane);
-                    atomicAdd(&s_sum[lane], s);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { float x = valid ? __uint_as_float(v[j]) : 0.0f; f[j] = x * x; }
-                    s = warp_transpose_reduce32(f, lane);
-                    atomicAdd(&s_sq[lane], s);
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = __uint_as_float(v[j]);
+                        st_sum[j] += x;
+                        st_sq[j] = fmaf(x, x, st_sq[j]);
+                    }
                 }
                 float o[32];
                 if (affine) {           // per-channel scale / shift from shared memory, 16 bytes per load
@@ -360,6 +365,10 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             if (++acc == a.nbuf) { acc = 0; acc_phase ^= 1; }
         }
         if (do_stats) {
+            float s = warp_transpose_reduce32(st_sum, lane);
+            atomicAdd(&s_sum[lane], s);
+            s = warp_transpose_reduce32(st_sq, lane);
+            atomicAdd(&s_sq[lane], s);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             const int i = threadIdx.x - EPI_WARP0 * 32;
             if (i < NC) {
