@@ -38,6 +38,7 @@ struct TsArgs {
     int LP, a_stages, a_stage_bytes, piece_bytes;
     uint32_t a_tx_bytes, tmem_cols;
     int nbuf, b_resident, stage_mode;            // stage_mode: f32 epilogue through the shared-memory transpose
+    int dbg;                                     // SFVOS_TSTACK_DBG (measurement only): 1 = the epilogue releases accumulators unread
     void* y;
     int y_bf16, relu, accumulate;
     long long y_cstride;
@@ -268,7 +269,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * a.Fg * NC;
-            for (int t = it.t0; t < it.t1; ++t) {
+            for (int t = it.t0; t < (a.dbg & 1 ? it.t0 : it.t1); ++t) {
                 const long long pix = (((long long)it.b * a.To + t) * a.H + h) * a.W + w;
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + (it.t1 - 1 - t) * NC, v);
@@ -452,6 +453,8 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
         const int m = env_int("SFVOS_TSTACK_STAGE", 1);
         a.stage_mode = (m >= 2 || (m == 1 && p->accumulate)) ? 1 : 0;
     }
+
+    a.dbg = env_int("SFVOS_TSTACK_DBG", 0);
 
     CUtensorMap tx, tw;
     int rc;
