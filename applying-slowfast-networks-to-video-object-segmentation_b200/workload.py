@@ -212,11 +212,13 @@ class HotPathStep:
         live = [(o, g) for o, g in zip(outs, grads[len(roi):]) if g is not None]
         torch.autograd.backward([o for o, _ in live], [g for _, g in live])
 
-    def capture(self, features, warmup=2, pool=None):
+    def capture(self, features, warmup=2, pool=None, zero_arena=False):
         """Capture one forward+backward on ``features`` (static device buffers) into a CUDA graph: ~430 kernel launches
         become one graph launch, which removes the launch gaps between the (many short) kernels of the small pyramid
         levels.  Returns (graph, loss): ``graph.replay()`` recomputes ``loss`` and every ``p.grad`` in place from the
-        current contents of ``features`` and the current parameter values (weight packing is part of the graph)."""
+        current contents of ``features`` and the current parameter values (weight packing is part of the graph).
+        With a gradient arena (ops.GRAD_ARENA) the gradients are its slices; ``zero_arena`` puts its clear at the head."""
+        from . import ops
         params = self.parameters()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -232,6 +234,8 @@ class HotPathStep:
         except AttributeError:
             pass
         with torch.cuda.graph(graph, pool=pool):
+            if zero_arena and ops.GRAD_ARENA is not None:
+                ops.GRAD_ARENA.zero()
             loss, _ = self.forward(features)
             loss.backward()
         return graph, loss

@@ -276,7 +276,16 @@ def run_ours(args, rank, local_rank, world):
     if os.environ.get("SFVOS_GRAPH", "1") != "0":
         try:
             pool = torch.cuda.graph_pool_handle()
-            graphs = [[step.capture_split(clips, zero_arena=(j == 0), pool=pool) for j, clips in enumerate(chunks(sq))] for sq in slots]
+            if world > 1:       # two graphs per micro-batch: the roi_heads all-reduce is launched between them
+                graphs = [[step.capture_split(clips, zero_arena=(j == 0), pool=pool) for j, clips in enumerate(chunks(sq))] for sq in slots]
+            else:               # one GPU: nothing to overlap, one graph per micro-batch (no join between the two backward phases)
+                graphs = []
+                for sq in slots:
+                    per = []
+                    for j, clips in enumerate(chunks(sq)):
+                        g, loss_t = step.capture(clips, warmup=1, pool=pool, zero_arena=(j == 0))
+                        per.append((g, None, loss_t))
+                    graphs.append(per)
             mode = "cuda_graph"
         except Exception as exc:                        # keep the run valid: report the eager number
             print(f"bench: CUDA-graph capture failed ({exc.__class__.__name__}: {exc}); timing eager launches", file=sys.stderr)
@@ -288,9 +297,10 @@ def run_ours(args, rank, local_rank, world):
         work = None
         for j, (g1, g2, _) in enumerate(graphs[slot]):
             g1.replay()
-            if j == n_micro - 1:
-                work = launch_roi_allreduce()
-            g2.replay()
+            if g2 is not None:
+                if j == n_micro - 1:
+                    work = launch_roi_allreduce()
+                g2.replay()
         reduce_and_step(work)
         return graphs[slot][-1][2]
 
