@@ -206,8 +206,11 @@ def run_ours(args, rank, local_rank, world):
     def reduce_and_step(roi_work):
         """Tail of the step: the (small) SlowFast range joins the roi_heads range already in flight, 1/world, SGD."""
         if world > 1:
-            sf_work = dist.all_reduce(arena.range("slow_fast"), op=dist.ReduceOp.AVG, async_op=True)
-            roi_work.wait(); sf_work.wait()
+            if roi_work is None:        # unsplit step: the whole arena in one collective
+                dist.all_reduce(arena.flat, op=dist.ReduceOp.AVG)
+            else:
+                sf_work = dist.all_reduce(arena.range("slow_fast"), op=dist.ReduceOp.AVG, async_op=True)
+                roi_work.wait(); sf_work.wait()
         opt.step()
 
     def launch_roi_allreduce():          # ncclAvg: the 1/world scale happens inside the collective, no extra pass over the arena
@@ -279,9 +282,10 @@ def run_ours(args, rank, local_rank, world):
     if os.environ.get("SFVOS_GRAPH", "1") != "0":
         try:
             pool = torch.cuda.graph_pool_handle()
-            if world > 1:       # two graphs per micro-batch: the roi_heads all-reduce is launched between them
+            split = world > 1 and os.environ.get("SFVOS_DP_SPLIT", "1") != "0"
+            if split:           # two graphs per micro-batch: the roi_heads all-reduce is launched between them
                 graphs = [[step.capture_split(clips, zero_arena=(j == 0), pool=pool) for j, clips in enumerate(chunks(sq))] for sq in slots]
-            else:               # one GPU: nothing to overlap, one graph per micro-batch (no join between the two backward phases)
+            else:               # nothing to overlap (or SFVOS_DP_SPLIT=0): one graph per micro-batch, no join between the backward phases
                 graphs = []
                 for sq in slots:
                     per = []
