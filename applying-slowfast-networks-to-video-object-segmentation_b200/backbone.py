@@ -37,7 +37,7 @@ def _packed(owner, name, w, umma):
     process-wide cache keyed by address would hand a new model the operands of a freed one."""
     cin = w.shape[1]
     cp = (cin + 63) // 64 * 64 if umma else cin
-    capturing = torch.cuda.is_current_stream_capturing()
+    capturing = w.is_cuda and torch.cuda.is_current_stream_capturing()
     cache = owner.__dict__.setdefault("_sfvos_packed", {})
     tag = (w.data_ptr(), w._version, str(w.device), tuple(w.shape), umma)
     hit = cache.get(name)
@@ -264,7 +264,7 @@ class RPNHead(tv_rpn.RPNHead):
         n_pad = (a_cls + a_box + 31) // 32 * 32
         dev = self.cls_logits.weight.device
         # cls_logits and bbox_pred as one GEMM over the stacked (zero-padded) weight
-        capturing = torch.cuda.is_current_stream_capturing()
+        capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
         prm = (self.cls_logits.weight, self.bbox_pred.weight, self.cls_logits.bias, self.bbox_pred.bias)
         key = tuple((t.data_ptr(), t._version) for t in prm) + (str(dev),)
         hit = self.__dict__.get("_sfvos_pred")

@@ -22,6 +22,7 @@ stay torchvision/torch.
 """
 import math
 import os
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -232,9 +233,33 @@ def pool_pair(pool_a: "MultiScaleRoIAlign", pool_b: "MultiScaleRoIAlign", x, box
 # ----------------------------------------------------------------------------------------------------------------------
 # mask head: 4 x (conv3x3 + bias + ReLU) on [K,256,14,14]
 # ----------------------------------------------------------------------------------------------------------------------
-def _pack(w, mode, umma, kc, tap=(0, 0)):
+_PACKED = {}      # id(parameter) -> (weakref to it, {key: (version, data_ptr, value)}); entries die with the parameter
+
+
+def _cached(owner, key, make):
+    """``make()`` cached per PARAMETER OBJECT until it is written to (``_version``) or re-allocated.  Keyed by object identity
+    with a weak reference - not by address, which a new model's parameter can inherit from a freed one - and bypassed inside a
+    CUDA-graph capture, where the packing kernels must be part of the graph (a replay has to see ITS step's weights)."""
+    if not isinstance(owner, nn.Parameter) or (owner.is_cuda and torch.cuda.is_current_stream_capturing()):
+        return make()
+    ent = _PACKED.get(id(owner))
+    if ent is None or ent[0]() is not owner:
+        k = id(owner)
+        ent = (weakref.ref(owner, lambda _r, k=k: _PACKED.pop(k, None)), {})
+        _PACKED[k] = ent
+    hit = ent[1].get(key)
+    if hit is None or hit[0] != owner._version or hit[1] != owner.data_ptr():
+        hit = (owner._version, owner.data_ptr(), make())
+        ent[1][key] = hit
+    return hit[2]
+
+
+def _pack(w, mode, umma, kc, tap=(0, 0), owner=None):
+    """Packed GEMM operand of a weight.  ``owner``: the nn.Parameter ``w`` is (a view of) - inference and evaluation call the
+    heads with unchanged weights thousands of times, so the operand is cached on it."""
     cp = (kc + 63) // 64 * 64 if umma else kc
-    return ops.pack_weights(w, mode, BF16 if umma else F32, cp, tap), cp
+    owner = w if owner is None else owner
+    return _cached(owner, ("pack", mode, umma, cp, tap), lambda: ops.pack_weights(w, mode, BF16 if umma else F32, cp, tap)), cp
 
 
 class _MaskHeadFn(torch.autograd.Function):
@@ -339,14 +364,18 @@ class _MaskPredictorFn(torch.autograd.Function):
     @staticmethod
     def _fprop_weights(wt, umma, C):
         """ConvTranspose2d weight [C, co, 2, 2] -> operand of the 1x1 convolution C -> 4*co (output channel = tap*co + n)."""
-        parts = [_pack(wt, 2, umma, C, tap)[0] for tap in _TAPS]         # umma: bf16 [co][C] each; simt: f32 [C][co]
-        return torch.cat(parts, dim=0) if umma else torch.cat(parts, dim=1).contiguous()
+        def make():
+            parts = [_pack(wt, 2, umma, C, tap)[0] for tap in _TAPS]     # umma: bf16 [co][C] each; simt: f32 [C][co]
+            return torch.cat(parts, dim=0) if umma else torch.cat(parts, dim=1).contiguous()
+        return _cached(wt, ("convt_fprop", umma, C), make)
 
     @staticmethod
     def _dgrad_weights(wt, umma, co):
         """-> operand of the 1x1 convolution 4*co -> C of the data gradient (input channel = tap*co + n)."""
-        parts = [_pack(wt, 3, umma, co, tap)[0] for tap in _TAPS]        # umma: bf16 [C][co] each; simt: f32 [co][C]
-        return torch.cat(parts, dim=1).contiguous() if umma else torch.cat(parts, dim=0)
+        def make():
+            parts = [_pack(wt, 3, umma, co, tap)[0] for tap in _TAPS]    # umma: bf16 [C][co] each; simt: f32 [co][C]
+            return torch.cat(parts, dim=1).contiguous() if umma else torch.cat(parts, dim=0)
+        return _cached(wt, ("convt_dgrad", umma, co), make)
 
     @staticmethod
     @ops.device_guard
@@ -496,7 +525,7 @@ def _rows_act(t2d):
 def _linear_fwd(x, w, b, umma, dt_act, relu, out_dtype=None):
     """x: Act [M,K]; w [N,K] f32 parameter (N a multiple of 32 <= 256 or of 256); -> Act [M,N]."""
     N, K = w.shape
-    wp, cp = _pack(w.view(N, K, 1, 1, 1), 0, umma, K)
+    wp, cp = _pack(w.view(N, K, 1, 1, 1), 0, umma, K, owner=w)
     y = Act.empty(1, 1, 1, x.W, N, out_dtype or dt_act, x.buf.device)
     if x.W:
         ops.conv(x, wp, cp, N, (1, 1, 1), (0, 0, 0), 1, y, umma=umma, relu=relu, shift=b)
@@ -516,7 +545,7 @@ def _linear_bwd(x, dy, w, umma, dx_dtype, need_dx=True):
     if need_dx:
         dx = Act.empty(1, 1, 1, x.W, K, dx_dtype, dev)
         if x.W:
-            wd, cpd = _pack(w.view(N, K, 1, 1, 1), 1, umma, N)
+            wd, cpd = _pack(w.view(N, K, 1, 1, 1), 1, umma, N, owner=w)
             ops.conv(dy, wd, cpd, K, (1, 1, 1), (0, 0, 0), 1, dx, umma=umma)
     return gw, dx
 
@@ -593,12 +622,16 @@ class _BoxPredictorFn(torch.autograd.Function):
         n_out = wc.shape[0] + wb.shape[0]
         n_pad = _pred_pad(n_out)
         K = wc.shape[1]
-        w = torch.zeros(n_pad, K, dtype=torch.float32, device=x.device)
-        w[:wc.shape[0]] = wc.detach()
-        w[wc.shape[0]:n_out] = wb.detach()
-        b = torch.zeros(n_pad, dtype=torch.float32, device=x.device)
-        b[:wc.shape[0]] = bc.detach()
-        b[wc.shape[0]:n_out] = bb.detach()
+
+        def stack():
+            w = torch.zeros(n_pad, K, dtype=torch.float32, device=x.device)
+            w[:wc.shape[0]] = wc.detach()
+            w[wc.shape[0]:n_out] = wb.detach()
+            b = torch.zeros(n_pad, dtype=torch.float32, device=x.device)
+            b[:wc.shape[0]] = bc.detach()
+            b[wc.shape[0]:n_out] = bb.detach()
+            return w, b
+        w, b = _cached(wc, ("stack", wb.data_ptr(), wb._version, bc.data_ptr(), bc._version, bb.data_ptr(), bb._version, str(x.device)), stack)
         xin = _as_rows(x, dt_act)
         y = _linear_fwd(xin, w, b, umma, dt_act, False, out_dtype=torch.float32)
         ctx.acts = (xin, w)
