@@ -398,9 +398,17 @@ int sfvos_conv_pair_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.a_stage_bytes = (int)((a.a_tx_bytes + 1023u) & ~1023u);
     a.b_half_bytes = (a.N / 2) * (int)ROW;
     const int smem_budget = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, scale/shift, stats*/;
-    a.a_stages = 3;
+    // Pipeline depth (measured, round 2, slow_conv1 fprop / slow_conv2 dgrad / slow_conv3 fprop at level 0, same box):
+    // 3 A x 10 B stages 360 / 347 / 406 us, 2 x 6 353 / 335 / 395, 2 x 8 346 / 331 / 394, 2 x 16 361 / 344 / 406, 2 x 3 380 / 365 / 422.
+    // Deeper prefetch does not help - the MMA thread's waits for weight stages are L2 -> SM BANDWIDTH (every pixel tile
+    // re-streams the layer's weights: 2.16 GB per launch against ~6300 B/clk chip-wide), not latency - and more bytes in flight
+    // make it slightly worse, so: 2 activation stages, at most 8 weight stages.
+    a.a_stages = env_int("SFVOS_PAIR_ASTAGES", 2);
+    if (a.a_stages < 2) a.a_stages = 2;
+    if (a.a_stages > 4) a.a_stages = 4;
     a.b_stages = (smem_budget - a.a_stages * a.a_stage_bytes) / a.b_half_bytes;
-    if (a.b_stages > 10) a.b_stages = 10;
+    const int b_cap = env_int("SFVOS_PAIR_BSTAGES", 8);
+    if (a.b_stages > b_cap) a.b_stages = b_cap;
     SF_CHECK(a.b_stages >= 3, "conv_pair: not enough shared memory");
     a.idesc = umma_idesc_bf16(2 * BM, a.N, 0, 0);
     uint32_t cols = 32;
