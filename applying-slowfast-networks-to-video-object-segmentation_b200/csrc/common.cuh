@@ -224,4 +224,163 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// ---- coalescing epilogue ---------------------------------------------------------------------------------------
+// tcgen05.ld 32x32b hands every lane ONE accumulator row (= one pixel): a direct store is 32 lanes x 16 B on 32 different
+// 128-byte lines per instruction, per-channel scale / shift cost 16 shared-memory loads per 32 columns, and the fused
+// BatchNorm statistics need a 31-shuffle transpose-reduce per quantity.  The epilogue warps therefore pass every
+// 32 row x 32 column f32 block through a warp-private 4 KB shared-memory tile (16-byte chunks XOR-swizzled by row:
+// conflict-free both ways) and continue in the TRANSPOSED ownership: lane = (sub = lane / 8, part = lane % 8) holds
+// columns 4 part .. 4 part + 3 of rows 4 i + sub, i = 0..7.  A store instruction then covers 4 pixels x 128 B (f32) or
+// 4 x 64 B (bf16) of whole sectors, a lane needs ONE float4 of scale / shift per block, and the column sums are 8 adds
+// in registers plus a 6-shuffle butterfly over the 4 lanes that share a column set.
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;          // per epilogue warp
+
+struct EpiRows {
+    int pix[8];          // pixel index (NOT yet multiplied by the channel stride) of tile row 4 i + sub, -1 = row not stored
+};
+// pix_own: this lane's own pixel index (row = lane of the warp's 32 rows) or -1
+__device__ __forceinline__ EpiRows epi_rows(int pix_own, int lane) {
+    EpiRows r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.pix[i] = __shfl_sync(0xffffffffu, pix_own, 4 * i + (lane >> 3));
+    return r;
+}
+
+struct EpiOut {
+    void* y;                         // output tensor, channels-last
+    long long y_cstride;             // elements per pixel
+    int y_bf16, relu, accumulate;
+    const __nv_bfloat16* relu_mask;  // fused ReLU backward: zero where the activation is not positive (nullable)
+    long long mask_cstride;
+};
+
+// Step 1: the lane's raw accumulator row v of a 32-column block -> x[i] = columns 4 part .. 4 part + 3 of row 4 i + sub.
+// All 32 lanes must call (the tile is warp-collective).
+__device__ __forceinline__ void epi_transpose(float* stage, const uint32_t (&v)[32], int lane, float4 (&x)[8]) {
+    const int sub = lane >> 3, part = lane & 7;
+    {
+        uint4* s = reinterpret_cast<uint4*>(stage) + lane * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s[c ^ (lane & 7)] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + sub;
+        x[i] = reinterpret_cast<const float4*>(stage)[row * 8 + (part ^ (row & 7))];
+    }
+    __syncwarp();                                        // the tile may be overwritten by the next block from here on
+}
+// Fused ReLU backward: zero the gradient where the bf16 activation of the layer below is not positive.
+__device__ __forceinline__ void epi_relu_mask(float4 (&x)[8], const EpiRows& rows, const EpiOut& o, int ch) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (rows.pix[i] >= 0) {
+            const uint2 m = __ldg(reinterpret_cast<const uint2*>(o.relu_mask + (long long)rows.pix[i] * o.mask_cstride + ch));
+            // bf16 > 0  <=>  sign bit clear and not zero
+            const uint32_t m0 = m.x & 0xffffu, m1 = m.x >> 16, m2 = m.y & 0xffffu, m3 = m.y >> 16;
+            if (!(m0 != 0 && m0 < 0x8000u)) x[i].x = 0.0f;
+            if (!(m1 != 0 && m1 < 0x8000u)) x[i].y = 0.0f;
+            if (!(m2 != 0 && m2 < 0x8000u)) x[i].z = 0.0f;
+            if (!(m3 != 0 && m3 < 0x8000u)) x[i].w = 0.0f;
+        }
+}
+// Column sums / sums of squares of the stored rows, accumulated into the caller's registers (columns 4 part ..).
+__device__ __forceinline__ void epi_colsum(const float4 (&x)[8], const EpiRows& rows, float (&s)[4], float (&q)[4]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (rows.pix[i] >= 0) {
+            s[0] += x[i].x; s[1] += x[i].y; s[2] += x[i].z; s[3] += x[i].w;
+            q[0] = fmaf(x[i].x, x[i].x, q[0]); q[1] = fmaf(x[i].y, x[i].y, q[1]);
+            q[2] = fmaf(x[i].z, x[i].z, q[2]); q[3] = fmaf(x[i].w, x[i].w, q[3]);
+        }
+}
+// Butterfly over the 4 lanes of a column set (lane bits 3, 4): afterwards lane bit 4 selects sums / squares and lane bit 3
+// the column pair, every lane holding 2 finished values, which it adds to sum_dst / sq_dst (nullable) at channel ch + ...
+__device__ __forceinline__ void epi_colsum_flush(const float (&s)[4], const float (&q)[4], int lane, float* sum_dst, float* sq_dst,
+                                                 int ch) {
+    const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+    float k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float send = up16 ? s[j] : q[j];
+        k[j] = (up16 ? q[j] : s[j]) + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float f[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = up8 ? k[j] : k[j + 2];
+        f[j] = (up8 ? k[j + 2] : k[j]) + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float* dst = up16 ? sq_dst : sum_dst;
+    if (dst != nullptr) {
+        atomicAdd(dst + ch + (up8 ? 2 : 0), f[0]);
+        atomicAdd(dst + ch + (up8 ? 2 : 0) + 1, f[1]);
+    }
+}
+// Per-channel affine / ReLU and the store (bf16, f32 or f32 read-modify-write).  scale / shift: nullable, indexed by
+// absolute channel (shared or global memory, 16-byte aligned at ch).
+__device__ __forceinline__ void epi_store(float4 (&x)[8], const EpiRows& rows, int ch, const float* scale, const float* shift,
+                                          const EpiOut& o) {
+    if (scale != nullptr || shift != nullptr) {
+        const float4 sc = scale ? *reinterpret_cast<const float4*>(scale + ch) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 sh = shift ? *reinterpret_cast<const float4*>(shift + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            x[i].x = fmaf(x[i].x, sc.x, sh.x); x[i].y = fmaf(x[i].y, sc.y, sh.y);
+            x[i].z = fmaf(x[i].z, sc.z, sh.z); x[i].w = fmaf(x[i].w, sc.w, sh.w);
+        }
+    }
+    if (o.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
+        }
+    }
+    if (o.y_bf16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (rows.pix[i] >= 0) {
+                uint2 u;
+                u.x = pack_bf16x2(x[i].x, x[i].y);
+                u.y = pack_bf16x2(x[i].z, x[i].w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(o.y) + (long long)rows.pix[i] * o.y_cstride + ch) = u;
+            }
+    } else if (o.accumulate) {
+        float4 old[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)                      // all reads of the read-modify-write in flight at once
+            old[i] = rows.pix[i] >= 0
+                         ? *reinterpret_cast<const float4*>(reinterpret_cast<float*>(o.y) + (long long)rows.pix[i] * o.y_cstride + ch)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (rows.pix[i] >= 0)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.y) + (long long)rows.pix[i] * o.y_cstride + ch) =
+                    make_float4(x[i].x + old[i].x, x[i].y + old[i].y, x[i].z + old[i].z, x[i].w + old[i].w);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (rows.pix[i] >= 0)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.y) + (long long)rows.pix[i] * o.y_cstride + ch) = x[i];
+    }
+}
+// The whole block: v = the lane's raw accumulator row, col = first output channel of the block.  sum_dst / sq_dst: nullable
+// atomicAdd targets indexed by absolute channel: column sums (and sums of squares) of the RAW (masked) accumulators over
+// the stored rows.
+__device__ __forceinline__ void epi_block(float* stage, const uint32_t (&v)[32], const EpiRows& rows, int lane, int col,
+                                          const float* scale, const float* shift, const EpiOut& o, float* sum_dst,
+                                          float* sq_dst) {
+    float4 x[8];
+    epi_transpose(stage, v, lane, x);
+    const int ch = col + 4 * (lane & 7);
+    if (o.relu_mask != nullptr) epi_relu_mask(x, rows, o, ch);
+    if (sum_dst != nullptr) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+        epi_colsum(x, rows, s, q);
+        epi_colsum_flush(s, q, lane, sum_dst, sq_dst, ch);
+    }
+    epi_store(x, rows, ch, scale, shift, o);
+}
 #endif  // __CUDACC__

@@ -33,6 +33,7 @@ struct PairArgs {
     int tiles_w, tiles_h, ntiles, npairs;
     int N, kt, pad_t, cchunks;
     int LP, a_stages, b_stages, a_stage_bytes, b_half_bytes;
+    int epi_stage;                               // epilogue through the shared-memory transpose (common.cuh: epi_block)
     uint32_t idesc, tmem_cols, a_tx_bytes;
     void* y;
     int y_bf16, relu, accumulate;
@@ -118,6 +119,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     float* s_shift = s_scale + 256;
     float* s_sum = s_shift + 256;
     float* s_sq = s_sum + 256;
+    float* s_stage = s_sq + 256;                              // EPI_STAGE_BYTES per epilogue warp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -249,6 +251,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * a.N;
+            if (a.epi_stage) {
+                const EpiRows rows = epi_rows(valid ? (int)pix : -1, lane);
+                EpiOut eo;
+                eo.y = a.y; eo.y_cstride = a.y_cstride; eo.y_bf16 = a.y_bf16; eo.relu = a.relu; eo.accumulate = a.accumulate;
+                eo.relu_mask = a.relu_mask; eo.mask_cstride = a.mask_cstride;
+                float* sum_dst = (do_stats || (a.relu_mask != nullptr && a.sum != nullptr)) ? s_sum : nullptr;
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + c0, v);
+                    tmem_ld_wait();
+                    epi_block(s_stage + ew * (EPI_STAGE_BYTES / 4), v, rows, lane, c0, affine ? s_scale : nullptr,
+                              affine ? s_shift : nullptr, eo, sum_dst, do_stats ? s_sq : nullptr);
+                }
+            } else
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + c0, v);
@@ -397,7 +413,13 @@ int sfvos_conv_pair_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.a_tx_bytes = (uint32_t)(a.LP * (TH + 2) * ROW);
     a.a_stage_bytes = (int)((a.a_tx_bytes + 1023u) & ~1023u);
     a.b_half_bytes = (a.N / 2) * (int)ROW;
-    const int smem_budget = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, scale/shift, stats*/;
+    const int small_bytes = 8192 /*barriers, scale/shift, stats*/ + (EPI_THREADS / 32) * EPI_STAGE_BYTES /*epilogue transpose tiles*/;
+    const int smem_budget = 227 * 1024 - 1024 /*align*/ - small_bytes;
+    // Measured (B200, level 0, B = 8): f32 outputs gain from the transposed epilogue (slow_conv1 fprop with statistics 350 -> 310 us,
+    // its f32 dgrad 340 -> 299 us); bf16 outputs without statistics do not (mask-head conv 191 -> 203 us) - this kernel runs at the
+    // shared-memory port's limit and the transpose tile adds 8 KB of traffic per 32-column block.
+    const int es = env_int("SFVOS_EPI_STAGE", -1);
+    a.epi_stage = es < 0 ? (p->y_dtype != SFVOS_BF16) : (es != 0);
     // Pipeline depth (measured, round 2, slow_conv1 fprop / slow_conv2 dgrad / slow_conv3 fprop at level 0, same box):
     // 3 A x 10 B stages 360 / 347 / 406 us, 2 x 6 353 / 335 / 395, 2 x 8 346 / 331 / 394, 2 x 16 361 / 344 / 406, 2 x 3 380 / 365 / 422.
     // Deeper prefetch does not help - the MMA thread's waits for weight stages are L2 -> SM BANDWIDTH (every pixel tile
@@ -441,7 +463,7 @@ int sfvos_conv_pair_launch(const sfvos_conv_params* p, cudaStream_t stream) {
         rc = sfvos_make_tmap(&tw, p->w, 3, dims, str, box, ROW);
         if (rc) return rc;
     }
-    const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_half_bytes + 1024 + 8192;
+    const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_half_bytes + 1024 + small_bytes;
     int clusters = sfvos_num_sms() / 2;
     if (clusters > a.npairs) clusters = a.npairs;
     SF_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -13,7 +13,8 @@
 // taps x G temporal taps: bytes ingested and A-operand reads per FLOP drop by G (3 for fast_conv1 at fp = 8).
 //   warp 0 = activation TMA producer, warp 3 = weight TMA producer (9 per-spatial-tap pieces, reloaded per
 //   (tap group, chunk) as soon as the MMAs of the previous chunk's last frame release them), warp 1 = MMA issuer,
-//   warp 2 = TMEM allocator, warps 4..7 = epilogue (per output frame: BN statistics, affine/ReLU, store).
+//   warp 2 = TMEM allocator, warps 4..11 = epilogue (per output frame: BN statistics, affine/ReLU, store; two warps per
+//   TMEM lane quarter take alternate frames).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -22,14 +23,12 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int NC = 32;                      // output channels per frame
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;             // warps 0-3: TMA (activations) / MMA / TMEM alloc / TMA (weights); warps 4-11: epilogue
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;             // TWO warps per TMEM lane quarter, taking alternate output frames
 constexpr int TW = 8, TH = 16;              // spatial tile (8 wide x 16 tall = 128 accumulator rows)
 constexpr int SMALL_BYTES = 2048;           // barriers, scale / shift, statistics
-constexpr int STAGE_PITCH = 33;             // floats per staged accumulator row (32 + 1: conflict-free both ways)
-constexpr int STAGE_BYTES = 4 * 32 * STAGE_PITCH * 4;   // one 32 x 32 f32 block per epilogue warp
-constexpr int STAGE_RESERVE = (STAGE_BYTES + 1023) / 1024 * 1024;
+constexpr int STAGE_RESERVE = (EPI_THREADS / 32) * EPI_STAGE_BYTES;   // one 32 x 32 f32 transpose tile per epilogue warp (common.cuh)
 
 struct TsArgs {
     int B, To, Ti, H, W;
@@ -247,118 +246,80 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
     } else if (warp >= EPI_WARP0) {
         // ------------------------------ epilogue ------------------------------
-        const int q = warp - EPI_WARP0;                  // TMEM lane quarter == warp id % 4
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3;                            // TMEM lane quarter == warp id % 4
+        const int par = ew >> 2;                         // this warp's frames: t0 + par, t0 + par + 2, ...
         const int r = q * 32 + lane;                     // accumulator row = pixel within the tile
         const int hl = r / TW, wl = r - hl * TW;
         const bool do_stats = (a.sum != nullptr);
         const bool affine = (a.scale != nullptr) || (a.shift != nullptr);
+        const bool staged = a.stage_mode != 0;
+        const long long frame_pix = (long long)a.H * a.W;
+        float* stage = s_stage + ew * (EPI_STAGE_BYTES / 4);
+        EpiOut eo;
+        eo.y = a.y; eo.y_cstride = a.y_cstride; eo.y_bf16 = a.y_bf16; eo.relu = a.relu; eo.accumulate = a.accumulate;
+        eo.relu_mask = nullptr; eo.mask_cstride = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        // BatchNorm statistics: this thread's row sums of x and x^2 per output channel stay in REGISTERS across every frame
-        // of every work item of the CTA; the cross-lane reduction (31 shuffles + selects per quantity) runs ONCE at the end
-        // instead of once per (item, frame).  ncu (round 2): the per-frame reductions were 314 of the epilogue's 407
-        // instructions per frame and its dependent shuffle chains kept the single epilogue warp of each scheduler at 0.15 IPC,
-        // which -- not the tensor pipe (34 % active) -- set the pace of the 32-channel layers.
-        float st_sum[32], st_sq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { st_sum[j] = 0.0f; st_sq[j] = 0.0f; }
+        // BatchNorm statistics: in the transposed ownership of the epilogue (common.cuh) a lane sees 4 channels of 8 pixels per
+        // frame, so its column sums of x and x^2 are 8 REGISTERS that live across every frame of every work item of the CTA; the
+        // cross-lane reduction (a 6-shuffle butterfly) runs ONCE at the end.  (Round 2, first version: per-(item, frame)
+        // transpose-reduces were 314 of the epilogue's 407 instructions per frame at 0.15 IPC.)
+        float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
             const Item it = decode_item(a, item);
             const int h = it.h0 + hl, w = it.w0 + wl;
             const bool valid = (h < a.H) && (w < a.W);
+            const long long pix0 = (((long long)it.b * a.To + it.t0) * a.H + h) * a.W + w;      // this lane's pixel in frame t0
+            const EpiRows rows0 = epi_rows(valid ? (int)pix0 : -1, lane);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * a.Fg * NC;
-            for (int t = it.t0; t < (a.dbg & 1 ? it.t0 : it.t1); ++t) {
-                const long long pix = (((long long)it.b * a.To + t) * a.H + h) * a.W + w;
+            for (int t = it.t0 + par; t < (a.dbg & 1 ? it.t0 : it.t1); t += 2) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + (it.t1 - 1 - t) * NC, v);
                 tmem_ld_wait();
-                if (do_stats && valid) {
+                if (staged) {
+                    EpiRows rt;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        st_sum[j] += x;
-                        st_sq[j] = fmaf(x, x, st_sq[j]);
-                    }
-                }
-                float o[32];
-                if (affine) {           // per-channel scale / shift from shared memory, 16 bytes per load
-                    const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
-                    const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 sc = sc4[j], sh = sh4[j];
-                        o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-                        o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-                        o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-                        o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
-                }
-                if (a.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.0f);
-                }
-                if (!a.y_bf16 && !a.stage_mode) {
-                    if (valid) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + pix * a.y_cstride);
+                    for (int i = 0; i < 8; ++i) rt.pix[i] = rows0.pix[i] >= 0 ? rows0.pix[i] + (t - it.t0) * (int)frame_pix : -1;
+                    float4 x[8];
+                    epi_transpose(stage, v, lane, x);
+                    if (do_stats) epi_colsum(x, rt, cs, cq);
+                    epi_store(x, rt, 4 * (lane & 7), affine ? s_scale : nullptr, affine ? s_shift : nullptr, eo);
+                } else if (valid) {
+                    // bf16 outputs without statistics (eval-mode folded layers): a thread owns one pixel's 64 bytes
+                    const long long pix = pix0 + (t - it.t0) * frame_pix;
+                    float o[32];
+                    if (affine) {           // per-channel scale / shift from shared memory, 16 bytes per load
+                        const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+                        const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            float4 u = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                            if (a.accumulate) {
-                                float4 old = dst[j];
-                                u.x += old.x; u.y += old.y; u.z += old.z; u.w += old.w;
-                            }
-                            dst[j] = u;
+                            const float4 sc = sc4[j], sh = sh4[j];
+                            o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+                            o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+                            o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+                            o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
                         }
-                    }
-                } else if (a.y_bf16) {
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride);
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
-                            u.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
-                            u.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
-                            u.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
-                            dst[j] = u;
-                        }
+                        for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
                     }
-                } else {
-                    // f32 rows (raw conv outputs, data gradients; the lateral dgrads read-modify-write them): a thread owns
-                    // one pixel's 128 bytes, so a direct store is 32 lanes x 16 B on 32 different lines per instruction.
-                    // Transpose the warp's 32 x 32 block through shared memory instead: 8 lanes cover one pixel's 128 B and an
-                    // instruction covers 4 neighbouring pixels = 512 contiguous bytes (of a dense 32-channel tensor).
-                    float* stage = s_stage + q * (32 * STAGE_PITCH);
+                    if (a.relu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stage[lane * STAGE_PITCH + j] = o[j];
-                    __syncwarp();
-                    const int sub = lane >> 3, part = lane & 7;
-                    float4* dsts[8];
-                    float4 olds[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {                    // all 8 reads of the read-modify-write in flight at once
-                        const int rr = q * 32 + 4 * i + sub;         // row of the tile
-                        const int hh = it.h0 + rr / TW, ww = it.w0 + (rr - (rr / TW) * TW);
-                        dsts[i] = nullptr;
-                        olds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (hh < a.H && ww < a.W) {
-                            const long long pp = (((long long)it.b * a.To + t) * a.H + hh) * a.W + ww;
-                            dsts[i] = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + pp * a.y_cstride) + part;
-                            if (a.accumulate) olds[i] = *dsts[i];
-                        }
+                        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.0f);
                     }
+                    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + pix * a.y_cstride);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float* sv = stage + (4 * i + sub) * STAGE_PITCH + 4 * part;
-                        if (dsts[i] != nullptr)
-                            *dsts[i] = make_float4(sv[0] + olds[i].x, sv[1] + olds[i].y, sv[2] + olds[i].z, sv[3] + olds[i].w);
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        u.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
+                        u.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+                        u.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+                        u.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+                        dst[j] = u;
                     }
-                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -366,10 +327,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             if (++acc == a.nbuf) { acc = 0; acc_phase ^= 1; }
         }
         if (do_stats) {
-            float s = warp_transpose_reduce32(st_sum, lane);
-            atomicAdd(&s_sum[lane], s);
-            s = warp_transpose_reduce32(st_sq, lane);
-            atomicAdd(&s_sq[lane], s);
+            epi_colsum_flush(cs, cq, lane, s_sum, s_sq, 4 * (lane & 7));
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             const int i = threadIdx.x - EPI_WARP0 * 32;
             if (i < NC) {
@@ -449,10 +407,10 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.y = p->y; a.y_bf16 = (p->y_dtype == SFVOS_BF16); a.relu = p->relu; a.accumulate = p->accumulate;
     a.y_cstride = p->y_cstride;
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
-    {   // 0 = direct stores, 1 = staged only for read-modify-write outputs, 2 = staged for every f32 output
-        const int m = env_int("SFVOS_TSTACK_STAGE", 1);
-        a.stage_mode = (m >= 2 || (m == 1 && p->accumulate)) ? 1 : 0;
-    }
+    // f32 outputs (raw conv outputs with statistics, data gradients, the read-modify-write lateral dgrads) always leave through
+    // the transposing epilogue; bf16 outputs without statistics (eval-mode folded layers) store directly unless forced
+    a.stage_mode = (!a.y_bf16 || a.sum != nullptr || env_int("SFVOS_TSTACK_STAGE", 1) >= 3) ? 1 : 0;
+    SF_CHECK(p->B * p->To * p->H * p->W < (1LL << 31), "conv_tstack: too many output pixels");
 
     a.dbg = env_int("SFVOS_TSTACK_DBG", 0);
 

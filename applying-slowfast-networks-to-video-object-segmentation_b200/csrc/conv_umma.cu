@@ -28,9 +28,9 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;             // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;             // TWO warps per TMEM lane quarter, each draining half of the accumulator's columns
 constexpr int HALO_LP = 16;                 // pixels per halo line in smem (tile width 8 + 2 halo, padded to 16)
 
 struct ConvArgs {
@@ -40,6 +40,7 @@ struct ConvArgs {
     int nchunks;                                // N tiles of one pixel tile (wide fc layers: Cout = nchunks * 256)
     int b_resident;                             // per-tap mode: ALL weight tiles stay in shared memory for the CTA's lifetime
     int halo, use_bo, a_stages, b_stages, a_stage_bytes, b_group;     // b_group = taps per B stage
+    int epi_stage;                              // epilogue through the shared-memory transpose (common.cuh: epi_block)
     uint32_t idesc, tmem_cols, a_tx_bytes;
     void* y;
     int y_bf16, relu, accumulate;
@@ -77,6 +78,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     float* s_shift = s_scale + 256;
     float* s_sum = s_shift + 256;
     float* s_sq = s_sum + 256;
+    float* s_stage = s_sq + 256;                              // EPI_STAGE_BYTES per epilogue warp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -230,7 +232,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     } else if (warp >= EPI_WARP0) {
         // ------------------------------ epilogue ------------------------------
-        const int q = warp - EPI_WARP0;                  // TMEM lane quarter == warp id % 4
+        // A single epilogue warp per scheduler runs its dependent chains (TMEM load -> transpose -> convert -> store) at
+        // ~0.15 IPC; measured on the mask predictor's ConvTranspose GEMM (K = 256, N = 1024, bf16 output): main loop alone
+        // 105 us, with the 4-warp epilogue 383 us.  Two warps per lane quarter split the accumulator's column blocks.
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3;                            // TMEM lane quarter == warp id % 4
+        const int c_split = ((a.N / 32 + 1) / 2) * 32;
+        const int c_begin = (ew >> 2) ? c_split : 0, c_end = (ew >> 2) ? a.N : c_split;
         const int r = q * 32 + lane;                     // accumulator row = pixel within the tile
         const int hl = r / a.TW;
         const int wl = r - hl * a.TW;
@@ -251,7 +259,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * a.N;
-            for (int c0 = 0; c0 < a.N; c0 += 32) {
+            if (a.epi_stage) {
+                const EpiRows rows = epi_rows(valid ? (int)pix : -1, lane);
+                EpiOut eo;
+                eo.y = a.y; eo.y_cstride = a.y_cstride; eo.y_bf16 = a.y_bf16; eo.relu = a.relu; eo.accumulate = a.accumulate;
+                eo.relu_mask = a.relu_mask; eo.mask_cstride = a.mask_cstride;
+                // wide fc layers (several N chunks): bias / scale straight from global memory, indexed by absolute channel
+                const float* scp = !affine ? nullptr : (a.nchunks > 1 ? a.scale : s_scale);
+                const float* shp = !affine ? nullptr : (a.nchunks > 1 ? a.shift : s_shift);
+                float* sum_dst = do_stats ? s_sum : (a.relu_mask != nullptr ? a.sum : nullptr);
+                float* sq_dst = do_stats ? s_sq : nullptr;
+                EpiRows rows_d = rows;
+                if (a.epi_stage & 2) {                   // DEBUG: nothing is stored
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rows_d.pix[i] = -1;
+                }
+                for (int c0 = c_begin; c0 < ((a.epi_stage & 4) ? 0 : c_end); c0 += 32) {      // DEBUG bit 2: accumulators released unread
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + c0, v);
+                    tmem_ld_wait();
+                    epi_block(s_stage + ew * (EPI_STAGE_BYTES / 4), v, rows_d, lane, nbase + c0, scp, shp, eo, sum_dst, sq_dst);
+                }
+            } else
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + c0, v);
                 tmem_ld_wait();
@@ -417,6 +447,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
                  "conv_umma: relu_mask needs the identity output mapping");
     }
     SF_CHECK(p->B * p->To * p->H * p->W < (1LL << 31), "conv_umma: too many output pixels");
+    SF_CHECK(p->B * p->To * (p->OH ? p->OH : p->H) * (p->OW ? p->OW : p->W) < (1LL << 31), "conv_umma: too many output pixels");
     int rc = sfvos_device_check();
     if (rc) return rc;
     if (sfvos_conv_tstack_applicable(p)) return sfvos_conv_tstack_launch(p, stream);
@@ -443,15 +474,19 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     a.pad_t = (int)p->pad_t; a.pad_h = (int)p->pad_h; a.pad_w = (int)p->pad_w;
     a.cchunks = (int)(p->Cp / BK);
     const int b_bytes = a.N * BK * 2;
-    const int smem_budget = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, scale/shift, stats*/;
+    const int small_bytes = 8192 /*barriers, scale/shift, stats*/ + (EPI_THREADS / 32) * EPI_STAGE_BYTES /*epilogue transpose tiles*/;
+    const int smem_budget = 227 * 1024 - 1024 /*align*/ - small_bytes;
+    a.epi_stage = env_int("SFVOS_EPI_STAGE", 1);
     uint32_t abox_w, abox_h;
     if (a.halo) {
         abox_w = HALO_LP; abox_h = (uint32_t)(a.TH + 2);
         a.a_stage_bytes = HALO_LP * (a.TH + 2) * BK * 2;                    // 36 KB (BK=64) / 18 KB (BK=32)
         // narrow N: the MMA-issuing thread, not the tensor pipe, is the limiter -> all 9 taps' weights per barrier
         a.b_group = (9 * b_bytes <= 72 * 1024 && a.N <= 64) ? 9 : 1;
+        if (a.b_group == 9 && smem_budget - 2 * 9 * b_bytes < 2 * a.a_stage_bytes) a.b_group = 3;   // N = 64 at BK = 64: 3 taps per barrier
         const int b_stage = a.b_group * b_bytes;
         a.b_stages = a.b_group == 9 ? 2 : 4;
+        while (a.b_stages > 2 && smem_budget - a.b_stages * b_stage < 2 * a.a_stage_bytes) --a.b_stages;     // wide N: fewer weight stages
         a.a_stages = (smem_budget - a.b_stages * b_stage) / a.a_stage_bytes;
         if (a.a_stages > 4) a.a_stages = 4;
         if (a.b_group == 1 && a.a_stages > 2 && b_bytes <= 8192) a.b_stages = 8;
@@ -461,7 +496,8 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         a.a_stage_bytes = BM * BK * 2;
         a.b_group = 1;
         const long long all_b = (long long)p->kt * p->kh * p->kw * a.cchunks * b_bytes;
-        if (all_b <= 144 * 1024 && env_int("SFVOS_B_RESIDENT", 1) && (a.nchunks == 1 || sfvos_num_sms() >= a.nchunks)) {
+        if (all_b <= 144 * 1024 && all_b + 3 * a.a_stage_bytes <= smem_budget && env_int("SFVOS_B_RESIDENT", 1) &&
+            (a.nchunks == 1 || sfvos_num_sms() >= a.nchunks)) {
             a.b_resident = 1;
             a.b_stages = (int)(all_b / b_bytes);
             int st = (int)((smem_budget - all_b) / a.a_stage_bytes);
@@ -508,7 +544,7 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
         rc = sfvos_make_tmap(&tw, p->w, 3, dims, str, box, BK * 2);
         if (rc) return rc;
     }
-    const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_group * b_bytes + 1024 + 8192;
+    const int smem_bytes = a.a_stages * a.a_stage_bytes + a.b_stages * a.b_group * b_bytes + 1024 + small_bytes;
     int grid = sfvos_num_sms();
     if (grid > a.ntiles * a.nchunks) grid = a.ntiles * a.nchunks;
     if (a.b_resident && a.nchunks > 1) grid -= grid % a.nchunks;     // every CTA keeps ONE N chunk (its resident weights)

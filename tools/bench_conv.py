@@ -43,6 +43,55 @@ def main():
             ms = sorted(ts)[len(ts) // 2]
             print(f"{case:12s} 1024 ROIs 14x14: {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s", flush=True)
             continue
+        if name in ("convt4", "maskconv", "fc6"):
+            # mask predictor ConvTranspose2d as ONE 1x1 GEMM 256 -> 1024 (bf16 out, bias + ReLU) / mask-head 3x3 conv fprop (bias + ReLU,
+            # bf16 out) or dgrad with the fused ReLU backward / box head fc6 (12544 -> 1024) as a 1x1 conv over 4096 "pixels"
+            K, Hm = 1024, 14
+            if name == "convt4" and mode == "d":      # data gradient of the ConvTranspose: 1x1 GEMM 1024 -> 256
+                x = ops.Act(torch.randn(K * Hm * Hm * 1024, device=dev).bfloat16(), K, 1, Hm, Hm, 1024)
+                wp = (torch.randn(256, 1024, device=dev) / 32).bfloat16().contiguous()
+                y = ops.Act.empty(K, 1, Hm, Hm, 256, torch.bfloat16, dev)
+                fn = lambda: ops.conv(x, wp, 1024, 256, (1, 1, 1), (0, 0, 0), 1, y, umma=True)
+                flops = 2.0 * K * Hm * Hm * 256 * 1024
+            elif name == "convt4":
+                x = ops.Act(torch.randn(K * Hm * Hm * 256, device=dev).bfloat16(), K, 1, Hm, Hm, 256)
+                wp = (torch.randn(1024, 256, device=dev) / 16).bfloat16().contiguous()
+                y = ops.Act.empty(K, 1, Hm, Hm, 1024, torch.bfloat16, dev)
+                bias = torch.zeros(1024, device=dev)
+                fn = lambda: ops.conv(x, wp, 256, 1024, (1, 1, 1), (0, 0, 0), 1, y, umma=True, relu=True, shift=bias)
+                flops = 2.0 * K * Hm * Hm * 256 * 1024
+            elif name == "fc6":
+                M = 4096
+                x = ops.Act(torch.randn(M * 12544, device=dev).bfloat16(), 1, 1, 1, M, 12544)
+                wp = (torch.randn(1024, 12544, device=dev) / 112).bfloat16().contiguous()
+                y = ops.Act.empty(1, 1, 1, M, 1024, torch.bfloat16, dev)
+                bias = torch.zeros(1024, device=dev)
+                fn = lambda: ops.conv(x, wp, 12544, 1024, (1, 1, 1), (0, 0, 0), 1, y, umma=True, relu=True, shift=bias)
+                flops = 2.0 * M * 12544 * 1024
+            else:
+                x = ops.Act(torch.randn(K * Hm * Hm * 256, device=dev).bfloat16(), K, 1, Hm, Hm, 256)
+                wt = torch.randn(256, 256, 1, 3, 3, device=dev) / 48
+                wp = ops.pack_weights(wt, 1 if mode == "d" else 0, ops.BF16, 256)
+                y = ops.Act.empty(K, 1, Hm, Hm, 256, torch.bfloat16, dev)
+                bias = torch.zeros(256, device=dev)
+                if mode == "d":
+                    act = ops.Act(torch.randn(K * Hm * Hm * 256, device=dev).relu().bfloat16(), K, 1, Hm, Hm, 256)
+                    fn = lambda: ops.conv(x, wp, 256, 256, (1, 3, 3), (0, 1, 1), 1, y, umma=True, relu_mask=act, dbias=bias)
+                else:
+                    fn = lambda: ops.conv(x, wp, 256, 256, (1, 3, 3), (0, 1, 1), 1, y, umma=True, relu=True, shift=bias)
+                flops = 2.0 * K * Hm * Hm * 256 * 256 * 9
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(a.reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sorted(ts)[len(ts) // 2]
+            envs = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("SFVOS_"))
+            print(f"{case:12s} {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s   [{envs}]", flush=True)
+            continue
         T, cin, cout, kt, khw = CASES[name]
         pad = 1 if khw == 3 else 0
         To = T - kt + 1
