@@ -20,7 +20,8 @@ class ConvParams(ctypes.Structure):
                 ("scale", vp), ("shift", vp), ("sum", vp), ("sumsq", vp),
                 ("accumulate", i32), ("reserved", i32),
                 ("OH", i64), ("OW", i64), ("oy_mul", i64), ("oy_off", i64), ("ox_mul", i64), ("ox_off", i64),
-                ("relu_mask", vp), ("relu_mask_cstride", i64)]
+                ("relu_mask", vp), ("relu_mask_cstride", i64),
+                ("addend", vp), ("addend_dtype", i32), ("reserved2", i32), ("addend_cstride", i64)]
 
 
 class WgradParams(ctypes.Structure):

@@ -253,6 +253,9 @@ struct EpiOut {
     int y_bf16, relu, accumulate;
     const __nv_bfloat16* relu_mask;  // fused ReLU backward: zero where the activation is not positive (nullable)
     long long mask_cstride;
+    const void* addend;              // optional: y = act(...) + addend[pixel, channel] (f32 or bf16 tensor indexed like y)
+    long long addend_cstride;
+    int addend_bf16;
 };
 
 // Step 1: the lane's raw accumulator row v of a 32-column block -> x[i] = columns 4 part .. 4 part + 3 of row 4 i + sub.
@@ -337,6 +340,26 @@ __device__ __forceinline__ void epi_store(float4 (&x)[8], const EpiRows& rows, i
         for (int i = 0; i < 8; ++i) {
             x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
         }
+    }
+    if (o.addend != nullptr) {
+        float4 ad[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                    // all reads in flight at once
+            ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rows.pix[i] >= 0) {
+                if (o.addend_bf16) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(o.addend) +
+                                                                    (long long)rows.pix[i] * o.addend_cstride + ch);
+                    ad[i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                                        __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+                } else {
+                    ad[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.addend) +
+                                                             (long long)rows.pix[i] * o.addend_cstride + ch);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[i].x += ad[i].x; x[i].y += ad[i].y; x[i].z += ad[i].z; x[i].w += ad[i].w; }
     }
     if (o.y_bf16) {
 #pragma unroll

@@ -44,6 +44,9 @@ struct PairArgs {
     float* sumsq;
     const __nv_bfloat16* relu_mask;          // fused ReLU backward (see sfvos_conv_params)
     long long mask_cstride;
+    const void* addend;                      // y = act(...) + addend (see sfvos_conv_params)
+    long long addend_cstride;
+    int addend_bf16;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -256,6 +259,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 EpiOut eo;
                 eo.y = a.y; eo.y_cstride = a.y_cstride; eo.y_bf16 = a.y_bf16; eo.relu = a.relu; eo.accumulate = a.accumulate;
                 eo.relu_mask = a.relu_mask; eo.mask_cstride = a.mask_cstride;
+                eo.addend = a.addend; eo.addend_cstride = a.addend_cstride; eo.addend_bf16 = a.addend_bf16;
                 float* sum_dst = (do_stats || (a.relu_mask != nullptr && a.sum != nullptr)) ? s_sum : nullptr;
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     uint32_t v[32];
@@ -419,7 +423,9 @@ int sfvos_conv_pair_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     // its f32 dgrad 340 -> 299 us); bf16 outputs without statistics do not (mask-head conv 191 -> 203 us) - this kernel runs at the
     // shared-memory port's limit and the transpose tile adds 8 KB of traffic per 32-column block.
     const int es = env_int("SFVOS_EPI_STAGE", -1);
-    a.epi_stage = es < 0 ? (p->y_dtype != SFVOS_BF16) : (es != 0);
+    a.epi_stage = es < 0 ? (p->y_dtype != SFVOS_BF16 || p->addend != nullptr) : (es != 0);
+    a.addend = p->addend; a.addend_cstride = p->addend_cstride; a.addend_bf16 = (p->addend_dtype == SFVOS_BF16);
+    SF_CHECK(p->addend == nullptr || a.epi_stage, "conv_pair: addend needs the transposing epilogue (SFVOS_EPI_STAGE)");
     // Pipeline depth (measured, round 2, slow_conv1 fprop / slow_conv2 dgrad / slow_conv3 fprop at level 0, same box):
     // 3 A x 10 B stages 360 / 347 / 406 us, 2 x 6 353 / 335 / 395, 2 x 8 346 / 331 / 394, 2 x 16 361 / 344 / 406, 2 x 3 380 / 365 / 422.
     // Deeper prefetch does not help - the MMA thread's waits for weight stages are L2 -> SM BANDWIDTH (every pixel tile

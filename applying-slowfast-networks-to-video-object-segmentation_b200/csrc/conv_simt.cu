@@ -197,6 +197,7 @@ extern "C" int sfvos_conv_simt(const sfvos_conv_params* p, sfvos_stream stream_)
     SF_CHECK(p->C % 4 == 0 && p->x_cstride % 4 == 0 && p->N % 4 == 0, "conv_simt: C, x_cstride, N must be multiples of 4");
     SF_CHECK(p->sum == nullptr && p->sumsq == nullptr, "conv_simt: fused statistics are umma-only; call sfvos_channel_stats");
     SF_CHECK(!(p->accumulate && p->y_dtype != SFVOS_F32), "conv_simt: accumulate needs an f32 output");
+    SF_CHECK(p->addend == nullptr, "conv_simt: addend is umma-only (use accumulate)");
     int rc = sfvos_device_check();
     if (rc) return rc;
     SimtArgs a;

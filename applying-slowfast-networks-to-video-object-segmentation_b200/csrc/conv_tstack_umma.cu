@@ -45,6 +45,9 @@ struct TsArgs {
     const float* shift;
     float* sum;
     float* sumsq;
+    const void* addend;                          // y = act(...) + addend (see sfvos_conv_params)
+    long long addend_cstride;
+    int addend_bf16;
 };
 
 struct Item {
@@ -259,6 +262,7 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         EpiOut eo;
         eo.y = a.y; eo.y_cstride = a.y_cstride; eo.y_bf16 = a.y_bf16; eo.relu = a.relu; eo.accumulate = a.accumulate;
         eo.relu_mask = nullptr; eo.mask_cstride = 0;
+        eo.addend = a.addend; eo.addend_cstride = a.addend_cstride; eo.addend_bf16 = a.addend_bf16;
         int acc = 0;
         uint32_t acc_phase = 0;
         // BatchNorm statistics: in the transposed ownership of the epilogue (common.cuh) a lane sees 4 channels of 8 pixels per
@@ -409,7 +413,8 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
     // f32 outputs (raw conv outputs with statistics, data gradients, the read-modify-write lateral dgrads) always leave through
     // the transposing epilogue; bf16 outputs without statistics (eval-mode folded layers) store directly unless forced
-    a.stage_mode = (!a.y_bf16 || a.sum != nullptr || env_int("SFVOS_TSTACK_STAGE", 1) >= 3) ? 1 : 0;
+    a.addend = p->addend; a.addend_cstride = p->addend_cstride; a.addend_bf16 = (p->addend_dtype == SFVOS_BF16);
+    a.stage_mode = (!a.y_bf16 || a.sum != nullptr || a.addend != nullptr || env_int("SFVOS_TSTACK_STAGE", 1) >= 3) ? 1 : 0;
     SF_CHECK(p->B * p->To * p->H * p->W < (1LL << 31), "conv_tstack: too many output pixels");
 
     a.dbg = env_int("SFVOS_TSTACK_DBG", 0);

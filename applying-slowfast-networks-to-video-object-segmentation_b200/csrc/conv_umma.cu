@@ -52,6 +52,9 @@ struct ConvArgs {
     int OH, OW, oy_mul, oy_off, ox_mul, ox_off;
     const __nv_bfloat16* relu_mask;          // fused ReLU backward (see sfvos_conv_params)
     long long mask_cstride;
+    const void* addend;                      // y = act(...) + addend (see sfvos_conv_params)
+    long long addend_cstride;
+    int addend_bf16;
 };
 
 // BK = channels per K step: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle; Cin = 32 layers).
@@ -264,6 +267,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 EpiOut eo;
                 eo.y = a.y; eo.y_cstride = a.y_cstride; eo.y_bf16 = a.y_bf16; eo.relu = a.relu; eo.accumulate = a.accumulate;
                 eo.relu_mask = a.relu_mask; eo.mask_cstride = a.mask_cstride;
+                eo.addend = a.addend; eo.addend_cstride = a.addend_cstride; eo.addend_bf16 = a.addend_bf16;
                 // wide fc layers (several N chunks): bias / scale straight from global memory, indexed by absolute channel
                 const float* scp = !affine ? nullptr : (a.nchunks > 1 ? a.scale : s_scale);
                 const float* shp = !affine ? nullptr : (a.nchunks > 1 ? a.shift : s_shift);
@@ -436,6 +440,9 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     SF_CHECK(p->C % 8 == 0 && p->x_cstride % 8 == 0, "conv_umma: C and x_cstride must be multiples of 8");
     SF_CHECK(p->y_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0, "conv_umma: y must be 16-byte aligned with cstride %% 8 == 0");
     SF_CHECK(!(p->accumulate && p->y_dtype != SFVOS_F32), "conv_umma: accumulate needs an f32 output");
+    SF_CHECK(p->addend == nullptr || (!p->accumulate && p->addend_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(p->addend) & 15) == 0 &&
+                                      (p->addend_dtype == SFVOS_F32 || p->addend_dtype == SFVOS_BF16)),
+             "conv_umma: addend must be a 16-byte aligned f32 / bf16 tensor with cstride %% 8 == 0, and excludes accumulate");
     SF_CHECK((p->sum == nullptr) == (p->sumsq == nullptr) || p->relu_mask != nullptr, "conv_umma: sum and sumsq must be given together");
     SF_CHECK(p->B > 0 && p->To > 0 && p->H > 0 && p->W > 0 && p->T > 0, "conv_umma: empty tensor");
     if (p->relu_mask != nullptr) {
@@ -519,6 +526,8 @@ extern "C" int sfvos_conv_umma(const sfvos_conv_params* p, sfvos_stream stream_)
     a.y_cstride = p->y_cstride;
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
     a.relu_mask = reinterpret_cast<const __nv_bfloat16*>(p->relu_mask); a.mask_cstride = p->relu_mask_cstride;
+    a.addend = p->addend; a.addend_cstride = p->addend_cstride; a.addend_bf16 = (p->addend_dtype == SFVOS_BF16);
+    SF_CHECK(p->addend == nullptr || (a.epi_stage & 1), "conv_umma: addend needs the transposing epilogue (SFVOS_EPI_STAGE)");
     a.OH = (int)(p->OH ? p->OH : p->H); a.OW = (int)(p->OW ? p->OW : p->W);
     a.oy_mul = (int)(p->oy_mul ? p->oy_mul : 1); a.ox_mul = (int)(p->ox_mul ? p->ox_mul : 1);
     a.oy_off = (int)p->oy_off; a.ox_off = (int)p->ox_off;

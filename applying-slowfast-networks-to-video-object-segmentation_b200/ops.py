@@ -175,7 +175,7 @@ def unpack_wgrad(dw, grad, mode, tap=(0, 0)):
 
 
 def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shift=None, stats=None, accumulate=False,
-         x_strides=None, scatter=None, relu_mask=None, dbias=None):
+         x_strides=None, scatter=None, relu_mask=None, dbias=None, addend=None):
     """x: Act (input), y: Act (output, B*To*OH*OW pixels).  k=(kt,kh,kw), pad=(pt,ph,pw).
     stats: optional f32 [2,N] tensor receiving (sum, sumsq) of the raw accumulators (umma only)."""
     p = ConvParams()
@@ -199,6 +199,9 @@ def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shi
         p.relu_mask = relu_mask.ptr(); p.relu_mask_cstride = relu_mask.cstride
         if dbias is not None:
             p.sum = _p(dbias)
+    if addend is not None:          # y = act(...) + addend: an Act indexed like y (f32 or bf16); tensor-core path only
+        assert umma and not accumulate and addend.npix == y.npix
+        p.addend = addend.ptr(); p.addend_dtype = dt(addend.buf); p.addend_cstride = addend.cstride
     # algorithmic FLOPs: no zero-padded taps.  fprop: To = T - kt + 1 output frames; a data-gradient launch
     # (full temporal padding, To = the forward INPUT frames) does the forward layer's work, one product per forward output
     # frame and tap, so it counts x.T (= the forward output frames) -- min() covers both

@@ -97,6 +97,14 @@ typedef struct sfvos_conv_params {
      * relu_bwd pass between two 3x3 convolutions of MaskRCNNHeads (TV mask_rcnn.py:284-296). */
     const void* relu_mask;
     int64_t relu_mask_cstride;
+    /* optional addend (umma): y = act(...) + addend[pixel, n], an f32 or bf16 tensor indexed like y (cstride in elements).
+     * accumulate = 1 is the special case addend = y (f32).  Lets the second of the two gradient paths into the fast
+     * pathway (a lateral dgrad on top of the fast convolution's dgrad, code/helpers/model.py:128-131,140-143) read the f32
+     * partial sum and store the total ONCE, in bf16, for the BatchNorm backward that consumes it. */
+    const void* addend;
+    int32_t addend_dtype;     /* SFVOS_F32 | SFVOS_BF16 */
+    int32_t reserved2;
+    int64_t addend_cstride;
 } sfvos_conv_params;
 
 /* tcgen05/TMEM/TMA bf16 kernel (the product path). */

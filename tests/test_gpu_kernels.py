@@ -144,6 +144,18 @@ def test_conv_dgrad(cin, cout, kt, khw, T, umma):
     dx.buf.fill_(0.25)
     ops.conv(dya, wd, cp, cin, (kt, khw, khw), (kt - 1, khw - 1 - pad, khw - 1 - pad), T, dx, umma=umma, accumulate=True)
     assert _err(_read_act(dx), dx_ref + 0.25) < 2e-5
+    if umma:
+        # addend: the total of two gradient paths stored once, in bf16 or f32, from an f32 or bf16 partial sum that is left
+        # untouched (sfvos_conv_params.addend: the lateral dgrad on top of the fast convolution's dgrad)
+        part = torch.randn(B, T, H, W, cin, generator=g).to(DEV)
+        for part_dtype in (torch.float32, torch.bfloat16):
+            pa = _mk_act(ops, part, part_dtype)
+            before = pa.buf.clone()
+            for out_dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 4e-3)):     # bf16: one rounding of the total (2^-9)
+                tot = ops.Act.empty(B, T, H, W, cin, out_dtype, DEV)
+                ops.conv(dya, wd, cp, cin, (kt, khw, khw), (kt - 1, khw - 1 - pad, khw - 1 - pad), T, tot, umma=True, addend=pa)
+                assert _err(_read_act(tot), dx_ref + _read_act(pa).float()) < tol
+            assert torch.equal(pa.buf, before)
 
 
 @pytest.mark.parametrize("umma", [True, False], ids=["umma", "simt"])
