@@ -53,6 +53,7 @@ _SIGS = {
     "sfvos_version": [],
     "sfvos_device_check": [],
     "sfvos_tma_overlap_supported": [vp],
+    "sfvos_probe_l2": [i32, vp, i64, i32, vp, vp],
     "sfvos_conv_umma": [ctypes.POINTER(ConvParams), vp],
     "sfvos_conv_simt": [ctypes.POINTER(ConvParams), vp],
     "sfvos_wgrad_umma": [ctypes.POINTER(WgradParams), vp],

@@ -3,6 +3,8 @@
 // backward, and the sigmoid/select of maskrcnn_inference (roi_heads.py:56-82).
 // N = n_cls (2) is far too narrow for a tensor-core tile, so these are warp-per-pixel dot products over the
 // contiguous channel axis (16-byte vector loads, shuffle reductions): HBM-bound on reading x once.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -230,6 +232,105 @@ mask_logits_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, co
     }
 }
 
+// The product path's instance of the kernel above (bf16, C = 256: one 8-channel group per lane, RELU, <= 2 classes), with the
+// memory-level parallelism the general kernel lacks.  ncu / timeline, round 2: the general kernel ran at 2.1 TB/s (33 % of the
+// HBM roofline): 119 registers -> 2 CTAs = 16 warps per SM, each with ONE 512-byte row in flight (+ one prefetched), i.e. a
+// latency chain of 98 trips per warp.  Here a warp loads FOUR pixels' rows and logit gradients per trip before it touches
+// any of them, and 3 CTAs fit an SM.  Same pixel -> warp assignment and accumulation order as the general kernel, so the
+// results are bit-identical to it.
+template <int NCLS>
+__global__ void __launch_bounds__(256, 3)
+mask_logits_relu_bwd_c256_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ glogits,
+                                 __nv_bfloat16* dx, float* dw, float* db, float* dbias_x, int S, int pixel_order) {
+    constexpr int C = 256, UNR = 4;
+    extern __shared__ float s_dw[];          // [8 warps][NCLS][C] + [8 warps][C]
+    __shared__ float s_db[8][NCLS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long k = blockIdx.x;
+    const int ss = S * S;
+    float* s_dbx = s_dw + 8 * NCLS * C;
+    const __nv_bfloat16* xk = x + k * ss * C + lane * 8;
+    __nv_bfloat16* dxk = dx + k * ss * C + lane * 8;
+    const float* gk = glogits + k * NCLS * ss;
+    float wv[NCLS][8], dwacc[NCLS][8], dbx[8], dbacc[NCLS];
+#pragma unroll
+    for (int q = 0; q < NCLS; ++q) {
+        ld8(w + q * C + lane * 8, wv[q]);
+        dbacc[q] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dwacc[q][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dbx[j] = 0.f;
+    const int n_it = warp < ss ? (ss - warp + 7) / 8 : 0;             // this warp's pixels: warp, warp + 8, ...
+    for (int i0 = 0; i0 < n_it; i0 += UNR) {
+        uint4 xv[UNR];
+        float g[UNR][NCLS];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int p = warp + 8 * (i0 + u);
+            xv[u] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int q = 0; q < NCLS; ++q) g[u][q] = 0.f;
+            if (i0 + u < n_it) {
+                xv[u] = __ldg(reinterpret_cast<const uint4*>(xk + (long long)p * C));
+                const long long sp = row_to_spatial(p, S, pixel_order);
+#pragma unroll
+                for (int q = 0; q < NCLS; ++q) g[u][q] = __ldg(gk + (long long)q * ss + sp);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (i0 + u < n_it) {
+                const int p = warp + 8 * (i0 + u);
+                const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                float v[8], o[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(xw[i] << 16); v[2 * i + 1] = __uint_as_float(xw[i] & 0xffff0000u); }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+                for (int q = 0; q < NCLS; ++q) {
+                    const float gq = g[u][q];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { o[j] = fmaf(gq, wv[q][j], o[j]); dwacc[q][j] = fmaf(gq, v[j], dwacc[q][j]); }
+                    if (lane == 0) dbacc[q] += gq;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = v[j] > 0.f ? o[j] : 0.f;
+                    dbx[j] += o[j];
+                }
+                st8(dxk + (long long)p * C, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NCLS; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_dw[(warp * NCLS + q) * C + lane * 8 + j] = dwacc[q][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_dbx[warp * C + lane * 8 + j] = dbx[j];
+    if (lane == 0)
+        for (int q = 0; q < NCLS; ++q) s_db[warp][q] = dbacc[q];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NCLS * C; i += blockDim.x) {
+        float sacc = 0.f;
+        for (int wi = 0; wi < 8; ++wi) sacc += s_dw[wi * NCLS * C + i];
+        atomicAdd(dw + i, sacc);
+    }
+    if (threadIdx.x < NCLS) {
+        float sacc = 0.f;
+        for (int wi = 0; wi < 8; ++wi) sacc += s_db[wi][threadIdx.x];
+        atomicAdd(db + threadIdx.x, sacc);
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float sacc = 0.f;
+        for (int wi = 0; wi < 8; ++wi) sacc += s_dbx[wi * C + i];
+        atomicAdd(dbias_x + i, sacc);
+    }
+}
+
 // glogits[k, cls, p] = (cls == labels[k]) ? gloss * (sigmoid(z) - t) / (K*S*S) : 0
 __global__ void mask_bce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                     const float* __restrict__ targets, const float* __restrict__ gloss, float* glogits,
@@ -315,6 +416,15 @@ extern "C" int sfvos_mask_logits_relu_bwd(const void* x, int32_t x_dtype, const 
     if (K == 0) return SFVOS_OK;
     const size_t sm = (size_t)8 * (n_cls + 1) * C * sizeof(float);
     SF_CHECK(sm <= 48 * 1024, "mask_logits_relu_bwd: n_cls*C too large");
+    if (x_dtype == SFVOS_BF16 && C == 256 && n_cls <= 2 && getenv("SFVOS_MASK_LOGITS_GENERIC") == nullptr) {
+        using bf = __nv_bfloat16;
+        if (n_cls == 2)
+            mask_logits_relu_bwd_c256_kernel<2><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const bf*>(x), w, glogits, reinterpret_cast<bf*>(dx), dw, db, dbias_x, (int)S, pixel_order);
+        else
+            mask_logits_relu_bwd_c256_kernel<1><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const bf*>(x), w, glogits, reinterpret_cast<bf*>(dx), dw, db, dbias_x, (int)S, pixel_order);
+        SF_LAUNCH_CHECK();
+        return SFVOS_OK;
+    }
     if (x_dtype == SFVOS_BF16)
         mask_logits_bwd_kernel<__nv_bfloat16, __nv_bfloat16, true><<<(int)K, 256, sm, CS(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, glogits, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, dbias_x, K, (int)S, (int)C, n_cls, pixel_order);
     else

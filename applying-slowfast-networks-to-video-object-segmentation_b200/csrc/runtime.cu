@@ -118,3 +118,40 @@ extern "C" int sfvos_tma_overlap_supported(const void* dev_ptr) {
     cached = sfvos_make_tmap(&m, dev_ptr, 5, dims, strides, box, 128) == SFVOS_OK ? 1 : 0;
     return cached;
 }
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Measurement probes (tools/bench_l2.py): the denominators of the kernels that are bound by the L2 rather than by HBM.
+//   kind 0: streaming 16-byte loads (grid-stride, summed)  -> L2 -> SM read bandwidth when the buffer fits the L2
+//   kind 1: streaming red.global.add.v4.f32                 -> vector-reduction throughput of the L2 (ROIAlign backward)
+// Every pass touches each 16-byte vector of the buffer once; `iters` passes per launch.
+// ----------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) probe_l2_kernel(int kind, float4* buf, long long nvec, int iters, float* sink) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float acc = 0.f;
+    for (int it = 0; it < iters; ++it)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+            if (kind == 0) {
+                const float4 v = __ldcg(buf + i);
+                acc += v.x + v.y + v.z + v.w;
+            } else {
+                atomicAdd(buf + i, make_float4(1.f, 1.f, 1.f, 1.f));
+            }
+        }
+    if (kind == 0 && acc == 123.456f) *sink = acc;          // keeps the loads alive
+}
+}  // namespace
+
+extern "C" int sfvos_probe_l2(int32_t kind, void* buf, int64_t nbytes, int32_t iters, float* sink, sfvos_stream stream) {
+    SF_CHECK(kind == 0 || kind == 1, "probe_l2: kind must be 0 (loads) or 1 (vector reductions)");
+    SF_CHECK(buf != nullptr && sink != nullptr && nbytes >= 16 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0, "probe_l2: bad buffer");
+    int rc = sfvos_device_check();
+    if (rc) return rc;
+    const long long nvec = nbytes / 16;
+    long long blocks = (nvec + 255) / 256;
+    const long long cap = (long long)sfvos_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    probe_l2_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(kind, reinterpret_cast<float4*>(buf), nvec, iters, sink);
+    SF_LAUNCH_CHECK();
+    return SFVOS_OK;
+}

@@ -397,7 +397,7 @@ def run_ours(args, rank, local_rank, world):
     # region.  What crosses PCIe is the sequence's features, every frame ONCE (the windows are views; the reference's
     # features_cache does the same on its side, model.py:191-227), in the feature dtype.  The copies are software-pipelined
     # like a data loader: step i+1's sequence goes into the other device slot on a copy stream while step i computes.
-    e2e_steps = max(2, min(args.steps, 6))
+    e2e_steps = max(2, min(args.steps, 20))      # the same K steps as the resident-input region (the first step's whole-sequence copy is not overlapped)
     host = wl.synthetic_sequence(n_frames, seed=1234 + 1000 * rank, device="cpu", dtype=feat_dtype, pin=True)
     ns = len(slots)
     copy_stream = torch.cuda.Stream(device=dev)

@@ -49,6 +49,11 @@ const char* sfvos_last_kernel(void);
  * once instead of once per window.  dev_ptr: any 16-byte aligned device pointer (not dereferenced). */
 int sfvos_tma_overlap_supported(const void* dev_ptr);
 
+/* Measurement probe (tools/bench_l2.py), not part of the path: `iters` passes over buf touching every 16-byte vector once,
+ * kind 0 = streaming loads (L2 -> SM read bandwidth when buf fits the L2), kind 1 = red.global.add.v4.f32 (the L2's
+ * vector-reduction throughput, the denominator of the ROIAlign backward).  sink: one f32 on the device. */
+int sfvos_probe_l2(int32_t kind, void* buf, int64_t nbytes, int32_t iters, float* sink, sfvos_stream stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution (fprop and dgrad share one kernel).
  * Replaces aten::conv3d / cudnn_convolution reached from nn.Conv3d at code/helpers/model.py:72-76,83-90

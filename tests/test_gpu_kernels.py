@@ -226,6 +226,26 @@ def test_bn_pieces_match_torch_batchnorm():
     assert _err(_read_act(y), ye.permute(0, 2, 3, 4, 1)) < 1e-5
 
 
+@pytest.mark.parametrize("C,H,W", [(256, 12, 22), (64, 8, 16), (128, 40, 23), (256, 12, 21), (72, 5, 8)])
+def test_layout_bf16_source(C, H, W):
+    """bf16 [frames,C,H,W] -> bf16 channels-last (the product path's layout pass): a pure transposition, bit-exact.  H*W % 8 == 0
+    and C % 64 == 0 take the byte-permute kernel (full, partial and single tiles); the others the general kernel."""
+    ops = _ops()
+    F_ = 3
+    x = torch.randn(F_, C, H, W, device=DEV).bfloat16()
+    act = ops.Act.empty(1, F_, H, W, C, torch.bfloat16, DEV)
+    ops.nchw_to_nhwc(x, act)
+    assert torch.equal(_read_act(act)[0], x.permute(0, 2, 3, 1))
+    # into a channel slice of a wider channels-last buffer (cstride > C), frames at an offset
+    cs = C + 64
+    buf = torch.zeros((F_ + 1) * H * W * cs, dtype=torch.bfloat16, device=DEV)
+    act2 = ops.Act(buf, 1, F_ + 1, H, W, C, cs, 32)
+    ops.nchw_to_nhwc(x, act2, frame_off=1)
+    got = buf.view(F_ + 1, H, W, cs)
+    assert torch.equal(got[1:, :, :, 32:32 + C], x.permute(0, 2, 3, 1))
+    assert int(got[0].abs().sum()) == 0 and int(got[1:, :, :, :32].abs().sum()) == 0 and int(got[1:, :, :, 32 + C:].abs().sum()) == 0
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layout_roundtrip(dtype):
     ops = _ops()

@@ -17,6 +17,7 @@ from conftest import GOLDEN, report
 from oracle import roi_oracle as ro
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda"
 
 
 def _nerr(a, b):
@@ -248,3 +249,46 @@ def test_roi_heads_train_and_eval_match_torchvision(precision):
         assert torch.equal(d_ref[0]["labels"], d_our[0]["labels"])
         assert _nerr(d_our[0]["boxes"], d_ref[0]["boxes"]) < 1e-4
         assert _nerr(d_our[0]["masks"], d_ref[0]["masks"]) < 1e-3
+
+@pytest.mark.parametrize("n_cls,pixel_order", [(2, 1), (2, 0), (1, 1)])
+def test_mask_logits_relu_bwd_fast_path_equals_the_general_kernel(n_cls, pixel_order, monkeypatch):
+    """bf16 / C = 256 / <= 2 classes runs a kernel with four rows in flight per warp (sfvos_mask_logits_relu_bwd); it keeps the
+    general kernel's pixel assignment and accumulation order, so dx must agree bit for bit (the reduced quantities up to the order of the CTAs' atomics) - and with a torch restatement of
+    d/dx [logits = W relu-output + b] followed by the ReLU backward (TV mask_rcnn.py:342-344)."""
+    from sfvos_b200 import ops
+    from sfvos_b200._lib import call
+    K, S, C = 5, 28, 256
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(K, S * S, C, generator=g).relu().bfloat16().to(DEV)            # rows in kernel order
+    w = (torch.randn(n_cls, C, generator=g) / 16).to(DEV)
+    gl = torch.randn(K, n_cls, S, S, generator=g).to(DEV)
+    outs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("SFVOS_MASK_LOGITS_GENERIC", "1")
+        dx = torch.empty_like(x)
+        dw, db, dbx = torch.zeros(n_cls, C, device=DEV), torch.zeros(n_cls, device=DEV), torch.zeros(C, device=DEV)
+        call("sfvos_mask_logits_relu_bwd", ops._p(x), ops.BF16, ops._p(w), ops._p(gl), ops._p(dx), ops.BF16, ops._p(dw), ops._p(db),
+             ops._p(dbx), K, S, C, n_cls, pixel_order, ops.stream())
+        torch.cuda.synchronize()
+        outs.append((dx, dw, db, dbx))
+    assert torch.equal(outs[0][0], outs[1][0])                    # dx: same arithmetic per element
+    for a, b in zip(outs[0][1:], outs[1][1:]):                    # per-CTA partial sums are equal; the CTAs' atomics land in any order
+        assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item() + 1e-7
+    # torch reference (rows -> spatial order for pixel_order 1: row (h*(S/2)+w)*4 + 2i + j = pixel (2h+i, 2w+j))
+    if pixel_order:
+        r = torch.arange(S * S, device=DEV)
+        tap, lw = r & 3, r >> 2
+        h, ww = lw // (S // 2), lw % (S // 2)
+        sp = (2 * h + (tap >> 1)) * S + 2 * ww + (tap & 1)
+    else:
+        sp = torch.arange(S * S, device=DEV)
+    g_rows = gl.reshape(K, n_cls, S * S)[:, :, sp]                                   # [K, cls, row]
+    xf = x.float()
+    dx_ref = torch.einsum("kcr,cd->krd", g_rows, w) * (xf > 0)
+    dw_ref = torch.einsum("kcr,krd->cd", g_rows, xf)
+    dx, dw, db, dbx = outs[0]
+    assert (dx.float() - dx_ref).abs().max().item() <= 4e-3 * dx_ref.abs().max().item()          # one bf16 rounding
+    assert (dw - dw_ref).abs().max().item() <= 1e-4 * dw_ref.abs().max().item()
+    assert (db - g_rows.sum((0, 2))).abs().max().item() <= 1e-4 * g_rows.sum((0, 2)).abs().max().item() + 1e-5
+    assert (dbx - dx_ref.sum((0, 1))).abs().max().item() <= 1e-3 * dx_ref.sum((0, 1)).abs().max().item()
