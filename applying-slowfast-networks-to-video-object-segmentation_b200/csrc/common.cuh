@@ -322,10 +322,29 @@ __device__ __forceinline__ void epi_colsum_flush(const float (&s)[4], const floa
         atomicAdd(dst + ch + (up8 ? 2 : 0) + 1, f[1]);
     }
 }
-// Per-channel affine / ReLU and the store (bf16, f32 or f32 read-modify-write).  scale / shift: nullable, indexed by
-// absolute channel (shared or global memory, 16-byte aligned at ch).
+// Raw loads of the addend rows (EpiOut.addend), kept apart from their use so that all 8 are in flight at once - and so that a
+// kernel can issue them BEFORE it waits for the accumulators (with the bf16 unpacking next to its load the compiler
+// serialised the 8 loads: lateral dgrad 177 us with an f32 addend, 418 us with a bf16 one).
+__device__ __forceinline__ void epi_addend_load(uint4 (&ad)[8], const EpiRows& rows, int ch, const EpiOut& o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ad[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (o.addend != nullptr && rows.pix[i] >= 0) {
+            if (o.addend_bf16) {
+                const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(o.addend) +
+                                                                (long long)rows.pix[i] * o.addend_cstride + ch);
+                ad[i].x = u.x; ad[i].y = u.y;
+            } else {
+                ad[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(o.addend) +
+                                                        (long long)rows.pix[i] * o.addend_cstride + ch);
+            }
+        }
+    }
+}
+// Per-channel affine / ReLU, the addend (ad: epi_addend_load) and the store (bf16, f32 or f32 read-modify-write).  scale / shift:
+// nullable, indexed by absolute channel (shared or global memory, 16-byte aligned at ch).
 __device__ __forceinline__ void epi_store(float4 (&x)[8], const EpiRows& rows, int ch, const float* scale, const float* shift,
-                                          const EpiOut& o) {
+                                          const EpiOut& o, const uint4 (&ad)[8]) {
     if (scale != nullptr || shift != nullptr) {
         const float4 sc = scale ? *reinterpret_cast<const float4*>(scale + ch) : make_float4(1.f, 1.f, 1.f, 1.f);
         const float4 sh = shift ? *reinterpret_cast<const float4*>(shift + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -342,24 +361,16 @@ __device__ __forceinline__ void epi_store(float4 (&x)[8], const EpiRows& rows, i
         }
     }
     if (o.addend != nullptr) {
-        float4 ad[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {                    // all reads in flight at once
-            ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rows.pix[i] >= 0) {
-                if (o.addend_bf16) {
-                    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(o.addend) +
-                                                                    (long long)rows.pix[i] * o.addend_cstride + ch);
-                    ad[i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
-                                        __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
-                } else {
-                    ad[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.addend) +
-                                                             (long long)rows.pix[i] * o.addend_cstride + ch);
-                }
+        for (int i = 0; i < 8; ++i) {
+            if (o.addend_bf16) {
+                x[i].x += __uint_as_float(ad[i].x << 16); x[i].y += __uint_as_float(ad[i].x & 0xffff0000u);
+                x[i].z += __uint_as_float(ad[i].y << 16); x[i].w += __uint_as_float(ad[i].y & 0xffff0000u);
+            } else {
+                x[i].x += __uint_as_float(ad[i].x); x[i].y += __uint_as_float(ad[i].y);
+                x[i].z += __uint_as_float(ad[i].z); x[i].w += __uint_as_float(ad[i].w);
             }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { x[i].x += ad[i].x; x[i].y += ad[i].y; x[i].z += ad[i].z; x[i].w += ad[i].w; }
     }
     if (o.y_bf16) {
 #pragma unroll
@@ -396,14 +407,16 @@ __device__ __forceinline__ void epi_block(float* stage, const uint32_t (&v)[32],
                                           const float* scale, const float* shift, const EpiOut& o, float* sum_dst,
                                           float* sq_dst) {
     float4 x[8];
-    epi_transpose(stage, v, lane, x);
+    uint4 ad[8];
     const int ch = col + 4 * (lane & 7);
+    epi_transpose(stage, v, lane, x);
+    epi_addend_load(ad, rows, ch, o);
     if (o.relu_mask != nullptr) epi_relu_mask(x, rows, o, ch);
     if (sum_dst != nullptr) {
         float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
         epi_colsum(x, rows, s, q);
         epi_colsum_flush(s, q, lane, sum_dst, sq_dst, ch);
     }
-    epi_store(x, rows, ch, scale, shift, o);
+    epi_store(x, rows, ch, scale, shift, o, ad);
 }
 #endif  // __CUDACC__

@@ -280,17 +280,20 @@ conv_tstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * a.Fg * NC;
             for (int t = it.t0 + par; t < (a.dbg & 1 ? it.t0 : it.t1); t += 2) {
+                EpiRows rt;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rt.pix[i] = rows0.pix[i] >= 0 ? rows0.pix[i] + (t - it.t0) * (int)frame_pix : -1;
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + (it.t1 - 1 - t) * NC, v);
                 tmem_ld_wait();
                 if (staged) {
-                    EpiRows rt;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rt.pix[i] = rows0.pix[i] >= 0 ? rows0.pix[i] + (t - it.t0) * (int)frame_pix : -1;
                     float4 x[8];
                     epi_transpose(stage, v, lane, x);
                     if (do_stats) epi_colsum(x, rt, cs, cq);
-                    epi_store(x, rt, 4 * (lane & 7), affine ? s_scale : nullptr, affine ? s_shift : nullptr, eo);
+                    // (issuing the addend loads before the TMEM load costs 32 more live registers: spills, 94 -> 112 us)
+                    uint4 ad[8];
+                    epi_addend_load(ad, rt, 4 * (lane & 7), eo);
+                    epi_store(x, rt, 4 * (lane & 7), affine ? s_scale : nullptr, affine ? s_shift : nullptr, eo, ad);
                 } else if (valid) {
                     // bf16 outputs without statistics (eval-mode folded layers): a thread owns one pixel's 64 bytes
                     const long long pix = pix0 + (t - it.t0) * frame_pix;
@@ -411,10 +414,11 @@ int sfvos_conv_tstack_launch(const sfvos_conv_params* p, cudaStream_t stream) {
     a.y = p->y; a.y_bf16 = (p->y_dtype == SFVOS_BF16); a.relu = p->relu; a.accumulate = p->accumulate;
     a.y_cstride = p->y_cstride;
     a.scale = p->scale; a.shift = p->shift; a.sum = p->sum; a.sumsq = p->sumsq;
-    // f32 outputs (raw conv outputs with statistics, data gradients, the read-modify-write lateral dgrads) always leave through
-    // the transposing epilogue; bf16 outputs without statistics (eval-mode folded layers) store directly unless forced
+    // f32 outputs, statistics and addends leave through the transposing epilogue; bf16 outputs without them (eval-mode folded
+    // layers, bf16 partial gradients) store row-per-lane - measured faster there (fast_conv2 dgrad 138 vs 147 us, fast_conv3
+    // 66 vs 74); SFVOS_TSTACK_STAGE=1 forces the transpose for A/B measurements
     a.addend = p->addend; a.addend_cstride = p->addend_cstride; a.addend_bf16 = (p->addend_dtype == SFVOS_BF16);
-    a.stage_mode = (!a.y_bf16 || a.sum != nullptr || a.addend != nullptr || env_int("SFVOS_TSTACK_STAGE", 1) >= 3) ? 1 : 0;
+    a.stage_mode = (!a.y_bf16 || a.sum != nullptr || a.addend != nullptr || env_int("SFVOS_TSTACK_STAGE", 0) >= 1) ? 1 : 0;
     SF_CHECK(p->B * p->To * p->H * p->W < (1LL << 31), "conv_tstack: too many output pixels");
 
     a.dbg = env_int("SFVOS_TSTACK_DBG", 0);

@@ -618,7 +618,7 @@ def _level_backward(mod, saved, g_out, need_input_grad, bank, fast_stream=None):
         Tensor-core path: the lateral's epilogue reads the f32 partial sum and stores the total ONCE in the activation
         dtype for the BatchNorm backward that consumes it (instead of a read-modify-write of the f32 buffer followed by two
         f32 reads): 6 of 20 bytes per element less.  Validation mode: f32 accumulate, as before."""
-        if mod._umma and gdt != torch.float32 and os.environ.get("SFVOS_LATERAL_ADDEND", "1") != "0":
+        if use_addend:
             return _layer_backward(mod, spec, dy, x_in, saved, bank, dx_dtype=gdt, dx_addend=d_part)
         _layer_backward(mod, spec, dy, x_in, saved, bank, dx=d_part, dx_accumulate=True)
         return d_part
@@ -628,12 +628,16 @@ def _level_backward(mod, saved, g_out, need_input_grad, bank, fast_stream=None):
     gdt = mod._act_dtype if os.environ.get("SFVOS_BF16_DGRAD", "1") != "0" else torch.float32
     if fast_stream is not None:
         fast_stream.wait_stream(main)                          # g_out is ready
-    d_f2 = fast(lambda: _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, bank))
+    # the fast convolutions' dgrads are PARTIAL sums that the lateral's epilogue reads once (lateral_sum): store them in the
+    # activation dtype as well (what bf16 autocast training does with every activation gradient); SFVOS_FAST_PARTIAL_BF16=0: f32
+    use_addend = mod._umma and gdt != torch.float32 and os.environ.get("SFVOS_LATERAL_ADDEND", "1") != "0"
+    pdt = gdt if use_addend and os.environ.get("SFVOS_FAST_PARTIAL_BF16", "1") != "0" else torch.float32
+    d_f2 = fast(lambda: _layer_backward(mod, sp["fast_conv3"], g_out.slice(224, 32), a["f2"], saved, bank, dx_dtype=pdt))
     d_s2 = _layer_backward(mod, sp["slow_conv3"], g_out.slice(0, 224), a["s2"], saved, bank, dx_dtype=gdt)
     if fast_stream is not None:
         fast_stream.wait_stream(main)                          # lateral 2 reads d_s2[192:]
     d_f1 = fast(lambda: _layer_backward(mod, sp["fast_conv2"], lateral_sum(sp["conv_f2s2"], d_s2.slice(192, 64), a["f2"], d_f2),
-                                        a["f1"], saved, bank))
+                                        a["f1"], saved, bank, dx_dtype=pdt))
     d_s1 = _layer_backward(mod, sp["slow_conv2"], d_s2.slice(0, 192), a["s1"], saved, bank, dx_dtype=gdt)
     if fast_stream is not None:
         fast_stream.wait_stream(main)                          # lateral 1 reads d_s1[192:]

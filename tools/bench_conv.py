@@ -109,8 +109,12 @@ def main():
             dy = ops.Act(torch.randn(B * To * H * W * cout, device=dev).bfloat16(), B, To, H, W, cout)
             cp = 32 if cout <= 32 else (cout + 63) // 64 * 64
             wd = ops.pack_weights(w, 1, ops.BF16, cp)
-            dx = ops.Act.empty(B, T, H, W, cin, torch.float32, dev)
-            fn = lambda: ops.conv(dy, wd, cp, cin, (kt, khw, khw), (kt - 1, khw - 1 - pad, khw - 1 - pad), T, dx, umma=True)
+            dx = ops.Act.empty(B, T, H, W, cin, torch.bfloat16 if os.environ.get("BENCH_DX_BF16") else torch.float32, dev)
+            addend = None
+            if os.environ.get("BENCH_ADDEND"):          # f32 | bf16: y = dgrad + addend (the lateral on top of the fast conv's partial gradient)
+                adt = torch.bfloat16 if os.environ["BENCH_ADDEND"] == "bf16" else torch.float32
+                addend = ops.Act(torch.randn(B * T * H * W * cin, device=dev).to(adt), B, T, H, W, cin)
+            fn = lambda: ops.conv(dy, wd, cp, cin, (kt, khw, khw), (kt - 1, khw - 1 - pad, khw - 1 - pad), T, dx, umma=True, addend=addend)
         else:
             x = ops.Act(torch.randn(B * T * H * W * cin, device=dev).bfloat16(), B, T, H, W, cin)
             dy = ops.Act(torch.randn(B * To * H * W * cout, device=dev).bfloat16(), B, To, H, W, cout)
