@@ -346,7 +346,7 @@ def run_ours(args, rank, local_rank, world):
     dom = max(tensor, key=lambda k: tensor[k][1]) if tensor else None          # the kernel with the largest share of the step
     dom_f, dom_ms, dom_n = tensor[dom] if dom else (0.0, 0.0, 0)
     achieved = dom_f / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
-    traffic, traffic_src, dram = None, None, {}
+    traffic, traffic_src, dram, tj = None, None, {}, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
@@ -368,6 +368,30 @@ def run_ours(args, rank, local_rank, world):
     # this ROI set (dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json <- profiles/ncu_kernels_r2.md), time = this
     # run's CUDA events.  The SURVEY 8(d) byte model (unique footprint per ROI, no credit for cache hits) is kept beside it: it
     # over-credits by 2-3x because the footprints of neighbouring ROIs and bins overlap in L1 / L2.
+    # The backward kernels are bound by the L2's vector-reduction throughput, not by HBM: their work is red.global.add.v4.f32
+    # into f32 maps, and ncu shows 83-89 % of what the L2 delivers on a streaming reduction probe.  So next to the DRAM figure
+    # every launch kind carries an "l2" record: bytes = ncu's L2 sector counts for that launch (reads for the forward gather,
+    # reductions for the backward scatter; profiles/traffic.json), peak = this GPU's L2 measured LIVE with sfvos_probe_l2 on an
+    # L2-resident 48 MB buffer (16-byte loads / red.v4.f32), time = this run's CUDA events.
+    l2_peak, l2_bytes = {}, {}
+    try:
+        from sfvos_b200._lib import call as _call
+        pb = torch.zeros((48 << 20) // 4, dtype=torch.float32, device=dev)
+        sink = torch.zeros(1, device=dev)
+        for kind, key in ((0, "read"), (1, "red")):
+            for _ in range(2):
+                _call("sfvos_probe_l2", kind, ops._p(pb), 48 << 20, 20, ops._p(sink), ops.stream())
+            ts = []
+            for _ in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); _call("sfvos_probe_l2", kind, ops._p(pb), 48 << 20, 20, ops._p(sink), ops.stream()); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            l2_peak[key] = (48 << 20) * 20 / (sorted(ts)[3] * 1e-3) / 1e9
+        del pb
+        l2_bytes = tj.get("roi_align_l2", {})
+    except Exception as exc:
+        print(f"bench: L2 probe skipped ({exc.__class__.__name__}: {exc})", file=sys.stderr)
     roi = {}
     for k, v in fam.items():
         if k.startswith("roi_align_") and v[1]:
@@ -376,6 +400,12 @@ def run_ours(args, rank, local_rank, world):
             if k in dram:
                 rec.update({"bound": "hbm", "achieved": round(dram[k] / us / 1e3, 1), "peak": peaks["hbm"], "unit": "GB/s",
                             "frac": round(dram[k] / us / 1e3 / peaks["hbm"], 4), "ncu_dram_bytes_per_launch": dram[k]})
+            if k in l2_bytes and l2_bytes[k]["kind"] in l2_peak:
+                kind = l2_bytes[k]["kind"]
+                gbs = l2_bytes[k]["bytes"] / us / 1e3
+                rec["l2"] = {"bound": "l2 " + ("vector reductions (red.global.add.v4.f32)" if kind == "red" else "-> SM reads"),
+                             "achieved": round(gbs, 1), "peak": round(l2_peak[kind], 1), "unit": "GB/s", "frac": round(gbs / l2_peak[kind], 4),
+                             "ncu_l2_bytes_per_launch": l2_bytes[k]["bytes"], "peak_source": "sfvos_probe_l2, 48 MB L2-resident buffer, this run"}
             roi[k] = rec
     for tag in ("fwd", "bwd", ""):
         ks = [k for k in fam if k.startswith("roi_align_" + tag) and fam[k][1]]
