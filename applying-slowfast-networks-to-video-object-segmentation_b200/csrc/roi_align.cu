@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256, 2) roi_align_fwd2_kernel(const RoiArgs a)
 constexpr int MAX_TAPS = 16;
 
 template <typename FT, bool NCHW>
-__global__ void __launch_bounds__(256, 2) roi_align_fwd3_kernel(const RoiArgs a) {
+__global__ void __launch_bounds__(256, NCHW ? 3 : 4) roi_align_fwd3_kernel(const RoiArgs a) {
     extern __shared__ float s_dyn[];                      // [NCHW: C * P*P floats] [P*P * 16 (offset, weight) pairs] [P*P counts]
     __shared__ RoiPlan plan;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -385,14 +385,9 @@ __global__ void __launch_bounds__(256, 2) roi_align_fwd3_kernel(const RoiArgs a)
             // all of the bin's loads in flight before the first FMA.  The first 9 slots (the typical 3 x 3 neighbourhood) are
             // loaded unconditionally -- a padding slot reads cell 0 and its value is discarded below, so NaNs cannot leak in --
             // which lets the compiler issue them back to back; slots 9..15 (bins wider than 2 cells) are predicated.
-            float4 v[MAX_TAPS];
+            float4 v[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) v[t] = ld4(base + (long long)tp[t].x * a.cstride + c);
-#pragma unroll
-            for (int t = 9; t < MAX_TAPS; ++t) {
-                v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t < n) v[t] = ld4(base + (long long)tp[t].x * a.cstride + c);
-            }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
@@ -402,12 +397,20 @@ __global__ void __launch_bounds__(256, 2) roi_align_fwd3_kernel(const RoiArgs a)
                 acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
             }
             if (n > 9) {
+                // bins wider than 2 cells per axis (rare): the remaining slots in a second round of loads, same accumulation
+                // order.  Keeping only 9 vectors live (instead of all 16) is what lets three CTAs share an SM.
+                float4 u[MAX_TAPS - 9];
+#pragma unroll
+                for (int t = 9; t < MAX_TAPS; ++t) {
+                    u[t - 9] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t < n) u[t - 9] = ld4(base + (long long)tp[t].x * a.cstride + c);
+                }
 #pragma unroll
                 for (int t = 9; t < MAX_TAPS; ++t)
                     if (t < n) {
                         const float w = __uint_as_float(tp[t].y);
-                        acc.x = fmaf(w, v[t].x, acc.x); acc.y = fmaf(w, v[t].y, acc.y);
-                        acc.z = fmaf(w, v[t].z, acc.z); acc.w = fmaf(w, v[t].w, acc.w);
+                        acc.x = fmaf(w, u[t - 9].x, acc.x); acc.y = fmaf(w, u[t - 9].y, acc.y);
+                        acc.z = fmaf(w, u[t - 9].z, acc.z); acc.w = fmaf(w, u[t - 9].w, acc.w);
                     }
             }
             acc.x *= 0.25f; acc.y *= 0.25f; acc.z *= 0.25f; acc.w *= 0.25f;
