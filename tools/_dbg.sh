@@ -1,2 +1,2 @@
-timeout 300 python tools/bench_roi.py 2>&1 | tail -4
-timeout 900 python -m pytest tests/test_gpu_roi_mask.py tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -m gpu -x -q --no-header -p no:cacheprovider 2>&1 | tail -2
+( time python bench.py --steps 20 --warmup 5 > gpurun_out/r2z2_bench.json 2> gpurun_out/r2z2_bench.err ) 2>&1 | tail -4; cut -c1-200 gpurun_out/r2z2_bench.json
+( time python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2z2_ref.json 2> gpurun_out/r2z2_ref.err ) 2>&1 | tail -4; cut -c1-300 gpurun_out/r2z2_ref.json
