@@ -18,8 +18,9 @@
 //   * fp32 accumulators live in TMEM, double buffered (2*N columns) so the epilogue of tile i overlaps the
 //     MMAs of tile i+1; persistent CTAs, one per SM
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator,
-//     warps 4..7 = epilogue (TMEM -> registers -> per-channel affine/ReLU -> global), which also reduces the
-//     per-channel sum / sum-of-squares of the raw fp32 accumulators for train-mode BatchNorm.
+//     warps 4..11 = epilogue, two per TMEM lane quarter splitting the accumulator's column blocks (TMEM -> registers ->
+//     shared-memory transpose (common.cuh: epi_block) -> per-channel affine/ReLU -> whole-sector stores), which also reduces
+//     the per-channel sum / sum-of-squares of the raw fp32 accumulators for train-mode BatchNorm.
 #include <math.h>
 #include <stdlib.h>
 
