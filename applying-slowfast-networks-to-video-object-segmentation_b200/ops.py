@@ -209,8 +209,9 @@ def conv(x, w_packed, Cp, N, k, pad, To, y, *, umma, relu=False, scale=None, shi
     _timed_call("conv_umma" if umma else "conv_simt", flops, "sfvos_conv_umma" if umma else "sfvos_conv_simt", p)
 
 
-def wgrad(x, dy, k, pad, dw, *, umma, dy_strides=None):
-    """dw f32 [taps, x.C, dy.C] += x^T dy over all pixels (x shifted per tap)."""
+def wgrad(x, dy, k, pad, dw, *, umma, dy_strides=None, flops=None):
+    """dw f32 [taps, x.C, dy.C] += x^T dy over all pixels (x shifted per tap).  ``flops``: algorithmic FLOPs of the launch when
+    they are not 2 * pixels(dy) * x.C * dy.C * taps (the operand-swapped lateral weight gradient)."""
     p = WgradParams()
     p.x = x.ptr(); p.B, p.T, p.H, p.W, p.C, p.x_cstride = x.B, x.T, x.H, x.W, x.C, x.cstride
     p.x_bstride = x.bstride
@@ -226,7 +227,8 @@ def wgrad(x, dy, k, pad, dw, *, umma, dy_strides=None):
         if nbytes:
             ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dw.device)
             p.workspace, p.workspace_bytes = _p(ws), nbytes
-    flops = 2.0 * x.B * dy.T * x.H * x.W * dy.C * x.C * k[0] * k[1] * k[2]
+    if flops is None:
+        flops = 2.0 * x.B * dy.T * x.H * x.W * dy.C * x.C * k[0] * k[1] * k[2]
     _timed_call("wgrad_umma" if umma else "wgrad_simt", flops, "sfvos_wgrad_umma" if umma else "sfvos_wgrad_simt", p)
 
 

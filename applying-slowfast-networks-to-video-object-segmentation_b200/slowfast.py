@@ -506,10 +506,11 @@ def _level_forward(mod, slow_in, fast_in, training, saved, scratch=None, fast_st
 
 class _GradSlot:
     """One set of gradient accumulators: parameter-gradient views + packed weight-gradient accumulators."""
-    __slots__ = ("grads", "dwp", "deterministic")
+    __slots__ = ("grads", "dwp", "deterministic", "swapped")
 
     def __init__(self, deterministic):
         self.grads, self.dwp, self.deterministic = {}, {}, deterministic
+        self.swapped = set()          # convs whose dwp accumulator holds the operand-swapped layout (see _layer_backward)
 
 
 class _GradBank:
@@ -565,7 +566,13 @@ class _GradBank:
             ops.axpby(self.scratch.buf[i * self.per_slot:(i + 1) * self.per_slot], first, 1.0, 1.0)
         grads = self.slots[0].grads
         for name, dwp in self.slots[0].dwp.items():
-            ops.unpack_wgrad(dwp, grads[name + ".weight"], 0)
+            if name in self.slots[0].swapped:
+                # operand-swapped lateral weight gradient: dwp = [kt][Cout][Cin] with the taps reversed (_layer_backward)
+                g = grads[name + ".weight"]
+                cout, cin, kt = g.shape[0], g.shape[1], g.shape[2]
+                g.add_(dwp.view(kt, cout, cin).flip(0).permute(1, 2, 0).reshape(g.shape))
+            else:
+                ops.unpack_wgrad(dwp, grads[name + ".weight"], 0)
         return grads
 
 
@@ -586,7 +593,19 @@ def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=Fal
                dbias=slot.grads.get(spec.conv + ".bias") if fixed_stats else None)
     pad = (0, spec.pad, spec.pad)
     if conv.weight.requires_grad:
-        ops.wgrad(x_in, dconv, spec.k, pad, slot.dwp[spec.conv], umma=umma)
+        if (umma and not slot.deterministic and spec.khw == 1 and spec.cin == 32 and spec.cout % 64 == 0 and spec.cout <= 128
+                and os.environ.get("SFVOS_LATERAL_WGRAD_SWAP", "1") != "0"):
+            # Lateral connection (32 -> 64 channels, k_t x 1 x 1): as dw[ta][c][n] = sum_t x[t+ta][c] dy[t][n] it is k_t GEMMs
+            # of 32 x 64 that each re-read dy and leave 3/4 of the MMA rows empty.  With the operands SWAPPED - "x" := dy,
+            # "dy" := x, temporal padding k_t - 1 - the same sum is dw'[k_t-1-ta][n][c] = sum_t' dy[t'-ta][n] x[t'][c], a problem
+            # with 32 output channels: the stacked weight-gradient kernel (wgrad_stack) fetches the dy tile once and
+            # multiplies it by all k_t input frames stacked along N (one 128 x 32 k_t x 16 MMA per K step; every byte of x and
+            # dy read once).  The accumulator keeps the swapped layout; _GradBank.finish un-swaps it.
+            ops.wgrad(dconv, x_in, spec.k, (spec.kt - 1, 0, 0), slot.dwp[spec.conv], umma=True,
+                      flops=2.0 * dconv.npix * spec.cin * spec.cout * spec.kt)
+            slot.swapped.add(spec.conv)
+        else:
+            ops.wgrad(x_in, dconv, spec.k, pad, slot.dwp[spec.conv], umma=umma)
     if not need_dx:
         return None
     wd, cpd = mod._packed(spec.conv, 1)

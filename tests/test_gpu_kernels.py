@@ -272,3 +272,27 @@ def test_relu_bwd_and_bias_grad():
     ref = dy * (y.float() > 0)
     assert _err(_read_act(dx), ref) < 5e-3
     assert _err(db, ref.reshape(-1, C).sum(0)) < 1e-5
+
+@pytest.mark.parametrize("kt,T", [(6, 6), (4, 4), (3, 5), (12, 12)])
+def test_lateral_wgrad_with_swapped_operands(kt, T):
+    """The lateral connection's weight gradient (32 -> 64 channels, k_t x 1 x 1) is computed with the operands swapped so that it
+    runs on the stacked 32-output-channel kernel: wgrad("x" := dy, "dy" := x, pad_t = k_t - 1) = dw'[k_t-1-ta][n][c]
+    (slowfast._layer_backward / _GradBank.finish).  Against torch's conv3d weight gradient and the direct launch."""
+    ops = _ops()
+    B, H, W, cin, cout = 2, 12, 21, 32, 64
+    To = T - kt + 1
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, T, H, W, cin, generator=g).to(DEV).bfloat16().float()
+    dy = torch.randn(B, To, H, W, cout, generator=g).to(DEV).bfloat16().float()
+    w = torch.zeros(cout, cin, kt, 1, 1, device=DEV, requires_grad=True)
+    (dw_ref,) = torch.autograd.grad(F.conv3d(x.permute(0, 4, 1, 2, 3), w), w, dy.permute(0, 4, 1, 2, 3))
+    xa, dya = _mk_act(ops, x, torch.bfloat16), _mk_act(ops, dy, torch.bfloat16)
+    direct = torch.zeros(kt * cin * cout, device=DEV)
+    ops.wgrad(xa, dya, (kt, 1, 1), (0, 0, 0), direct, umma=True)
+    g_direct = torch.zeros(dw_ref.shape, device=DEV)
+    ops.unpack_wgrad(direct, g_direct, 0)
+    swapped = torch.zeros(kt * cin * cout, device=DEV)
+    ops.wgrad(dya, xa, (kt, 1, 1), (kt - 1, 0, 0), swapped, umma=True)
+    g_swapped = swapped.view(kt, cout, cin).flip(0).permute(1, 2, 0).reshape(dw_ref.shape)
+    assert _err(g_direct, dw_ref) < 5e-5
+    assert _err(g_swapped, dw_ref) < 5e-5
