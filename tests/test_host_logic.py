@@ -95,3 +95,28 @@ def test_dgrad_flops_exclude_zero_padded_temporal_taps():
     assert abs(fwd / 1e9 - 1369.8) < 1.0 and abs(bwd / 1e9 - 114.2) < 0.2     # = the layer's forward GFLOP
     import inspect
     assert "min(To, x.T)" in inspect.getsource(ops.conv)
+
+
+@pytest.mark.parametrize("kt,T", [(6, 6), (4, 4), (3, 5)])
+def test_swapped_lateral_weight_gradient_identity(kt, T):
+    """Host-side algebra of slowfast._layer_backward / _GradBank.finish for the lateral connections (code/helpers/model.py:83-90,
+    invoked :128-131,140-143): the weight gradient of the valid temporal convolution y = conv3d(x, W), W [Cout,Cin,kt,1,1], equals
+    the weight-gradient problem with the operands swapped ("x" := dy, "dy" := x, temporal padding kt - 1), un-swapped with
+    flip(taps) + transpose(channels).  Here the swapped problem is evaluated with plain torch on the CPU, in the layout the kernel
+    accumulates: dw'[ta'][c' = Cout][n' = Cin] = sum_{b,t',px} dy[b, t' + ta' - (kt-1), px, c'] * x[b, t', px, n']."""
+    import torch.nn.functional as F
+    B, H, W, cin, cout = 2, 3, 4, 8, 16
+    To = T - kt + 1
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, T, H, W, generator=g, dtype=torch.float64)
+    dy = torch.randn(B, cout, To, H, W, generator=g, dtype=torch.float64)
+    w = torch.zeros(cout, cin, kt, 1, 1, dtype=torch.float64, requires_grad=True)
+    (dw_ref,) = torch.autograd.grad(F.conv3d(x, w), w, dy)
+    dwp = torch.zeros(kt, cout, cin, dtype=torch.float64)
+    for tap in range(kt):
+        for t in range(T):                       # t' runs over the frames of the swapped problem's "dy" (= x)
+            src = t + tap - (kt - 1)             # frame of the swapped problem's "x" (= dy); out of range = zero padding
+            if 0 <= src < To:
+                dwp[tap] += torch.einsum("bchw,bnhw->cn", dy[:, :, src], x[:, :, t])
+    unswapped = dwp.flip(0).permute(1, 2, 0).reshape(dw_ref.shape)      # exactly _GradBank.finish's expression
+    assert torch.allclose(unswapped, dw_ref, rtol=1e-12, atol=1e-12)
