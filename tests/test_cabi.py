@@ -35,16 +35,18 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_c_layout(tmp_path):
     from sfvos_b200 import _lib
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sfvos.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sfvos.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(sfvos_conv_params), sizeof(sfvos_wgrad_params), sizeof(sfvos_roi_params),'
                     'offsetof(sfvos_conv_params, OH), offsetof(sfvos_wgrad_params, dw), offsetof(sfvos_roi_params, out),'
-                    'sizeof(sfvos_bn_running_params), offsetof(sfvos_bn_running_params, momentum));return 0;}\n')
+                    'sizeof(sfvos_bn_running_params), offsetof(sfvos_bn_running_params, momentum),'
+                    'offsetof(sfvos_conv_params, addend), offsetof(sfvos_conv_params, addend_cstride));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.ConvParams), ctypes.sizeof(_lib.WgradParams), ctypes.sizeof(_lib.RoiParams),
             _lib.ConvParams.OH.offset, _lib.WgradParams.dw.offset, _lib.RoiParams.out.offset,
-            ctypes.sizeof(_lib.BnRunningParams), _lib.BnRunningParams.momentum.offset]
+            ctypes.sizeof(_lib.BnRunningParams), _lib.BnRunningParams.momentum.offset,
+            _lib.ConvParams.addend.offset, _lib.ConvParams.addend_cstride.offset]
     assert got == want
 
 
