@@ -605,6 +605,7 @@ def _layer_backward(mod, spec, dy, x_in, saved, bank, dx=None, dx_accumulate=Fal
                       flops=2.0 * dconv.npix * spec.cin * spec.cout * spec.kt)
             slot.swapped.add(spec.conv)
         else:
+            slot.swapped.discard(spec.conv)
             ops.wgrad(x_in, dconv, spec.k, pad, slot.dwp[spec.conv], umma=umma)
     if not need_dx:
         return None
